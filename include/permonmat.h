@@ -1,0 +1,3 @@
+/* permonmat.h -- compatibility name: reference code that includes <permonmat.h> gets the B200 C ABI. */
+#pragma once
+#include "permon_b200.h"

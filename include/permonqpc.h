@@ -1,0 +1,3 @@
+/* permonqpc.h -- compatibility name: reference code that includes <permonqpc.h> gets the B200 C ABI. */
+#pragma once
+#include "permon_b200.h"

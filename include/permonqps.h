@@ -1,0 +1,3 @@
+/* permonqps.h -- compatibility name: reference code that includes <permonqps.h> gets the B200 C ABI. */
+#pragma once
+#include "permon_b200.h"

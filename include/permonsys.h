@@ -1,0 +1,3 @@
+/* permonsys.h -- compatibility name: reference code that includes <permonsys.h> gets the B200 C ABI. */
+#pragma once
+#include "permon_b200.h"

@@ -1,0 +1,3 @@
+/* permonvec.h -- compatibility name: reference code that includes <permonvec.h> gets the B200 C ABI. */
+#pragma once
+#include "permon_b200.h"

@@ -1,0 +1,133 @@
+// device.h -- internal C++ interface between the host-side PERMON objects and the CUDA kernels.
+// Nothing here is exported; the C ABI lives in include/permon_b200.h.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "mpgp_ctl.h"
+
+namespace pb {
+
+// ---- device context -----------------------------------------------------------------------------
+struct DevCtx {
+  int          device      = -1;
+  int          sm_count    = 0;
+  bool         ready       = false;
+  cudaStream_t stream      = nullptr;   // compute stream (library-owned or caller-provided)
+  cudaStream_t own_stream  = nullptr;
+  cudaStream_t comm_stream = nullptr;   // NCCL halo traffic, overlapped with interior rows
+  int64_t      launches    = 0;         // kernels launched by this library (bench.py: gpu_launches)
+};
+DevCtx &ctx();
+int     dev_init();                      // 0 on success, PETSC_ERR_GPU otherwise
+void    set_error(const char *fmt, ...);
+const char *last_error();
+int     cuda_fail(cudaError_t e, const char *what, const char *file, int line);
+#define PB_CUDA(call)                                                  \
+  do {                                                                 \
+    cudaError_t e_ = (call);                                           \
+    if (e_ != cudaSuccess) return pb::cuda_fail(e_, #call, __FILE__, __LINE__); \
+  } while (0)
+#define PB_CHK(call)            \
+  do {                          \
+    int ierr_ = (call);         \
+    if (ierr_) return ierr_;    \
+  } while (0)
+
+// ---- profiling (bench.py roofline) -----------------------------------------------------------------
+enum KFamily { KF_SPMV_A = 0, KF_UPDATE_B, KF_SPMV_A2, KF_DIR_C, KF_CTRL, KF_SPMV_PLAIN, KF_VEC, KF_QPC, KF_HALO, KF_COUNT };
+const char *family_name(int f);
+void        prof_begin();
+int         prof_end();
+int         prof_get(int family, int64_t *launches, double *ms, double *bytes_per_launch);
+void        prof_pre(int family, double bytes);
+void        prof_post(int family);
+
+// ---- device CSR ------------------------------------------------------------------------------------
+struct CsrDev {
+  int           n      = 0;        // rows
+  int           ncols  = 0;
+  int64_t       nnz    = 0;
+  const int    *ia     = nullptr;  // [n+1]
+  const int    *ja     = nullptr;  // [nnz] local column ids
+  const double *a      = nullptr;  // [nnz]
+  const int    *rows   = nullptr;  // optional compressed row list (off-diagonal block): row id of each stored row
+  int           kind   = 0;        // 0: tile-streamed (short rows), 1: vector (W lanes per row)
+  int           W      = 32;
+  int           tile_cap = 0;      // max nnz of a 256-row tile (stream kind)
+  int           grid   = 0;        // persistent grid size (fixed => reproducible reductions)
+};
+
+struct BoxDev {
+  const double *lb = nullptr, *ub = nullptr;   // full local length; NULL = absent
+  double        astol = 0.0;
+};
+
+struct RedBuf {
+  double   *partials = nullptr;   // [maxblocks][PB_NRED]
+  unsigned *counter  = nullptr;
+  double   *out      = nullptr;   // where the last block stores the record (PB_NRED doubles)
+};
+
+// ---- kernels: generic vector ops (deterministic) -----------------------------------------------------
+int k_set(int n, double *x, double a);
+int k_copy(int n, const double *x, double *y);
+int k_scale(int n, double *x, double a);
+int k_axpy(int n, double *y, double a, const double *x);
+int k_aypx(int n, double *y, double a, const double *x);
+int k_waxpy(int n, double *w, double a, const double *x, const double *y);
+int k_pmax(int n, double *w, const double *x, const double *y);
+int k_pmin(int n, double *w, const double *x, const double *y);
+int k_dot(int n, const double *x, const double *y, RedBuf rb);          // rb.out[0] = local x.y
+int k_mdot2(int n, const double *x, const double *y0, const double *y1, RedBuf rb);   // out[0]=x.y0, out[1]=x.y1
+int k_dense_rows_mult(int n, int m, const double *B, const double *x, RedBuf rb);     // out[j] = B_j . x
+int k_dense_rows_multT_add(int n, int m, const double *B, const double *t /*device, m*/, double scale, double *y, int accumulate);
+int k_scatter_is(int nis, const int *is, const double *sub, double fill, int n, double *full);  // full = fill; full[is]=sub
+
+// QPC box (generic path and the public QPC* API)
+int k_qpc_project(int n, const double *x, BoxDev bx, double *Px);
+int k_qpc_grads(int n, const double *x, const double *g, BoxDev bx, double *gf, double *gc);
+int k_qpc_gradreduced(int n, const double *x, const double *gf, double alpha, BoxDev bx, double *gr);
+int k_qpc_feas(int n, const double *x, const double *d, BoxDev bx, RedBuf rb);        // out[RA_FEAS] = local min
+int k_box_mult(int n, const double *r, int has_lb, int has_ub, double *llb, double *lub);
+int k_kkt_box(int n, const double *x, const double *bound, const double *lam, int upper, RedBuf rb);
+
+// SpMV
+int k_spmv(const CsrDev &A, const double *x, double *y, int accumulate);   // y (+)= A x ; honours A.rows
+
+// ---- fused MPGP kernels -------------------------------------------------------------------------------
+struct MpgpVecs {
+  int     n = 0;
+  double *x = nullptr, *g = nullptr, *p = nullptr, *Ap = nullptr, *gf = nullptr;
+  const double *b = nullptr;
+  BoxDev  bx;
+  const double *B = nullptr;     // [m][n] dense equality rows (local columns), or NULL
+  int     m = 0;
+  double *t = nullptr;           // inner-dimension work vector for product operators
+};
+// K_A  : Ap = A xin (xin = p, or t for product operators) + [p.Ap, g.p, B p, alpha_f]
+int k_fused_A(const CsrDev &A, const double *xin, const MpgpVecs &v, const MpgpCtl *S, RedBuf rb, const unsigned char *skip_epilogue);
+// K_A' : g = A xin - b (+rho B^T Bu), split, p = gf, [|gP|^2, |gc|^2, |gf|^2]; runs when step=='e' or init
+int k_fused_A2(const CsrDev &A, const double *xin, const MpgpVecs &v, const MpgpCtl *S, RedBuf rb, const unsigned char *skip_epilogue);
+// off-diagonal (ghost) contribution + deferred epilogue for boundary rows (multi-GPU)
+int k_fused_A_ghost(const CsrDev &Ao, const double *ghost, const MpgpVecs &v, const MpgpCtl *S, RedBuf rb, int second);
+// K_B  : the c / p / e update of x, g (+ split, reductions)
+int k_fused_B(const MpgpVecs &v, const MpgpCtl *S, RedBuf rb);
+// K_C  : direction update p = gf - bcg p | p = gc | nothing
+int k_fused_C(const MpgpVecs &v, const MpgpCtl *S);
+// initial projection x = P(x) (+ B u)
+int k_fused_project(const MpgpVecs &v, const MpgpCtl *S, RedBuf rb);
+// plain product-operator first factor, device-driven: t = M2 xin when the phase is active
+int k_spmv_gated(const CsrDev &A, const double *x, double *y, const MpgpCtl *S, int phase /*0: K_A, 1: K_A'*/);
+// one-thread control kernels
+int k_ctrl_A(MpgpCtl *S, const double *ra);
+int k_ctrl_E(MpgpCtl *S, const double *rb);
+int k_ctrl_B(MpgpCtl *S, const double *rb);
+// halo pack: buf[k] = x[idx[k]]
+int k_pack(int n, const int *idx, const double *x, double *buf);
+
+int  spmv_config(CsrDev &A, const int *h_ia);   // picks kind / W / grid from the host row pointer
+int  elementwise_grid();
+int  max_red_blocks();
+
+}  // namespace pb

@@ -1,0 +1,992 @@
+// kernels.cu -- hand-written CUDA kernels (sm_100a) of the MPGP / SMALXE hot path.
+//
+// Kernel families (DESIGN.md gives the byte counts and the roofline of each):
+//   K_A   fused SpMV            Ap = A p  with epilogue  p.Ap, g.p, B p, alpha_f = max feasible step
+//   K_B   fused update          x -= a p, g -= a Ap, QPCGrads split, reduced gradient / expansion half step,
+//                               |gP|^2 |gc|^2 |gf|^2 Ap.gf B u
+//   K_A'  fused SpMV            g = A x - b with epilogue split, p = gf and the three norms (expansion, init)
+//   K_C   direction update      p = gf - beta p  |  p = gc
+//   ctrl  one-thread kernels    step selection and stopping tests on device scalars (mpgp_ctl.h)
+// plus the un-fused vector / QPC kernels used by set-up, post-solve, the option variants that are not on
+// the headline path, and the public QPC*/Vec*/Mat* entry points.
+//
+// All reductions are deterministic: fixed per-thread order, fixed shuffle tree, one record per CTA, and the
+// last CTA to finish adds the CTA records in index order (threadfence reduction).  Grids are persistent and
+// sized from the SM count once per matrix, so results are reproducible run to run.
+//
+// Reference semantics restated by the fused epilogues (file:line into permon/permon):
+//   QPCGrads_Box        src/qpc/impls/box/qpcbox.c:41-55      QPCGradReduced_Box  :86-92
+//   QPCFeas_Box         src/qpc/impls/box/qpcbox.c:125-137    QPCProject_Box      :298-303
+//   MPGP step formulas  src/qps/impls/mpgp/mpgp.c:299-323 (expansion), :553-560 (CG), :623-638 (proportioning)
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "device.h"
+
+namespace pb {
+
+// =====================================================================================================
+// context, errors, profiling
+// =====================================================================================================
+static DevCtx      g_ctx;
+static std::string g_err;
+DevCtx            &ctx() { return g_ctx; }
+const char        *last_error() { return g_err.c_str(); }
+
+void set_error(const char *fmt, ...)
+{
+  char    buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  if (getenv("PERMON_B200_VERBOSE")) fprintf(stderr, "[permon_b200] %s\n", buf);
+}
+
+int cuda_fail(cudaError_t e, const char *what, const char *file, int line)
+{
+  set_error("CUDA error %d (%s) in %s at %s:%d", (int)e, cudaGetErrorString(e), what, file, line);
+  return 97; /* PETSC_ERR_GPU */
+}
+
+int dev_init()
+{
+  DevCtx &c = g_ctx;
+  if (c.ready) return 0;
+  int         count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count <= 0) {
+    set_error("no usable CUDA device (%s): permon_b200 has no CPU execution path", e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+    return 97;
+  }
+  if (c.device < 0) {
+    const char *lr = getenv("LOCAL_RANK");
+    c.device = lr ? atoi(lr) % count : 0;
+  }
+  PB_CUDA(cudaSetDevice(c.device));
+  cudaDeviceProp prop;
+  PB_CUDA(cudaGetDeviceProperties(&prop, c.device));
+  c.sm_count = prop.multiProcessorCount;
+  if (prop.major < 10) {
+    set_error("device %d is sm_%d%d; this library is built for sm_100a (B200) only", c.device, prop.major, prop.minor);
+    return 97;
+  }
+  PB_CUDA(cudaStreamCreateWithFlags(&c.own_stream, cudaStreamNonBlocking));
+  PB_CUDA(cudaStreamCreateWithFlags(&c.comm_stream, cudaStreamNonBlocking));
+  if (!c.stream) c.stream = c.own_stream;
+  c.ready = true;
+  return 0;
+}
+
+static const char *g_family_names[KF_COUNT] = {"K_A spmv+dots+feas", "K_B update+split", "K_A' spmv+grad+split", "K_C direction", "ctrl", "spmv plain", "vec", "qpc", "halo"};
+const char        *family_name(int f) { return (f >= 0 && f < KF_COUNT) ? g_family_names[f] : "?"; }
+
+struct ProfRec {
+  int         fam;
+  double      bytes;
+  cudaEvent_t a, b;
+};
+static bool                 g_prof_on = false;
+static std::vector<ProfRec> g_prof;
+static size_t               g_prof_used = 0;
+static double               g_prof_ms[KF_COUNT], g_prof_bytes[KF_COUNT];
+static int64_t              g_prof_n[KF_COUNT];
+
+void prof_begin()
+{
+  g_prof_on   = true;
+  g_prof_used = 0;
+}
+void prof_pre(int family, double bytes)
+{
+  g_ctx.launches++;
+  if (!g_prof_on) return;
+  if (g_prof_used == g_prof.size()) {
+    if (g_prof.size() >= 200000) return;
+    ProfRec r;
+    cudaEventCreate(&r.a);
+    cudaEventCreate(&r.b);
+    g_prof.push_back(r);
+  }
+  ProfRec &r = g_prof[g_prof_used];
+  r.fam   = family;
+  r.bytes = bytes;
+  cudaEventRecord(r.a, g_ctx.stream);
+}
+void prof_post(int family)
+{
+  (void)family;
+  if (!g_prof_on) return;
+  if (g_prof_used >= g_prof.size()) return;
+  cudaEventRecord(g_prof[g_prof_used].b, g_ctx.stream);
+  g_prof_used++;
+}
+int prof_end()
+{
+  g_prof_on = false;
+  cudaStreamSynchronize(g_ctx.stream);
+  for (int f = 0; f < KF_COUNT; f++) g_prof_ms[f] = g_prof_bytes[f] = 0.0, g_prof_n[f] = 0;
+  for (size_t i = 0; i < g_prof_used; i++) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, g_prof[i].a, g_prof[i].b);
+    g_prof_ms[g_prof[i].fam] += ms;
+    g_prof_bytes[g_prof[i].fam] += g_prof[i].bytes;
+    g_prof_n[g_prof[i].fam]++;
+  }
+  return KF_COUNT;
+}
+int prof_get(int f, int64_t *launches, double *ms, double *bytes_per_launch)
+{
+  if (f < 0 || f >= KF_COUNT) return 63;
+  *launches         = g_prof_n[f];
+  *ms               = g_prof_ms[f];
+  *bytes_per_launch = g_prof_n[f] ? g_prof_bytes[f] / (double)g_prof_n[f] : 0.0;
+  return 0;
+}
+
+#define LAUNCH_CHECK()                                                           \
+  do {                                                                           \
+    cudaError_t e_ = cudaGetLastError();                                         \
+    if (e_ != cudaSuccess) return cuda_fail(e_, "kernel launch", __FILE__, __LINE__); \
+  } while (0)
+
+static constexpr int NT = 256;   // threads per CTA everywhere
+static constexpr int TR = 256;   // rows per SpMV tile (stream kind)
+
+int elementwise_grid() { return g_ctx.sm_count * 8; }
+int max_red_blocks() { return g_ctx.sm_count * 16; }
+
+// =====================================================================================================
+// deterministic grid reduction of an 8-double record (slots in MINMASK are min-reduced, others summed)
+// =====================================================================================================
+template <int MINMASK>
+__device__ __forceinline__ double red_op(int k, double a, double b)
+{
+  if ((MINMASK >> k) & 1) return (b < a) ? b : a;
+  return a + b;
+}
+template <int MINMASK>
+__device__ __forceinline__ double red_identity(int k)
+{
+  return ((MINMASK >> k) & 1) ? HUGE_VAL : 0.0;
+}
+
+template <int MINMASK>
+__device__ __forceinline__ void block_reduce8(double (&v)[PB_NRED], double (*sm)[32])
+{
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+#pragma unroll
+  for (int k = 0; k < PB_NRED; k++) {
+    double t = v[k];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) t = red_op<MINMASK>(k, t, __shfl_xor_sync(0xffffffffu, t, o));
+    if (lane == 0) sm[k][warp] = t;
+  }
+  __syncthreads();
+  if (warp == 0) {
+#pragma unroll
+    for (int k = 0; k < PB_NRED; k++) {
+      double t = (lane < nw) ? sm[k][lane] : red_identity<MINMASK>(k);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) t = red_op<MINMASK>(k, t, __shfl_xor_sync(0xffffffffu, t, o));
+      v[k] = t;   // valid in lane 0 of warp 0 (== thread 0)
+    }
+  }
+  __syncthreads();
+}
+
+// every thread of every CTA of the grid must call this exactly once
+template <int MINMASK>
+__device__ void grid_reduce8(double (&v)[PB_NRED], RedBuf rb, const double *prev)
+{
+  __shared__ double sm[PB_NRED][32];
+  __shared__ int    s_last;
+  block_reduce8<MINMASK>(v, sm);
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int k = 0; k < PB_NRED; k++) rb.partials[(size_t)blockIdx.x * PB_NRED + k] = v[k];
+    __threadfence();
+    unsigned t = atomicAdd(rb.counter, 1u);
+    s_last     = (t == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (s_last) {
+    __threadfence();
+    double w[PB_NRED];
+#pragma unroll
+    for (int k = 0; k < PB_NRED; k++) {
+      double t = red_identity<MINMASK>(k);
+      for (int b = threadIdx.x; b < (int)gridDim.x; b += blockDim.x) t = red_op<MINMASK>(k, t, __ldcg(&rb.partials[(size_t)b * PB_NRED + k]));
+      w[k] = t;
+    }
+    block_reduce8<MINMASK>(w, sm);
+    if (threadIdx.x == 0) {
+#pragma unroll
+      for (int k = 0; k < PB_NRED; k++) rb.out[k] = prev ? red_op<MINMASK>(k, prev[k], w[k]) : w[k];
+      *rb.counter = 0u;
+    }
+  }
+}
+
+// =====================================================================================================
+// box helpers (QPC box semantics)
+// =====================================================================================================
+struct BoxVal {
+  double lb, ub;
+  bool   has_lb, has_ub;
+};
+__device__ __forceinline__ BoxVal load_box(const BoxDev &bx, int r)
+{
+  BoxVal b;
+  b.has_lb = bx.lb != nullptr;
+  b.has_ub = bx.ub != nullptr;
+  b.lb     = b.has_lb ? bx.lb[r] : 0.0;
+  b.ub     = b.has_ub ? bx.ub[r] : 0.0;
+  return b;
+}
+// QPCGrads (qpc.c:552-553 prefill + qpcbox.c:41-55)
+__device__ __forceinline__ void box_split(double x, double g, const BoxVal &b, double astol, double &gf, double &gc)
+{
+  gf = g;
+  gc = 0.0;
+  if (b.has_lb && fabs(x - b.lb) <= astol) {
+    gf = 0.0;
+    gc = (g < 0.0) ? g : 0.0;
+  } else if (b.has_ub && fabs(x - b.ub) <= astol) {
+    gf = 0.0;
+    gc = (g < 0.0) ? 0.0 : g;   // PetscMax(g,0)
+  }
+}
+// QPCGradReduced (qpc.c:601 prefill + qpcbox.c:86-92)
+__device__ __forceinline__ double box_reduced(double x, double gf, const BoxVal &b, double alpha)
+{
+  double gr = gf;
+  if (b.has_lb && gf > 0.0) {
+    double t = (x - b.lb) / alpha;
+    gr       = (gf < t) ? gf : t;
+  } else if (b.has_ub && gf < 0.0) {
+    double t = (x - b.ub) / alpha;
+    gr       = (gf < t) ? t : gf;
+  }
+  return gr;
+}
+// QPCFeas_Box (qpcbox.c:125-137)
+__device__ __forceinline__ double box_feas(double x, double d, const BoxVal &b, double cur)
+{
+  const double PINF = 1.7976931348623157e+308 / 4.0;
+  if (d > 0. && b.has_lb && b.lb > -PINF) {
+    double a = (x - b.lb) / d;
+    if (a < cur) cur = a;
+  }
+  if (d < 0. && b.has_ub && b.ub < PINF) {
+    double a = (x - b.ub) / d;
+    if (a < cur) cur = a;
+  }
+  return cur;
+}
+// QPCProject_Box (qpcbox.c:298-303)
+__device__ __forceinline__ double box_project(double x, const BoxVal &b)
+{
+  if (b.has_lb) {
+    x = (x < b.lb) ? b.lb : x;
+    if (b.has_ub) x = (x < b.ub) ? x : b.ub;
+  } else if (b.has_ub) {
+    x = (x < b.ub) ? x : b.ub;
+  }
+  return x;
+}
+
+// =====================================================================================================
+// SpMV skeletons.  Epi supplies: active(), row(r, ax, acc), finalize(acc).
+// =====================================================================================================
+
+// tile-streamed CSR ("CSR-stream"): the CTA reads the nnz range of a 256-row tile with unit-stride loads,
+// multiplies with the gathered x on the fly and parks the products in shared memory; then one thread per
+// row adds its segment in storage order (== the reference's running sum) and runs the fused epilogue.
+template <class Epi>
+__global__ void __launch_bounds__(NT) k_spmv_stream(CsrDev A, const double *__restrict__ x, Epi epi)
+{
+  if (!epi.active()) return;
+  extern __shared__ double s_prod[];
+  typename Epi::Acc acc;
+  epi.init(acc);
+  const int ntiles = (A.n + TR - 1) / TR;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int r0 = tile * TR;
+    const int r1 = min(r0 + TR, A.n);
+    const int k0 = __ldg(A.ia + r0), k1 = __ldg(A.ia + r1);
+    for (int k = k0 + threadIdx.x; k < k1; k += NT) s_prod[k - k0] = __ldg(A.a + k) * __ldg(x + __ldg(A.ja + k));
+    __syncthreads();
+    const int r = r0 + threadIdx.x;
+    if (r < r1) {
+      const int ks = __ldg(A.ia + r) - k0, ke = __ldg(A.ia + r + 1) - k0;
+      double    s  = 0.0;
+      for (int k = ks; k < ke; k++) s += s_prod[k];
+      epi.row(A.rows ? __ldg(A.rows + r) : r, s, acc);
+    }
+    __syncthreads();
+  }
+  epi.finalize(acc);
+}
+
+// vector CSR: W lanes per row, unit-stride loads along the row, shuffle tree, lane 0 runs the epilogue
+template <class Epi, int W>
+__global__ void __launch_bounds__(NT) k_spmv_vector(CsrDev A, const double *__restrict__ x, Epi epi)
+{
+  if (!epi.active()) return;
+  typename Epi::Acc acc;
+  epi.init(acc);
+  const int lane    = threadIdx.x & (W - 1);
+  const int gid     = (blockIdx.x * NT + threadIdx.x) / W;
+  const int ngroups = gridDim.x * (NT / W);
+  const int gpw     = 32 / W;                                    // groups per warp
+  const int wfirst  = (gid / gpw) * gpw;                         // first group of my warp
+  for (int base = wfirst; base < A.n; base += ngroups) {         // uniform trip count inside a warp
+    const int r = base + (gid - wfirst);
+    double    s = 0.0;
+    if (r < A.n) {
+      const int ks = __ldg(A.ia + r), ke = __ldg(A.ia + r + 1);
+      for (int k = ks + lane; k < ke; k += W) s += __ldg(A.a + k) * __ldg(x + __ldg(A.ja + k));
+    }
+#pragma unroll
+    for (int o = W / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0 && r < A.n) epi.row(A.rows ? __ldg(A.rows + r) : r, s, acc);
+  }
+  epi.finalize(acc);
+}
+
+template <class K>
+static int occ_blocks(K kernel, size_t smem)
+{
+  int nb = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernel, NT, smem) != cudaSuccess || nb < 1) nb = 1;
+  return nb;
+}
+
+template <class Epi, int W>
+static void launch_vector(const CsrDev &A, const double *x, const Epi &epi)
+{
+  static int occ = 0;
+  if (!occ) occ = occ_blocks(k_spmv_vector<Epi, W>, 0);
+  int64_t need = ((int64_t)A.n * W + NT - 1) / NT;
+  int64_t grid = (int64_t)g_ctx.sm_count * occ;
+  if (grid > need) grid = need;
+  if (grid > max_red_blocks()) grid = max_red_blocks();
+  if (grid < 1) grid = 1;
+  k_spmv_vector<Epi, W><<<(int)grid, NT, 0, g_ctx.stream>>>(A, x, epi);
+}
+
+template <class Epi>
+static int launch_spmv(const CsrDev &A, const double *x, const Epi &epi, int family, double bytes)
+{
+  prof_pre(family, bytes);
+  if (A.n == 0) {
+    // still run one CTA so that reductions publish their (identity) record
+    k_spmv_vector<Epi, 32><<<1, NT, 0, g_ctx.stream>>>(A, x, epi);
+  } else if (A.kind == 0) {
+    static int    occ = 0;
+    static size_t occ_smem = (size_t)-1;
+    size_t        smem = (size_t)A.tile_cap * sizeof(double);
+    if (!occ || occ_smem != smem) {
+      occ      = occ_blocks(k_spmv_stream<Epi>, smem);
+      occ_smem = smem;
+    }
+    int ntiles = (A.n + TR - 1) / TR;
+    int grid   = g_ctx.sm_count * occ;
+    if (grid > ntiles) grid = ntiles;
+    if (grid > max_red_blocks()) grid = max_red_blocks();
+    k_spmv_stream<Epi><<<grid, NT, smem, g_ctx.stream>>>(A, x, epi);
+  } else {
+    switch (A.W) {
+    case 2: launch_vector<Epi, 2>(A, x, epi); break;
+    case 4: launch_vector<Epi, 4>(A, x, epi); break;
+    case 8: launch_vector<Epi, 8>(A, x, epi); break;
+    case 16: launch_vector<Epi, 16>(A, x, epi); break;
+    default: launch_vector<Epi, 32>(A, x, epi); break;
+    }
+  }
+  prof_post(family);
+  LAUNCH_CHECK();
+  return 0;
+}
+
+// decide the kernel flavour from the row pointer (host copy)
+int spmv_config(CsrDev &A, const int *h_ia)
+{
+  const int n = A.n;
+  int       maxrow = 0, cap = 0;
+  for (int r0 = 0; r0 < n; r0 += TR) {
+    int r1 = (r0 + TR < n) ? r0 + TR : n;
+    int t  = h_ia[r1] - h_ia[r0];
+    if (t > cap) cap = t;
+  }
+  for (int r = 0; r < n; r++) {
+    int l = h_ia[r + 1] - h_ia[r];
+    if (l > maxrow) maxrow = l;
+  }
+  const double avg = n ? (double)A.nnz / n : 0.0;
+  const char  *force = getenv("PERMON_B200_SPMV");   // "stream" | "vector" (A/B measurements)
+  bool         stream = (cap <= 5632 && maxrow <= 64);   // <= 44 KB of products per tile
+  if (force && !strcmp(force, "vector")) stream = false;
+  if (stream) {
+    A.kind     = 0;
+    A.tile_cap = (cap + 31) & ~31;
+    if (A.tile_cap < 32) A.tile_cap = 32;
+  } else {
+    A.kind = 1;
+    int W  = 32;
+    if (avg <= 3) W = 2;
+    else if (avg <= 6) W = 4;
+    else if (avg <= 12) W = 8;
+    else if (avg <= 24) W = 16;
+    A.W = W;
+  }
+  return 0;
+}
+
+// ---- epilogues ---------------------------------------------------------------------------------------
+struct EpiPlain {
+  double *y;
+  int     accumulate;
+  struct Acc {};
+  __device__ bool active() const { return true; }
+  __device__ void init(Acc &) const {}
+  __device__ void row(int r, double ax, Acc &) const { y[r] = accumulate ? y[r] + ax : ax; }
+  __device__ void finalize(Acc &) const {}
+};
+
+struct EpiGated {   // plain SpMV that only runs in the right phase of the device-driven iteration
+  double        *y;
+  const MpgpCtl *S;
+  int            phase;
+  struct Acc {};
+  __device__ bool active() const
+  {
+    if (S->reason != 0) return false;
+    return phase == 0 ? true : (S->step == 'e' || S->init);
+  }
+  __device__ void init(Acc &) const {}
+  __device__ void row(int r, double ax, Acc &) const { y[r] = ax; }
+  __device__ void finalize(Acc &) const {}
+};
+
+struct AccRed {
+  double v[PB_NRED];
+};
+
+// K_A epilogue: Ap_r = (A p)_r ; p.Ap ; g.p ; B p ; max feasible step (QPCFeas)
+struct EpiA {
+  const double        *p, *g, *x;
+  double              *Ap;
+  BoxDev               bx;
+  const double        *B;
+  int                  m, n;
+  const MpgpCtl       *S;
+  RedBuf               rb;
+  const unsigned char *skip;    // rows whose epilogue is deferred to the ghost pass (multi-GPU)
+  typedef AccRed       Acc;
+  __device__ bool active() const { return S->reason == 0; }
+  __device__ void init(Acc &a) const
+  {
+#pragma unroll
+    for (int k = 0; k < PB_NRED; k++) a.v[k] = 0.0;
+    a.v[RA_FEAS] = HUGE_VAL;
+  }
+  __device__ void epilogue(int r, double ax, Acc &a) const
+  {
+    const double pr = p[r];
+    a.v[RA_PAP] += pr * ax;
+    a.v[RA_GP] += g[r] * pr;
+    for (int j = 0; j < m; j++) a.v[RA_BP + j] += B[(size_t)j * n + r] * pr;
+    a.v[RA_FEAS] = box_feas(x[r], pr, load_box(bx, r), a.v[RA_FEAS]);
+  }
+  __device__ void row(int r, double ax, Acc &a) const
+  {
+    Ap[r] = ax;
+    if (skip && skip[r]) return;
+    epilogue(r, ax, a);
+  }
+  __device__ void finalize(Acc &a) const { grid_reduce8<(1 << RA_FEAS)>(a.v, rb, nullptr); }
+};
+
+// K_A' epilogue: g_r = (A x)_r + rho (B^T Bu)_r - b_r ; split ; p = gf ; |gP|^2 |gc|^2 |gf|^2
+struct EpiA2 {
+  const double        *x, *b;
+  double              *g, *p;
+  BoxDev               bx;
+  const double        *B;
+  int                  m, n;
+  const MpgpCtl       *S;
+  RedBuf               rb;
+  const unsigned char *skip;
+  typedef AccRed       Acc;
+  __device__ bool active() const { return S->reason == 0 && (S->step == 'e' || S->init); }
+  __device__ void init(Acc &a) const
+  {
+#pragma unroll
+    for (int k = 0; k < PB_NRED; k++) a.v[k] = 0.0;
+  }
+  __device__ void epilogue(int r, double ax, Acc &a) const
+  {
+    double gr = ax;
+    if (m > 0) {
+      double t = 0.0;
+      for (int j = 0; j < m; j++) t += B[(size_t)j * n + r] * S->Bu[j];
+      gr += S->rho * t;
+    }
+    gr -= b[r];
+    double gf, gc;
+    box_split(x[r], gr, load_box(bx, r), bx.astol, gf, gc);
+    g[r] = gr;
+    p[r] = gf;
+    const double gP = gf + gc;
+    a.v[RB_GP2] += gP * gP;
+    a.v[RB_GC2] += gc * gc;
+    a.v[RB_GF2] += gf * gf;
+  }
+  __device__ void row(int r, double ax, Acc &a) const
+  {
+    if (skip && skip[r]) {
+      g[r] = ax;   // partial product parked in g until the ghost pass
+      return;
+    }
+    epilogue(r, ax, a);
+  }
+  __device__ void finalize(Acc &a) const { grid_reduce8<0>(a.v, rb, nullptr); }
+};
+
+// ghost pass (multi-GPU): add the off-diagonal block product to the parked partial result, then run the
+// deferred epilogue of K_A (SECOND = false) or K_A' (SECOND = true) for the boundary rows
+template <bool SECOND>
+struct EpiGhost {
+  EpiA          ea;
+  EpiA2         e2;
+  const double *prev;   // record of the diagonal pass, combined by the last CTA
+  typedef AccRed Acc;
+  __device__ bool active() const { return SECOND ? e2.active() : ea.active(); }
+  __device__ void init(Acc &a) const
+  {
+    if (SECOND) e2.init(a);
+    else ea.init(a);
+  }
+  __device__ void row(int r, double ax, Acc &a) const
+  {
+    if (SECOND) {
+      e2.epilogue(r, e2.g[r] + ax, a);
+    } else {
+      const double f = ea.Ap[r] + ax;
+      ea.Ap[r]       = f;
+      ea.epilogue(r, f, a);
+    }
+  }
+  __device__ void finalize(Acc &a) const
+  {
+    if (SECOND) grid_reduce8<0>(a.v, e2.rb, prev);
+    else grid_reduce8<(1 << RA_FEAS)>(a.v, ea.rb, prev);
+  }
+};
+
+int k_spmv(const CsrDev &A, const double *x, double *y, int accumulate)
+{
+  EpiPlain e{y, accumulate};
+  return launch_spmv(A, x, e, KF_SPMV_PLAIN, 12.0 * (double)A.nnz + 4.0 * (A.n + 1) + 16.0 * A.n);
+}
+
+int k_spmv_gated(const CsrDev &A, const double *x, double *y, const MpgpCtl *S, int phase)
+{
+  EpiGated e{y, S, phase};
+  return launch_spmv(A, x, e, KF_SPMV_PLAIN, 12.0 * (double)A.nnz + 4.0 * (A.n + 1) + 16.0 * A.n);
+}
+
+static double bytes_A(const CsrDev &A, const MpgpVecs &v)
+{   // CSR + p(gather) + g + x + lb[+ub] + B rows, write Ap
+  return 12.0 * (double)A.nnz + 4.0 * (A.n + 1) + 8.0 * v.n * (4 + (v.bx.lb ? 1 : 0) + (v.bx.ub ? 1 : 0) + v.m);
+}
+static double bytes_A2(const CsrDev &A, const MpgpVecs &v)
+{   // CSR + x(gather) + b + lb[+ub] + B rows, write g, p
+  return 12.0 * (double)A.nnz + 4.0 * (A.n + 1) + 8.0 * v.n * (4 + (v.bx.lb ? 1 : 0) + (v.bx.ub ? 1 : 0) + v.m);
+}
+
+int k_fused_A(const CsrDev &A, const double *xin, const MpgpVecs &v, const MpgpCtl *S, RedBuf rb, const unsigned char *skip)
+{
+  EpiA e{v.p, v.g, v.x, v.Ap, v.bx, v.B, v.m, v.n, S, rb, skip};
+  return launch_spmv(A, xin, e, KF_SPMV_A, bytes_A(A, v));
+}
+
+int k_fused_A2(const CsrDev &A, const double *xin, const MpgpVecs &v, const MpgpCtl *S, RedBuf rb, const unsigned char *skip)
+{
+  EpiA2 e{v.x, v.b, v.g, v.p, v.bx, v.B, v.m, v.n, S, rb, skip};
+  return launch_spmv(A, xin, e, KF_SPMV_A2, bytes_A2(A, v));
+}
+
+int k_fused_A_ghost(const CsrDev &Ao, const double *ghost, const MpgpVecs &v, const MpgpCtl *S, RedBuf rb, int second)
+{
+  // rb.out: final record; the diagonal pass left its record in rb.out as well -> read it as `prev`
+  EpiA  ea{v.p, v.g, v.x, v.Ap, v.bx, v.B, v.m, v.n, S, rb, nullptr};
+  EpiA2 e2{v.x, v.b, v.g, v.p, v.bx, v.B, v.m, v.n, S, rb, nullptr};
+  double bytes = 12.0 * (double)Ao.nnz + 8.0 * Ao.n * 8;
+  if (second) {
+    EpiGhost<true> e{ea, e2, rb.out};
+    return launch_spmv(Ao, ghost, e, KF_SPMV_A2, bytes);
+  }
+  EpiGhost<false> e{ea, e2, rb.out};
+  return launch_spmv(Ao, ghost, e, KF_SPMV_A, bytes);
+}
+
+// =====================================================================================================
+// K_B: fused step  (mpgp.c:553-555 CG, :633-638 proportioning, :316-321 expansion std/fixed)
+// =====================================================================================================
+__global__ void __launch_bounds__(NT) k_update_B(MpgpVecs v, const MpgpCtl *__restrict__ S, RedBuf rb)
+{
+  if (S->reason != 0) return;
+  const int    step = S->step;
+  const double acg = S->acg, afeas = S->afeas, alpha = S->alpha, rho = S->rho, astol = v.bx.astol;
+  const int    m = v.m, n = v.n;
+  double       bp[PB_MAXEQ];
+#pragma unroll
+  for (int j = 0; j < PB_MAXEQ; j++) bp[j] = (j < m) ? S->Bp[j] : 0.0;
+  double acc[PB_NRED];
+#pragma unroll
+  for (int k = 0; k < PB_NRED; k++) acc[k] = 0.0;
+
+  const int stride = gridDim.x * NT;
+  for (int r = blockIdx.x * NT + threadIdx.x; r < n; r += stride) {
+    const double xr = v.x[r], pr = v.p[r], gr0 = v.g[r];
+    double       apr = v.Ap[r];
+    double       brow[PB_MAXEQ] = {0.0, 0.0, 0.0, 0.0};
+    if (m > 0) {   // A_rho p = A p + rho B^T (B p)
+      double t = 0.0;
+#pragma unroll
+      for (int j = 0; j < PB_MAXEQ; j++) {
+        brow[j] = (j < m) ? v.B[(size_t)j * n + r] : 0.0;
+        t += brow[j] * bp[j];
+      }
+      apr += rho * t;
+    }
+    const BoxVal b = load_box(v.bx, r);
+    if (step == 'e') {
+      const double xh = xr - afeas * pr;          // mpgp.c:316
+      const double gh = gr0 - afeas * apr;        // mpgp.c:317
+      double       gf, gc;
+      box_split(xh, gh, b, astol, gf, gc);        // mpgp.c:318
+      const double grd = box_reduced(xh, gf, b, alpha);
+      const double xn  = xh - alpha * grd;        // mpgp.c:321
+      v.x[r]           = xn;
+#pragma unroll
+      for (int j = 0; j < PB_MAXEQ; j++)
+        if (j < m) acc[RB_BU + j] += brow[j] * xn;
+    } else {
+      const double xn = xr - acg * pr;            // mpgp.c:553 / :633
+      const double gn = gr0 - acg * apr;          // mpgp.c:554 / :634
+      double       gf, gc;
+      box_split(xn, gn, b, astol, gf, gc);        // mpgp.c:555 / :635
+      v.x[r] = xn;
+      v.g[r] = gn;
+      if (step == 'c') {
+        v.gf[r] = gf;
+        acc[RB_APGF] += apr * gf;                 // mpgp.c:558
+      } else {
+        v.p[r] = gf;                              // mpgp.c:638
+      }
+      const double gP = gf + gc;
+      acc[RB_GP2] += gP * gP;
+      acc[RB_GC2] += gc * gc;
+      acc[RB_GF2] += gf * gf;
+#pragma unroll
+      for (int j = 0; j < PB_MAXEQ; j++)
+        if (j < m) acc[RB_BU + j] += brow[j] * xn;
+    }
+  }
+  grid_reduce8<0>(acc, rb, nullptr);
+}
+
+int k_fused_B(const MpgpVecs &v, const MpgpCtl *S, RedBuf rb)
+{
+  int grid = elementwise_grid();
+  int need = (v.n + NT - 1) / NT;
+  if (need < 1) need = 1;
+  if (grid > need) grid = need;
+  // x p g Ap lb[ub] read, x g gf written (CG step)
+  prof_pre(KF_UPDATE_B, 8.0 * v.n * (7 + (v.bx.lb ? 1 : 0) + (v.bx.ub ? 1 : 0) + v.m));
+  k_update_B<<<grid, NT, 0, g_ctx.stream>>>(v, S, rb);
+  prof_post(KF_UPDATE_B);
+  LAUNCH_CHECK();
+  return 0;
+}
+
+// =====================================================================================================
+// K_C: direction update  (mpgp.c:560 p = gf - bcg p ; :623 p = gc)
+// =====================================================================================================
+__global__ void __launch_bounds__(NT) k_direction_C(MpgpVecs v, const MpgpCtl *__restrict__ S)
+{
+  const int pmode = S->pmode;
+  if (S->reason != 0 || pmode == 0) return;
+  const double bcg = S->bcg, astol = v.bx.astol;
+  const int    stride = gridDim.x * NT;
+  if (pmode == 1) {
+    for (int r = blockIdx.x * NT + threadIdx.x; r < v.n; r += stride) v.p[r] = v.gf[r] - bcg * v.p[r];
+  } else {
+    for (int r = blockIdx.x * NT + threadIdx.x; r < v.n; r += stride) {
+      double gf, gc;
+      box_split(v.x[r], v.g[r], load_box(v.bx, r), astol, gf, gc);
+      v.p[r] = gc;
+    }
+  }
+}
+
+int k_fused_C(const MpgpVecs &v, const MpgpCtl *S)
+{
+  int grid = elementwise_grid();
+  int need = (v.n + NT - 1) / NT;
+  if (need < 1) need = 1;
+  if (grid > need) grid = need;
+  prof_pre(KF_DIR_C, 8.0 * v.n * 3);
+  k_direction_C<<<grid, NT, 0, g_ctx.stream>>>(v, S);
+  prof_post(KF_DIR_C);
+  LAUNCH_CHECK();
+  return 0;
+}
+
+// initial projection x = P(x) (mpgp.c:497) + B u of the projected iterate
+__global__ void __launch_bounds__(NT) k_project_init(MpgpVecs v, const MpgpCtl *__restrict__ S, RedBuf rb)
+{
+  if (S->reason != 0) return;
+  double acc[PB_NRED];
+#pragma unroll
+  for (int k = 0; k < PB_NRED; k++) acc[k] = 0.0;
+  const int stride = gridDim.x * NT;
+  for (int r = blockIdx.x * NT + threadIdx.x; r < v.n; r += stride) {
+    const double xn = box_project(v.x[r], load_box(v.bx, r));
+    v.x[r]          = xn;
+    for (int j = 0; j < v.m; j++) acc[RB_BU + j] += v.B[(size_t)j * v.n + r] * xn;
+  }
+  grid_reduce8<0>(acc, rb, nullptr);
+}
+
+int k_fused_project(const MpgpVecs &v, const MpgpCtl *S, RedBuf rb)
+{
+  int grid = elementwise_grid();
+  int need = (v.n + NT - 1) / NT;
+  if (need < 1) need = 1;
+  if (grid > need) grid = need;
+  prof_pre(KF_QPC, 8.0 * v.n * 3);
+  k_project_init<<<grid, NT, 0, g_ctx.stream>>>(v, S, rb);
+  prof_post(KF_QPC);
+  LAUNCH_CHECK();
+  return 0;
+}
+
+// =====================================================================================================
+// ctrl kernels
+// =====================================================================================================
+__global__ void k_ctrl_A_kernel(MpgpCtl *S, const double *ra) { mpgp_ctrl_A(S, ra); }
+__global__ void k_ctrl_E_kernel(MpgpCtl *S, const double *rb) { mpgp_ctrl_E(S, rb); }
+__global__ void k_ctrl_B_kernel(MpgpCtl *S, const double *rb) { mpgp_ctrl_B(S, rb); }
+
+int k_ctrl_A(MpgpCtl *S, const double *ra)
+{
+  prof_pre(KF_CTRL, 0);
+  k_ctrl_A_kernel<<<1, 1, 0, g_ctx.stream>>>(S, ra);
+  prof_post(KF_CTRL);
+  LAUNCH_CHECK();
+  return 0;
+}
+int k_ctrl_E(MpgpCtl *S, const double *rb)
+{
+  prof_pre(KF_CTRL, 0);
+  k_ctrl_E_kernel<<<1, 1, 0, g_ctx.stream>>>(S, rb);
+  prof_post(KF_CTRL);
+  LAUNCH_CHECK();
+  return 0;
+}
+int k_ctrl_B(MpgpCtl *S, const double *rb)
+{
+  prof_pre(KF_CTRL, 0);
+  k_ctrl_B_kernel<<<1, 1, 0, g_ctx.stream>>>(S, rb);
+  prof_post(KF_CTRL);
+  LAUNCH_CHECK();
+  return 0;
+}
+
+// =====================================================================================================
+// generic vector kernels
+// =====================================================================================================
+template <class F>
+__global__ void __launch_bounds__(NT) k_elementwise(int n, F f)
+{
+  const int stride = gridDim.x * NT;
+  for (int i = blockIdx.x * NT + threadIdx.x; i < n; i += stride) f(i);
+}
+template <class F>
+static int launch_ew(int n, F f, int family, double bytes)
+{
+  if (n <= 0) return 0;
+  int grid = elementwise_grid();
+  int need = (n + NT - 1) / NT;
+  if (grid > need) grid = need;
+  prof_pre(family, bytes);
+  k_elementwise<<<grid, NT, 0, g_ctx.stream>>>(n, f);
+  prof_post(family);
+  LAUNCH_CHECK();
+  return 0;
+}
+
+int k_set(int n, double *x, double a)
+{
+  return launch_ew(n, [=] __device__(int i) { x[i] = a; }, KF_VEC, 8.0 * n);
+}
+int k_copy(int n, const double *x, double *y)
+{
+  if (x == y) return 0;
+  return launch_ew(n, [=] __device__(int i) { y[i] = x[i]; }, KF_VEC, 16.0 * n);
+}
+int k_scale(int n, double *x, double a)
+{
+  return launch_ew(n, [=] __device__(int i) { x[i] *= a; }, KF_VEC, 16.0 * n);
+}
+int k_axpy(int n, double *y, double a, const double *x)
+{
+  return launch_ew(n, [=] __device__(int i) { y[i] += a * x[i]; }, KF_VEC, 24.0 * n);
+}
+int k_aypx(int n, double *y, double a, const double *x)
+{
+  return launch_ew(n, [=] __device__(int i) { y[i] = x[i] + a * y[i]; }, KF_VEC, 24.0 * n);
+}
+int k_waxpy(int n, double *w, double a, const double *x, const double *y)
+{
+  return launch_ew(n, [=] __device__(int i) { w[i] = a * x[i] + y[i]; }, KF_VEC, 24.0 * n);
+}
+int k_pmax(int n, double *w, const double *x, const double *y)
+{
+  return launch_ew(n, [=] __device__(int i) { double a = x[i], b = y[i]; w[i] = (a < b) ? b : a; }, KF_VEC, 24.0 * n);
+}
+int k_pmin(int n, double *w, const double *x, const double *y)
+{
+  return launch_ew(n, [=] __device__(int i) { double a = x[i], b = y[i]; w[i] = (a < b) ? a : b; }, KF_VEC, 24.0 * n);
+}
+int k_scatter_is(int nis, const int *is, const double *sub, double fill, int n, double *full)
+{
+  PB_CHK(k_set(n, full, fill));
+  return launch_ew(nis, [=] __device__(int k) { full[is[k]] = sub[k]; }, KF_VEC, 20.0 * nis);
+}
+int k_pack(int n, const int *idx, const double *x, double *buf)
+{
+  return launch_ew(n, [=] __device__(int k) { buf[k] = x[idx[k]]; }, KF_HALO, 20.0 * n);
+}
+int k_dense_rows_multT_add(int n, int m, const double *B, const double *t, double scale, double *y, int accumulate)
+{
+  return launch_ew(n, [=] __device__(int i) {
+    double s = 0.0;
+    for (int j = 0; j < m; j++) s += B[(size_t)j * n + i] * t[j];
+    y[i] = accumulate ? y[i] + scale * s : scale * s;
+  }, KF_VEC, 8.0 * n * (m + 2));
+}
+int k_qpc_project(int n, const double *x, BoxDev bx, double *Px)
+{
+  return launch_ew(n, [=] __device__(int i) { Px[i] = box_project(x[i], load_box(bx, i)); }, KF_QPC, 32.0 * n);
+}
+int k_qpc_grads(int n, const double *x, const double *g, BoxDev bx, double *gf, double *gc)
+{
+  return launch_ew(n, [=] __device__(int i) {
+    double a, c;
+    box_split(x[i], g[i], load_box(bx, i), bx.astol, a, c);
+    gf[i] = a;
+    gc[i] = c;
+  }, KF_QPC, 48.0 * n);
+}
+int k_qpc_gradreduced(int n, const double *x, const double *gf, double alpha, BoxDev bx, double *gr)
+{
+  return launch_ew(n, [=] __device__(int i) { gr[i] = box_reduced(x[i], gf[i], load_box(bx, i), alpha); }, KF_QPC, 40.0 * n);
+}
+int k_box_mult(int n, const double *r, int has_lb, int has_ub, double *llb, double *lub)
+{   // QPComputeMissingBoxMultipliers qp.c:858-881
+  return launch_ew(n, [=] __device__(int i) {
+    const double ri = r[i];
+    if (has_lb) llb[i] = (has_ub && ri < 0.0) ? 0.0 : ri;
+    if (has_ub) {
+      const double u = -1.0 * ri;
+      lub[i]         = (has_lb && u < 0.0) ? 0.0 : u;
+    }
+  }, KF_VEC, 24.0 * n);
+}
+
+// reductions ---------------------------------------------------------------------------------------------
+template <int MINMASK, class F>
+__global__ void __launch_bounds__(NT) k_reduce(int n, F f, RedBuf rb)
+{
+  double acc[PB_NRED];
+#pragma unroll
+  for (int k = 0; k < PB_NRED; k++) acc[k] = red_identity<MINMASK>(k);
+  const int stride = gridDim.x * NT;
+  for (int i = blockIdx.x * NT + threadIdx.x; i < n; i += stride) f(i, acc);
+  grid_reduce8<MINMASK>(acc, rb, nullptr);
+}
+template <int MINMASK, class F>
+static int launch_red(int n, F f, RedBuf rb, int family, double bytes)
+{
+  int grid = elementwise_grid();
+  int need = (n + NT - 1) / NT;
+  if (need < 1) need = 1;
+  if (grid > need) grid = need;
+  prof_pre(family, bytes);
+  k_reduce<MINMASK><<<grid, NT, 0, g_ctx.stream>>>(n, f, rb);
+  prof_post(family);
+  LAUNCH_CHECK();
+  return 0;
+}
+int k_dot(int n, const double *x, const double *y, RedBuf rb)
+{
+  return launch_red<0>(n, [=] __device__(int i, double(&a)[PB_NRED]) { a[0] += x[i] * y[i]; }, rb, KF_VEC, 16.0 * n);
+}
+int k_mdot2(int n, const double *x, const double *y0, const double *y1, RedBuf rb)
+{
+  return launch_red<0>(n, [=] __device__(int i, double(&a)[PB_NRED]) {
+    const double xi = x[i];
+    a[0] += xi * y0[i];
+    a[1] += xi * y1[i];
+  }, rb, KF_VEC, 24.0 * n);
+}
+int k_dense_rows_mult(int n, int m, const double *B, const double *x, RedBuf rb)
+{
+  return launch_red<0>(n, [=] __device__(int i, double(&a)[PB_NRED]) {
+    const double xi = x[i];
+    for (int j = 0; j < m; j++) a[j] += B[(size_t)j * n + i] * xi;
+  }, rb, KF_VEC, 8.0 * n * (m + 1));
+}
+int k_qpc_feas(int n, const double *x, const double *d, BoxDev bx, RedBuf rb)
+{
+  return launch_red<(1 << RA_FEAS)>(n, [=] __device__(int i, double(&a)[PB_NRED]) { a[RA_FEAS] = box_feas(x[i], d[i], load_box(bx, i), a[RA_FEAS]); }, rb, KF_QPC, 32.0 * n);
+}
+// QPCViewKKT_Box numbers (qpcbox.c:333-427): out[0]=sum min(x-lb,0)^2 | max(x-ub,0)^2, out[1]=sum min(lam,0)^2,
+// out[2]=lam'(lb-x) | lam'(x-ub) with the infinite-bound convention of the reference
+int k_kkt_box(int n, const double *x, const double *bound, const double *lam, int upper, RedBuf rb)
+{
+  const double PINF = 1.7976931348623157e+308 / 4.0;
+  return launch_red<0>(n, [=] __device__(int i, double(&a)[PB_NRED]) {
+    const double xi = x[i], bi = bound[i], li = lam[i];
+    double       d, t;
+    if (!upper) {
+      d = xi - bi;
+      d = (d < 0.0) ? d : 0.0;
+      t = bi - xi;
+      if (bi <= -PINF) t = -1.0;
+    } else {
+      d = xi - bi;
+      d = (d < 0.0) ? 0.0 : d;
+      t = xi - bi;
+      if (bi >= PINF) t = 1.0;
+    }
+    const double lm = (li < 0.0) ? li : 0.0;
+    a[0] += d * d;
+    a[1] += lm * lm;
+    a[2] += li * t;
+  }, rb, KF_QPC, 24.0 * n);
+}
+
+}  // namespace pb

@@ -1,0 +1,1300 @@
+// shim.cpp -- the PETSc stand-in behind include/permon_b200.h: communicator (one process per GPU, NCCL),
+// options database, viewers, IS, Vec and Mat with host<->device validity tracking, the row-partitioned AIJ
+// matrix with its halo plan, and the generic (un-fused) Mat/Vec operations built on the CUDA kernels.
+// There is no CPU arithmetic here: every numerical operation launches a kernel from kernels.cu.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <nccl.h>
+#include <stdarg.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <fstream>
+#include <sstream>
+
+#include "objects.h"
+
+using namespace pb;
+
+static _p_PermonComm g_world, g_self;
+MPI_Comm             PETSC_COMM_WORLD = &g_world;
+MPI_Comm             PETSC_COMM_SELF  = &g_self;
+
+static std::map<std::string, std::string> g_opts;
+static std::map<MPI_Comm, Reducer>        g_reducers;
+
+namespace pb {
+
+int err(int code, const char *fmt, ...)
+{
+  char    buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  set_error("%s", buf);
+  return code;
+}
+
+#define PB_NCCL(call)                                                                          \
+  do {                                                                                         \
+    ncclResult_t r_ = (call);                                                                  \
+    if (r_ != ncclSuccess) return pb::err(PETSC_ERR_LIB, "NCCL error %d (%s) in %s at %s:%d", (int)r_, ncclGetErrorString(r_), #call, __FILE__, __LINE__); \
+  } while (0)
+
+// ---------------------------------------------------------------------------------------------------
+// options
+// ---------------------------------------------------------------------------------------------------
+int options_get(const std::string &prefix, const char *name, std::string *val)
+{
+  std::string key = std::string("-") + prefix + (name[0] == '-' ? name + 1 : name);
+  auto        it = g_opts.find(key);
+  if (it == g_opts.end()) return 0;
+  if (val) *val = it->second;
+  return 1;
+}
+bool options_real(const std::string &prefix, const char *name, double *v)
+{
+  std::string s;
+  if (!options_get(prefix, name, &s)) return false;
+  if (s == "PETSC_DECIDE" || s == "decide") *v = PETSC_DECIDE;
+  else *v = atof(s.c_str());
+  return true;
+}
+bool options_int(const std::string &prefix, const char *name, PetscInt *v)
+{
+  std::string s;
+  if (!options_get(prefix, name, &s)) return false;
+  *v = (PetscInt)atol(s.c_str());
+  return true;
+}
+bool options_bool(const std::string &prefix, const char *name, bool *v)
+{
+  std::string s;
+  if (!options_get(prefix, name, &s)) return false;
+  std::string t = s;
+  std::transform(t.begin(), t.end(), t.begin(), ::tolower);
+  *v = (t.empty() || t == "1" || t == "true" || t == "yes" || t == "on");
+  return true;
+}
+bool options_string(const std::string &prefix, const char *name, std::string *v) { return options_get(prefix, name, v) != 0; }
+
+void vprintf_viewer(PetscViewer v, const char *fmt, ...)
+{
+  if (PETSC_COMM_WORLD->rank != 0) return;
+  FILE *f = (v && v->f) ? v->f : stdout;
+  int   tab = v ? v->tab : 0;
+  for (int i = 0; i < tab; i++) fputs("  ", f);
+  va_list ap;
+  va_start(ap, fmt);
+  vfprintf(f, fmt, ap);
+  va_end(ap);
+  fflush(f);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// reducer
+// ---------------------------------------------------------------------------------------------------
+int Reducer::init(MPI_Comm c)
+{
+  comm = c;
+  PB_CHK(dev_init());
+  const int size = c->size;
+  PB_CUDA(cudaMalloc(&rb.partials, sizeof(double) * PB_NRED * (size_t)max_red_blocks()));
+  PB_CUDA(cudaMalloc(&rb.counter, sizeof(unsigned)));
+  PB_CUDA(cudaMemset(rb.counter, 0, sizeof(unsigned)));
+  PB_CUDA(cudaMalloc(&d_all, sizeof(double) * PB_NRED * size));
+  PB_CUDA(cudaMemset(d_all, 0, sizeof(double) * PB_NRED * size));
+  if (size > 1) {
+    PB_CUDA(cudaMalloc(&d_local, sizeof(double) * PB_NRED));
+    PB_CUDA(cudaMemset(d_local, 0, sizeof(double) * PB_NRED));
+  } else {
+    d_local = d_all;
+  }
+  PB_CUDA(cudaMallocHost(&h_all, sizeof(double) * PB_NRED * size));
+  rb.out = d_local;
+  return 0;
+}
+void Reducer::destroy()
+{
+  if (!rb.partials) return;
+  cudaFree(rb.partials);
+  cudaFree(rb.counter);
+  if (d_local != d_all) cudaFree(d_local);
+  cudaFree(d_all);
+  cudaFreeHost(h_all);
+  rb = RedBuf();
+  d_local = d_all = h_all = nullptr;
+}
+int Reducer::gather() { return comm_allgather_records(comm, d_local, d_all); }
+int Reducer::fetch()
+{
+  PB_CUDA(cudaMemcpyAsync(h_all, d_all, sizeof(double) * PB_NRED * comm->size, cudaMemcpyDeviceToHost, ctx().stream));
+  PB_CUDA(cudaStreamSynchronize(ctx().stream));
+  return 0;
+}
+double Reducer::sum(int slot) const
+{
+  double s = 0.0;
+  for (int r = 0; r < comm->size; r++) s += h_all[r * PB_NRED + slot];
+  return s;
+}
+double Reducer::min(int slot) const
+{
+  double s = HUGE_VAL;
+  for (int r = 0; r < comm->size; r++)
+    if (h_all[r * PB_NRED + slot] < s) s = h_all[r * PB_NRED + slot];
+  return s;
+}
+Reducer &reducer(MPI_Comm comm)
+{
+  Reducer &r = g_reducers[comm];
+  if (!r.rb.partials) r.init(comm);
+  return r;
+}
+
+int comm_allgather_records(MPI_Comm comm, const double *d_local, double *d_all)
+{
+  if (comm->size == 1) return 0;
+  if (!comm->nccl) return err(PETSC_ERR_ARG_WRONGSTATE, "multi-rank communicator without NCCL (call PermonB200CommInitRank on a GPU box)");
+  ctx().launches++;
+  PB_NCCL(ncclAllGather(d_local, d_all, PB_NRED, ncclDouble, (ncclComm_t)comm->nccl, ctx().stream));
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Vec internals
+// ---------------------------------------------------------------------------------------------------
+int vec_layout(MPI_Comm comm, PetscInt n, PetscInt *N, PetscInt *rstart)
+{
+  if (comm->size == 1) {
+    *N      = n;
+    *rstart = 0;
+    return 0;
+  }
+  if (!comm->agi) return err(PETSC_ERR_ARG_WRONGSTATE, "communicator has no host exchange");
+  std::vector<int64_t> all(comm->size);
+  if (comm->agi(comm->agctx, (int64_t)n, all.data())) return err(PETSC_ERR_LIB, "host all-gather failed");
+  int64_t s = 0, tot = 0;
+  for (int r = 0; r < comm->size; r++) {
+    if (r < comm->rank) s += all[r];
+    tot += all[r];
+  }
+  *N      = (PetscInt)tot;
+  *rstart = (PetscInt)s;
+  return 0;
+}
+
+int vec_create(MPI_Comm comm, PetscInt n, PetscInt N, Vec *v)
+{
+  _p_Vec *w = new _p_Vec;
+  w->comm   = comm;
+  w->n      = n;
+  if (N == PETSC_DECIDE || comm->size > 1) {
+    PetscInt NN = 0, rs = 0;
+    int      ierr = vec_layout(comm, n, &NN, &rs);
+    if (ierr) {
+      delete w;
+      return ierr;
+    }
+    w->N      = NN;
+    w->rstart = rs;
+  } else {
+    w->N      = N;
+    w->rstart = 0;
+  }
+  *v = w;
+  return 0;
+}
+
+static int vec_alloc_dev(Vec v)
+{
+  if (v->d) return 0;
+  PB_CHK(dev_init());
+  PB_CUDA(cudaMalloc(&v->d, sizeof(double) * (size_t)std::max<PetscInt>(v->n, 1)));
+  v->d_owned = true;
+  return 0;
+}
+static int vec_alloc_host(Vec v)
+{
+  if (v->h) return 0;
+  v->h = (double *)malloc(sizeof(double) * (size_t)std::max<PetscInt>(v->n, 1));
+  if (!v->h) return err(PETSC_ERR_MEM, "out of host memory");
+  v->h_owned = true;
+  return 0;
+}
+int vec_dev_read(Vec v, const double **d)
+{
+  PB_CHK(vec_alloc_dev(v));
+  if (!v->d_valid) {
+    if (v->h_valid) PB_CUDA(cudaMemcpyAsync(v->d, v->h, sizeof(double) * (size_t)v->n, cudaMemcpyHostToDevice, ctx().stream));
+    else PB_CUDA(cudaMemsetAsync(v->d, 0, sizeof(double) * (size_t)v->n, ctx().stream));
+    v->d_valid = true;
+  }
+  *d = v->d;
+  return 0;
+}
+int vec_dev_write(Vec v, double **d)
+{
+  PB_CHK(vec_alloc_dev(v));
+  v->d_valid = true;
+  v->h_valid = false;
+  v->state++;
+  *d = v->d;
+  return 0;
+}
+int vec_dev_rw(Vec v, double **d)
+{
+  const double *c;
+  PB_CHK(vec_dev_read(v, &c));
+  v->h_valid = false;
+  v->state++;
+  *d = v->d;
+  return 0;
+}
+int vec_host_read(Vec v, const double **h)
+{
+  PB_CHK(vec_alloc_host(v));
+  if (!v->h_valid) {
+    if (v->d_valid) {
+      PB_CUDA(cudaMemcpyAsync(v->h, v->d, sizeof(double) * (size_t)v->n, cudaMemcpyDeviceToHost, ctx().stream));
+      PB_CUDA(cudaStreamSynchronize(ctx().stream));
+    } else {
+      memset(v->h, 0, sizeof(double) * (size_t)v->n);
+    }
+    v->h_valid = true;
+  }
+  *h = v->h;
+  return 0;
+}
+int vec_host_write(Vec v, double **h)
+{
+  PB_CHK(vec_alloc_host(v));
+  if (v->d_valid && ctx().ready) PB_CUDA(cudaStreamSynchronize(ctx().stream));   // pending device readers of the old contents
+  v->h_valid = true;
+  v->d_valid = false;
+  v->state++;
+  *h = v->h;
+  return 0;
+}
+int vec_host_rw(Vec v, double **h)
+{
+  const double *c;
+  PB_CHK(vec_host_read(v, &c));
+  v->d_valid = false;
+  v->state++;
+  *h = v->h;
+  return 0;
+}
+
+int vec_dot(Vec x, Vec y, double *val)
+{
+  if (x->n != y->n) return err(PETSC_ERR_ARG_INCOMP, "VecDot: local sizes differ (%d vs %d)", (int)x->n, (int)y->n);
+  const double *dx, *dy;
+  PB_CHK(vec_dev_read(x, &dx));
+  PB_CHK(vec_dev_read(y, &dy));
+  Reducer &R = reducer(x->comm);
+  PB_CHK(k_dot(x->n, dx, dy, R.rb));
+  PB_CHK(R.gather());
+  PB_CHK(R.fetch());
+  *val = R.sum(0);
+  return 0;
+}
+int vec_norm2(Vec x, double *val)
+{
+  double d;
+  PB_CHK(vec_dot(x, x, &d));
+  *val = sqrt(d);
+  return 0;
+}
+int vec_mdot2(Vec x, Vec y0, Vec y1, double *v0, double *v1)
+{
+  const double *dx, *d0, *d1;
+  PB_CHK(vec_dev_read(x, &dx));
+  PB_CHK(vec_dev_read(y0, &d0));
+  PB_CHK(vec_dev_read(y1, &d1));
+  Reducer &R = reducer(x->comm);
+  PB_CHK(k_mdot2(x->n, dx, d0, d1, R.rb));
+  PB_CHK(R.gather());
+  PB_CHK(R.fetch());
+  *v0 = R.sum(0);
+  *v1 = R.sum(1);
+  return 0;
+}
+
+}  // namespace pb
+
+_p_Vec::~_p_Vec()
+{
+  if (h_owned && h) free(h);
+  if (d_owned && d) cudaFree(d);
+}
+
+// =====================================================================================================
+// life cycle and B200 helpers
+// =====================================================================================================
+static bool g_initialized = false;
+
+static void options_insert_tokens(const std::vector<std::string> &tok)
+{
+  for (size_t i = 0; i < tok.size(); i++) {
+    const std::string &t = tok[i];
+    if (t.size() < 2 || t[0] != '-' || (t[1] >= '0' && t[1] <= '9')) continue;
+    std::string val;
+    if (i + 1 < tok.size()) {
+      const std::string &nx = tok[i + 1];
+      bool is_key = nx.size() >= 2 && nx[0] == '-' && !((nx[1] >= '0' && nx[1] <= '9') || nx[1] == '.');
+      if (!is_key) {
+        val = nx;
+        i++;
+      }
+    }
+    g_opts[t] = val;
+  }
+}
+static void options_insert_file(const std::string &path)
+{
+  std::ifstream f(path);
+  if (!f) return;
+  std::string              line;
+  std::vector<std::string> tok;
+  while (std::getline(f, line)) {
+    size_t h = line.find('#');
+    if (h != std::string::npos) line = line.substr(0, h);
+    std::istringstream is(line);
+    std::string        w;
+    while (is >> w) tok.push_back(w);
+  }
+  options_insert_tokens(tok);
+}
+
+PetscErrorCode PermonInitialize(int *argc, char ***args, const char file[], const char help[])
+{
+  (void)help;
+  if (g_initialized) return 0;
+  // rc files exactly as src/sys/permoninit.c:62-73: ~/.permonrc, ./permonrc, ./.permonrc, then argv
+  const char *home = getenv("HOME");
+  if (home) options_insert_file(std::string(home) + "/.permonrc");
+  options_insert_file("permonrc");
+  options_insert_file(".permonrc");
+  if (file) options_insert_file(file);
+  if (argc && args && *args) {
+    std::vector<std::string> tok;
+    for (int i = 1; i < *argc; i++) tok.push_back((*args)[i]);
+    options_insert_tokens(tok);
+  }
+  g_initialized = true;
+  return 0;
+}
+
+PetscErrorCode PermonFinalize(void)
+{
+  for (auto &kv : g_reducers) kv.second.destroy();
+  g_reducers.clear();
+  if (g_world.nccl) {
+    ncclCommDestroy((ncclComm_t)g_world.nccl);
+    g_world.nccl = nullptr;
+  }
+  g_initialized = false;
+  return 0;
+}
+
+PetscErrorCode PermonB200GetDeviceCount(int *count)
+{
+  int c = 0;
+  if (cudaGetDeviceCount(&c) != cudaSuccess) c = 0;
+  *count = c;
+  return 0;
+}
+PetscErrorCode PermonB200SetDevice(int device)
+{
+  if (ctx().ready && ctx().device != device) return err(PETSC_ERR_ARG_WRONGSTATE, "device already initialised as %d", ctx().device);
+  ctx().device = device;
+  return 0;
+}
+PetscErrorCode PermonB200SetStream(void *s)
+{
+  PB_CHK(dev_init());
+  PB_CUDA(cudaStreamSynchronize(ctx().stream));
+  ctx().stream = s ? (cudaStream_t)s : ctx().own_stream;
+  return 0;
+}
+PetscErrorCode PermonB200GetStream(void **s)
+{
+  PB_CHK(dev_init());
+  *s = (void *)ctx().stream;
+  return 0;
+}
+PetscErrorCode PermonB200Synchronize(void)
+{
+  PB_CHK(dev_init());
+  PB_CUDA(cudaStreamSynchronize(ctx().stream));
+  PB_CUDA(cudaStreamSynchronize(ctx().comm_stream));
+  return 0;
+}
+PetscErrorCode PermonB200GetUniqueId(void *id128)
+{
+  ncclUniqueId id;
+  PB_NCCL(ncclGetUniqueId(&id));
+  static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+  memcpy(id128, &id, 128);
+  return 0;
+}
+
+// default host exchange over NCCL (device staging); only used at set-up time
+static int nccl_agi(void *vctx, int64_t value, int64_t *all)
+{
+  MPI_Comm c = (MPI_Comm)vctx;
+  int64_t *d = nullptr;
+  if (cudaMalloc(&d, sizeof(int64_t) * (c->size + 1)) != cudaSuccess) return 1;
+  cudaMemcpyAsync(d + c->size, &value, sizeof(int64_t), cudaMemcpyHostToDevice, ctx().stream);
+  if (ncclAllGather(d + c->size, d, 1, ncclInt64, (ncclComm_t)c->nccl, ctx().stream) != ncclSuccess) return 1;
+  cudaMemcpyAsync(all, d, sizeof(int64_t) * c->size, cudaMemcpyDeviceToHost, ctx().stream);
+  if (cudaStreamSynchronize(ctx().stream) != cudaSuccess) return 1;
+  cudaFree(d);
+  return 0;
+}
+static int nccl_agv(void *vctx, const void *sendbuf, int64_t sendbytes, void *recvbuf, const int64_t *recvbytes)
+{
+  MPI_Comm c = (MPI_Comm)vctx;
+  int64_t  mx = 0;
+  for (int r = 0; r < c->size; r++) mx = std::max(mx, recvbytes[r]);
+  mx = (mx + 15) & ~(int64_t)15;
+  if (mx == 0) return 0;
+  char *d = nullptr;
+  if (cudaMalloc(&d, (size_t)mx * (c->size + 1)) != cudaSuccess) return 1;
+  char *mine = d + (size_t)mx * c->size;
+  cudaMemcpyAsync(mine, sendbuf, (size_t)sendbytes, cudaMemcpyHostToDevice, ctx().stream);
+  if (ncclAllGather(mine, d, (size_t)mx, ncclChar, (ncclComm_t)c->nccl, ctx().stream) != ncclSuccess) return 1;
+  std::vector<char> h((size_t)mx * c->size);
+  cudaMemcpyAsync(h.data(), d, h.size(), cudaMemcpyDeviceToHost, ctx().stream);
+  if (cudaStreamSynchronize(ctx().stream) != cudaSuccess) return 1;
+  char *out = (char *)recvbuf;
+  for (int r = 0; r < c->size; r++) {
+    memcpy(out, h.data() + (size_t)mx * r, (size_t)recvbytes[r]);
+    out += recvbytes[r];
+  }
+  cudaFree(d);
+  return 0;
+}
+
+PetscErrorCode PermonB200CommInitRank(int nranks, int rank, const void *id128)
+{
+  if (nranks < 1 || rank < 0 || rank >= nranks) return err(PETSC_ERR_ARG_OUTOFRANGE, "bad rank %d of %d", rank, nranks);
+  if (nranks > PB_MAXRANKS) return err(PETSC_ERR_SUP, "at most %d ranks", PB_MAXRANKS);
+  g_world.rank = rank;
+  g_world.size = nranks;
+  if (nranks == 1) return 0;
+  PB_CHK(dev_init());
+  ncclUniqueId id;
+  memcpy(&id, id128, 128);
+  ncclComm_t c;
+  PB_NCCL(ncclCommInitRank(&c, nranks, id, rank));
+  g_world.nccl  = (ncclComm *)c;
+  g_world.agi   = nccl_agi;
+  g_world.agv   = nccl_agv;
+  g_world.agctx = &g_world;
+  return 0;
+}
+
+PetscErrorCode PermonB200CommSetHostExchange(int nranks, int rank, PermonB200AllGatherI64 agi, PermonB200AllGatherV agv, void *cctx)
+{
+  g_world.rank  = rank;
+  g_world.size  = nranks;
+  g_world.agi   = agi;
+  g_world.agv   = agv;
+  g_world.agctx = cctx;
+  return 0;
+}
+
+PetscErrorCode PermonB200ProfileBegin(void)
+{
+  PB_CHK(dev_init());
+  prof_begin();
+  return 0;
+}
+PetscErrorCode PermonB200ProfileEnd(int *nfamilies)
+{
+  int n = prof_end();
+  if (nfamilies) *nfamilies = n;
+  return 0;
+}
+PetscErrorCode PermonB200ProfileGet(int family, const char **name, int64_t *launches, double *total_ms, double *bytes_per_launch)
+{
+  if (name) *name = family_name(family);
+  return prof_get(family, launches, total_ms, bytes_per_launch);
+}
+PetscErrorCode PermonB200GetLaunchCount(int64_t *launches)
+{
+  *launches = ctx().launches;
+  return 0;
+}
+const char *PermonB200GetLastErrorMessage(void) { return last_error(); }
+
+// ---- options -----------------------------------------------------------------------------------------
+PetscErrorCode PetscOptionsSetValue(void *, const char name[], const char value[])
+{
+  if (!name || name[0] != '-') return err(PETSC_ERR_ARG_WRONG, "option name must start with '-'");
+  g_opts[name] = value ? value : "";
+  return 0;
+}
+PetscErrorCode PetscOptionsClearValue(void *, const char name[])
+{
+  g_opts.erase(name);
+  return 0;
+}
+PetscErrorCode PetscOptionsClear(void *)
+{
+  g_opts.clear();
+  return 0;
+}
+PetscErrorCode PetscOptionsInsertString(void *, const char in_str[])
+{
+  std::istringstream       is(in_str ? in_str : "");
+  std::vector<std::string> tok;
+  std::string              w;
+  while (is >> w) tok.push_back(w);
+  options_insert_tokens(tok);
+  return 0;
+}
+PetscErrorCode PetscOptionsHasName(void *, const char pre[], const char name[], PetscBool *set)
+{
+  *set = options_get(pre ? pre : "", name, nullptr) ? PETSC_TRUE : PETSC_FALSE;
+  return 0;
+}
+
+// ---- viewers ----------------------------------------------------------------------------------------
+PetscErrorCode PetscViewerASCIIOpen(MPI_Comm comm, const char name[], PetscViewer *viewer)
+{
+  _p_PetscViewer *v = new _p_PetscViewer;
+  v->comm = comm;
+  if (name && strcmp(name, "stdout")) {
+    v->f = (comm->rank == 0) ? fopen(name, "w") : nullptr;
+    v->own = true;
+    if (comm->rank == 0 && !v->f) {
+      delete v;
+      return err(PETSC_ERR_ARG_WRONG, "cannot open %s", name);
+    }
+  }
+  *viewer = v;
+  return 0;
+}
+PetscErrorCode PetscViewerDestroy(PetscViewer *viewer)
+{
+  if (!viewer || !*viewer) return 0;
+  if ((*viewer)->own && (*viewer)->f) fclose((*viewer)->f);
+  delete *viewer;
+  *viewer = nullptr;
+  return 0;
+}
+
+// ---- IS ------------------------------------------------------------------------------------------------
+PetscErrorCode ISCreateStride(MPI_Comm comm, PetscInt n, PetscInt first, PetscInt step, IS *is)
+{
+  _p_IS *s = new _p_IS;
+  s->comm = comm;
+  s->idx.resize(n);
+  for (PetscInt i = 0; i < n; i++) s->idx[i] = first + i * step;
+  *is = s;
+  return 0;
+}
+PetscErrorCode ISCreateGeneral(MPI_Comm comm, PetscInt n, const PetscInt idx[], int, IS *is)
+{
+  _p_IS *s = new _p_IS;
+  s->comm = comm;
+  s->idx.assign(idx, idx + n);
+  *is = s;
+  return 0;
+}
+PetscErrorCode ISGetLocalSize(IS is, PetscInt *n)
+{
+  *n = (PetscInt)is->idx.size();
+  return 0;
+}
+PetscErrorCode ISDestroy(IS *is)
+{
+  if (!is || !*is) return 0;
+  if (--(*is)->refct == 0) {
+    if ((*is)->d_local) cudaFree((*is)->d_local);
+    delete *is;
+  }
+  *is = nullptr;
+  return 0;
+}
+
+// ---- Vec -----------------------------------------------------------------------------------------------
+PetscErrorCode VecCreateSeq(MPI_Comm comm, PetscInt n, Vec *v) { return vec_create(comm, n, n, v); }
+PetscErrorCode VecCreateMPI(MPI_Comm comm, PetscInt n, PetscInt N, Vec *v) { return vec_create(comm, n, N, v); }
+PetscErrorCode VecCreateSeqWithArray(MPI_Comm comm, PetscInt, PetscInt n, const PetscScalar array[], Vec *v)
+{
+  PB_CHK(vec_create(comm, n, n, v));
+  if (array) {
+    (*v)->h       = const_cast<double *>(array);
+    (*v)->h_valid = true;
+  }
+  return 0;
+}
+PetscErrorCode VecCreateMPIWithArray(MPI_Comm comm, PetscInt, PetscInt n, PetscInt N, const PetscScalar array[], Vec *v)
+{
+  PB_CHK(vec_create(comm, n, N, v));
+  if (array) {
+    (*v)->h       = const_cast<double *>(array);
+    (*v)->h_valid = true;
+  }
+  return 0;
+}
+PetscErrorCode VecCreateSeqCUDAWithArray(MPI_Comm comm, PetscInt, PetscInt n, const PetscScalar darray[], Vec *v)
+{
+  PB_CHK(dev_init());
+  PB_CHK(vec_create(comm, n, n, v));
+  if (darray) {
+    (*v)->d       = const_cast<double *>(darray);
+    (*v)->d_valid = true;
+  }
+  return 0;
+}
+PetscErrorCode VecCreateMPICUDAWithArray(MPI_Comm comm, PetscInt, PetscInt n, PetscInt N, const PetscScalar darray[], Vec *v)
+{
+  PB_CHK(dev_init());
+  PB_CHK(vec_create(comm, n, N, v));
+  if (darray) {
+    (*v)->d       = const_cast<double *>(darray);
+    (*v)->d_valid = true;
+  }
+  return 0;
+}
+PetscErrorCode VecDuplicate(Vec v, Vec *newv)
+{
+  _p_Vec *w = new _p_Vec;
+  w->comm   = v->comm;
+  w->n      = v->n;
+  w->N      = v->N;
+  w->rstart = v->rstart;
+  *newv     = w;
+  return 0;
+}
+PetscErrorCode VecDestroy(Vec *v)
+{
+  if (!v || !*v) return 0;
+  unref(*v);
+  return 0;
+}
+PetscErrorCode VecGetSize(Vec v, PetscInt *N)
+{
+  *N = v->N;
+  return 0;
+}
+PetscErrorCode VecGetLocalSize(Vec v, PetscInt *n)
+{
+  *n = v->n;
+  return 0;
+}
+PetscErrorCode VecGetOwnershipRange(Vec v, PetscInt *low, PetscInt *high)
+{
+  if (low) *low = v->rstart;
+  if (high) *high = v->rstart + v->n;
+  return 0;
+}
+PetscErrorCode VecGetArray(Vec v, PetscScalar **a) { return vec_host_rw(v, a); }
+PetscErrorCode VecRestoreArray(Vec, PetscScalar **a)
+{
+  if (a) *a = nullptr;
+  return 0;
+}
+PetscErrorCode VecGetArrayRead(Vec v, const PetscScalar **a) { return vec_host_read(v, a); }
+PetscErrorCode VecRestoreArrayRead(Vec, const PetscScalar **a)
+{
+  if (a) *a = nullptr;
+  return 0;
+}
+PetscErrorCode VecCUDAGetArray(Vec v, PetscScalar **d) { return vec_dev_rw(v, d); }
+PetscErrorCode VecCUDARestoreArray(Vec, PetscScalar **d)
+{
+  if (d) *d = nullptr;
+  return 0;
+}
+PetscErrorCode VecCUDAGetArrayRead(Vec v, const PetscScalar **d) { return vec_dev_read(v, d); }
+PetscErrorCode VecCUDARestoreArrayRead(Vec, const PetscScalar **d)
+{
+  if (d) *d = nullptr;
+  return 0;
+}
+PetscErrorCode VecSet(Vec v, PetscScalar alpha)
+{
+  double *d;
+  PB_CHK(vec_dev_write(v, &d));
+  v->invalidated = false;
+  return k_set(v->n, d, alpha);
+}
+PetscErrorCode VecZeroEntries(Vec v) { return VecSet(v, 0.0); }
+PetscErrorCode VecCopy(Vec x, Vec y)
+{
+  if (x == y) return 0;
+  if (x->n != y->n) return err(PETSC_ERR_ARG_INCOMP, "VecCopy: local sizes differ");
+  const double *dx;
+  double       *dy;
+  PB_CHK(vec_dev_read(x, &dx));
+  PB_CHK(vec_dev_write(y, &dy));
+  y->invalidated = x->invalidated;
+  return k_copy(x->n, dx, dy);
+}
+PetscErrorCode VecScale(Vec x, PetscScalar alpha)
+{
+  double *d;
+  PB_CHK(vec_dev_rw(x, &d));
+  return k_scale(x->n, d, alpha);
+}
+PetscErrorCode VecAXPY(Vec y, PetscScalar alpha, Vec x)
+{
+  if (x->n != y->n) return err(PETSC_ERR_ARG_INCOMP, "VecAXPY: local sizes differ");
+  const double *dx;
+  double       *dy;
+  PB_CHK(vec_dev_read(x, &dx));
+  PB_CHK(vec_dev_rw(y, &dy));
+  return k_axpy(y->n, dy, alpha, dx);
+}
+PetscErrorCode VecAYPX(Vec y, PetscScalar beta, Vec x)
+{
+  if (x->n != y->n) return err(PETSC_ERR_ARG_INCOMP, "VecAYPX: local sizes differ");
+  const double *dx;
+  double       *dy;
+  PB_CHK(vec_dev_read(x, &dx));
+  PB_CHK(vec_dev_rw(y, &dy));
+  return k_aypx(y->n, dy, beta, dx);
+}
+PetscErrorCode VecWAXPY(Vec w, PetscScalar alpha, Vec x, Vec y)
+{
+  const double *dx, *dy;
+  double       *dw;
+  PB_CHK(vec_dev_read(x, &dx));
+  PB_CHK(vec_dev_read(y, &dy));
+  if (w == x || w == y) PB_CHK(vec_dev_rw(w, &dw));
+  else PB_CHK(vec_dev_write(w, &dw));
+  return k_waxpy(w->n, dw, alpha, dx, dy);
+}
+PetscErrorCode VecPointwiseMax(Vec w, Vec x, Vec y)
+{
+  const double *dx, *dy;
+  double       *dw;
+  PB_CHK(vec_dev_read(x, &dx));
+  PB_CHK(vec_dev_read(y, &dy));
+  if (w == x || w == y) PB_CHK(vec_dev_rw(w, &dw));
+  else PB_CHK(vec_dev_write(w, &dw));
+  return k_pmax(w->n, dw, dx, dy);
+}
+PetscErrorCode VecPointwiseMin(Vec w, Vec x, Vec y)
+{
+  const double *dx, *dy;
+  double       *dw;
+  PB_CHK(vec_dev_read(x, &dx));
+  PB_CHK(vec_dev_read(y, &dy));
+  if (w == x || w == y) PB_CHK(vec_dev_rw(w, &dw));
+  else PB_CHK(vec_dev_write(w, &dw));
+  return k_pmin(w->n, dw, dx, dy);
+}
+PetscErrorCode VecDot(Vec x, Vec y, PetscScalar *val) { return vec_dot(x, y, val); }
+PetscErrorCode VecNorm(Vec x, NormType type, PetscReal *val)
+{
+  if (type != NORM_2) return err(PETSC_ERR_SUP, "only NORM_2 is on the path");
+  return vec_norm2(x, val);
+}
+// VecInvalidate / VecIsInvalidated: src/vec/interface/permonvecutils.c:266,303 ("this multiplier is not computed")
+PetscErrorCode VecInvalidate(Vec vec)
+{
+  vec->invalidated = true;
+  return 0;
+}
+PetscErrorCode VecIsInvalidated(Vec vec, PetscBool *flg)
+{
+  *flg = vec->invalidated ? PETSC_TRUE : PETSC_FALSE;
+  return 0;
+}
+
+// =====================================================================================================
+// Mat
+// =====================================================================================================
+_p_Mat::~_p_Mat()
+{
+  if (kind == MK_AIJ && d_owned) {
+    cudaFree((void *)Ad.ia);
+    cudaFree((void *)Ad.ja);
+    cudaFree((void *)Ad.a);
+  }
+  if (kind == MK_AIJ) {
+    cudaFree((void *)Ao.ia);
+    cudaFree((void *)Ao.ja);
+    cudaFree((void *)Ao.a);
+    cudaFree((void *)Ao.rows);
+  }
+  if (halo) {
+    cudaFree(halo->d_send_idx);
+    cudaFree(halo->d_send);
+    cudaFree(halo->d_ghost);
+    cudaFree(halo->d_skip);
+    if (halo->ev_packed) cudaEventDestroy(halo->ev_packed);
+    if (halo->ev_arrived) cudaEventDestroy(halo->ev_arrived);
+    if (halo->ev_consumed) cudaEventDestroy(halo->ev_consumed);
+    delete halo;
+  }
+  pb::unref(row);
+  pb::unref(M1);
+  pb::unref(M2);
+  pb::unref(twork);
+  pb::unref(A);
+  if (pf && --pf->refct == 0) delete pf;
+}
+
+static int upload_csr(pb::CsrDev &C, int nrows, int ncols, const int *ia, const int *ja, const double *a, const int *rows)
+{
+  const int64_t nnz = ia[nrows];
+  C.n     = nrows;
+  C.ncols = ncols;
+  C.nnz   = nnz;
+  int *dia, *dja;
+  double *da;
+  PB_CUDA(cudaMalloc(&dia, sizeof(int) * (size_t)(nrows + 1)));
+  PB_CUDA(cudaMalloc(&dja, sizeof(int) * (size_t)std::max<int64_t>(nnz, 1)));
+  PB_CUDA(cudaMalloc(&da, sizeof(double) * (size_t)std::max<int64_t>(nnz, 1)));
+  cudaStream_t s = ctx().stream;
+  PB_CUDA(cudaMemcpyAsync(dia, ia, sizeof(int) * (size_t)(nrows + 1), cudaMemcpyHostToDevice, s));
+  PB_CUDA(cudaMemcpyAsync(dja, ja, sizeof(int) * (size_t)nnz, cudaMemcpyHostToDevice, s));
+  PB_CUDA(cudaMemcpyAsync(da, a, sizeof(double) * (size_t)nnz, cudaMemcpyHostToDevice, s));
+  C.ia = dia;
+  C.ja = dja;
+  C.a  = da;
+  if (rows) {
+    int *dr;
+    PB_CUDA(cudaMalloc(&dr, sizeof(int) * (size_t)std::max(nrows, 1)));
+    PB_CUDA(cudaMemcpyAsync(dr, rows, sizeof(int) * (size_t)nrows, cudaMemcpyHostToDevice, s));
+    C.rows = dr;
+  }
+  PB_CHK(spmv_config(C, ia));
+  return 0;
+}
+
+PetscErrorCode MatCreateSeqAIJWithArrays(MPI_Comm comm, PetscInt m, PetscInt n, PetscInt i[], PetscInt j[], PetscScalar a[], Mat *mat)
+{
+  if (comm->size > 1) return MatCreateMPIAIJWithArrays(comm, m, n, PETSC_DECIDE, PETSC_DECIDE, i, j, a, mat);
+  PB_CHK(dev_init());
+  if (!i || (i[m] > 0 && (!j || !a))) return err(PETSC_ERR_ARG_NULL, "null CSR array");
+  _p_Mat *A = new _p_Mat;
+  A->comm = comm;
+  A->kind = MK_AIJ;
+  A->m = A->M = m;
+  A->n = A->N = n;
+  int ierr = upload_csr(A->Ad, m, n, i, j, a, nullptr);
+  if (ierr) {
+    delete A;
+    return ierr;
+  }
+  // the host arrays belong to the caller and may be pageable: make sure the copies have left them
+  PB_CUDA(cudaStreamSynchronize(ctx().stream));
+  *mat = A;
+  return 0;
+}
+
+PetscErrorCode MatCreateSeqAIJCUSPARSEWithArrays(MPI_Comm comm, PetscInt m, PetscInt n, const PetscInt di[], const PetscInt dj[], const PetscScalar da[], Mat *mat)
+{
+  if (comm->size > 1) return err(PETSC_ERR_SUP, "device-array constructor is sequential");
+  PB_CHK(dev_init());
+  _p_Mat *A = new _p_Mat;
+  A->comm = comm;
+  A->kind = MK_AIJ;
+  A->m = A->M = m;
+  A->n = A->N = n;
+  A->d_owned  = false;
+  std::vector<int> hia((size_t)m + 1);
+  PB_CUDA(cudaMemcpy(hia.data(), di, sizeof(int) * (size_t)(m + 1), cudaMemcpyDeviceToHost));
+  A->Ad.n = m;
+  A->Ad.ncols = n;
+  A->Ad.nnz = hia[m];
+  A->Ad.ia = di;
+  A->Ad.ja = dj;
+  A->Ad.a  = da;
+  PB_CHK(spmv_config(A->Ad, hia.data()));
+  *mat = A;
+  return 0;
+}
+
+// Row-partitioned AIJ: split into the diagonal block (local columns) and the off-diagonal block (ghost
+// columns, compressed rows), and build the halo plan -- the layout of PETSc's Mat_MPIAIJ
+// (include/permon/private/petsc/mpiaij.h:49-83: A, B, garray, lvec, Mvctx).
+PetscErrorCode MatCreateMPIAIJWithArrays(MPI_Comm comm, PetscInt m, PetscInt n, PetscInt M, PetscInt N, const PetscInt i[], const PetscInt j[], const PetscScalar a[], Mat *mat)
+{
+  (void)M;
+  (void)N;
+  if (n == PETSC_DECIDE) n = m;
+  if (comm->size == 1) {
+    // one rank: no ghosts possible
+    return MatCreateSeqAIJWithArrays(comm, m, n, const_cast<PetscInt *>(i), const_cast<PetscInt *>(j), const_cast<PetscScalar *>(a), mat);
+  }
+  if (!comm->agi || !comm->agv) return err(PETSC_ERR_ARG_WRONGSTATE, "communicator has no host exchange");
+  const int size = comm->size, rank = comm->rank;
+  std::vector<int64_t> rows_all(size), cols_all(size);
+  if (comm->agi(comm->agctx, m, rows_all.data()) || comm->agi(comm->agctx, n, cols_all.data())) return err(PETSC_ERR_LIB, "host all-gather failed");
+  std::vector<int64_t> rs(size + 1, 0), cs(size + 1, 0);
+  for (int r = 0; r < size; r++) {
+    rs[r + 1] = rs[r] + rows_all[r];
+    cs[r + 1] = cs[r] + cols_all[r];
+  }
+  _p_Mat *A = new _p_Mat;
+  A->comm   = comm;
+  A->kind   = MK_AIJ;
+  A->m      = m;
+  A->n      = n;
+  A->M      = (PetscInt)rs[size];
+  A->N      = (PetscInt)cs[size];
+  A->rstart = (PetscInt)rs[rank];
+  A->cstart = (PetscInt)cs[rank];
+  const PetscInt c0 = A->cstart, c1 = A->cstart + n;
+  const int64_t  nnz = i[m];
+  HaloPlan      *H = new HaloPlan;
+  A->halo          = H;
+  // ghosts
+  std::vector<PetscInt> gh;
+  for (int64_t k = 0; k < nnz; k++)
+    if (j[k] < c0 || j[k] >= c1) gh.push_back(j[k]);
+  std::sort(gh.begin(), gh.end());
+  gh.erase(std::unique(gh.begin(), gh.end()), gh.end());
+  H->garray = gh;
+  // split
+  std::vector<int>    dia(m + 1, 0), dja, oia(1, 0), oja, orow;
+  std::vector<double> da, oa;
+  std::vector<unsigned char> skip(std::max<PetscInt>(m, 1), 0);
+  dja.reserve(nnz);
+  da.reserve(nnz);
+  for (PetscInt r = 0; r < m; r++) {
+    bool has = false;
+    for (PetscInt k = i[r]; k < i[r + 1]; k++) {
+      if (j[k] >= c0 && j[k] < c1) {
+        dja.push_back(j[k] - c0);
+        da.push_back(a[k]);
+      } else {
+        oja.push_back((int)(std::lower_bound(gh.begin(), gh.end(), j[k]) - gh.begin()));
+        oa.push_back(a[k]);
+        has = true;
+      }
+    }
+    dia[r + 1] = (int)dja.size();
+    if (has) {
+      orow.push_back(r);
+      oia.push_back((int)oja.size());
+      skip[r] = 1;
+    }
+  }
+  H->nboundary = (PetscInt)orow.size();
+  // neighbours that own my ghosts
+  H->recv_off.push_back(0);
+  for (size_t g = 0; g < gh.size();) {
+    int owner = (int)(std::upper_bound(cs.begin(), cs.end(), (int64_t)gh[g]) - cs.begin()) - 1;
+    size_t e = g;
+    while (e < gh.size() && gh[e] < cs[owner + 1]) e++;
+    H->neigh.push_back(owner);
+    H->recv_off.push_back((PetscInt)e);
+    g = e;
+  }
+  // everybody publishes its ghost list; I pick what I own => my send lists (in the requester's ghost order)
+  std::vector<int64_t> gbytes(size);
+  if (comm->agi(comm->agctx, (int64_t)(gh.size() * sizeof(PetscInt)), gbytes.data())) return err(PETSC_ERR_LIB, "host all-gather failed");
+  int64_t tot = 0;
+  for (int r = 0; r < size; r++) tot += gbytes[r];
+  std::vector<PetscInt> allg((size_t)(tot / sizeof(PetscInt)) + 1);
+  if (comm->agv(comm->agctx, gh.data(), (int64_t)(gh.size() * sizeof(PetscInt)), allg.data(), gbytes.data())) return err(PETSC_ERR_LIB, "host all-gather failed");
+  {
+    std::vector<PetscInt> sneigh, soff(1, 0), sidx;
+    size_t                off = 0;
+    for (int r = 0; r < size; r++) {
+      size_t cnt = (size_t)(gbytes[r] / sizeof(PetscInt));
+      if (r != rank) {
+        size_t before = sidx.size();
+        for (size_t k = 0; k < cnt; k++) {
+          PetscInt g = allg[off + k];
+          if (g >= c0 && g < c1) sidx.push_back(g - c0);
+        }
+        if (sidx.size() > before) {
+          sneigh.push_back(r);
+          soff.push_back((PetscInt)sidx.size());
+        }
+      }
+      off += cnt;
+    }
+    // symmetric sparsity is assumed (Hessians are symmetric): the ranks I receive from are the ranks I send to
+    if (sneigh != H->neigh) {
+      delete A;
+      return err(PETSC_ERR_SUP, "non-symmetric halo pattern (send and receive neighbour sets differ)");
+    }
+    H->send_off = soff;
+    H->send_idx = sidx;
+  }
+  PB_CHK(dev_init());
+  int ierr = upload_csr(A->Ad, m, n, dia.data(), dja.data(), da.data(), nullptr);
+  if (!ierr) ierr = upload_csr(A->Ao, (int)orow.size(), (int)gh.size(), oia.data(), oja.data(), oa.data(), orow.data());
+  if (ierr) {
+    delete A;
+    return ierr;
+  }
+  PB_CUDA(cudaMalloc(&H->d_send_idx, sizeof(int) * std::max<size_t>(H->send_idx.size(), 1)));
+  PB_CUDA(cudaMalloc(&H->d_send, sizeof(double) * std::max<size_t>(H->send_idx.size(), 1)));
+  PB_CUDA(cudaMalloc(&H->d_ghost, sizeof(double) * std::max<size_t>(gh.size(), 1)));
+  PB_CUDA(cudaMalloc(&H->d_skip, std::max<PetscInt>(m, 1)));
+  PB_CUDA(cudaMemcpyAsync(H->d_send_idx, H->send_idx.data(), sizeof(int) * H->send_idx.size(), cudaMemcpyHostToDevice, ctx().stream));
+  PB_CUDA(cudaMemcpyAsync(H->d_skip, skip.data(), (size_t)m, cudaMemcpyHostToDevice, ctx().stream));
+  PB_CUDA(cudaEventCreateWithFlags(&H->ev_packed, cudaEventDisableTiming));
+  PB_CUDA(cudaEventCreateWithFlags(&H->ev_arrived, cudaEventDisableTiming));
+  PB_CUDA(cudaEventCreateWithFlags(&H->ev_consumed, cudaEventDisableTiming));
+  PB_CUDA(cudaStreamSynchronize(ctx().stream));
+  *mat = A;
+  return 0;
+}
+
+PetscErrorCode MatB200GetHaloInfo(Mat A, PetscInt *nghost, const PetscInt **garray, PetscInt *nneigh, const PetscInt **neigh_rank, const PetscInt **recv_off,
+                                  const PetscInt **send_off, const PetscInt **send_idx, PetscInt *nboundary_rows)
+{
+  static const PetscInt zero = 0;
+  HaloPlan             *H = A->halo;
+  if (nghost) *nghost = H ? (PetscInt)H->garray.size() : 0;
+  if (garray) *garray = H ? H->garray.data() : nullptr;
+  if (nneigh) *nneigh = H ? (PetscInt)H->neigh.size() : 0;
+  if (neigh_rank) *neigh_rank = H ? H->neigh.data() : nullptr;
+  if (recv_off) *recv_off = H ? H->recv_off.data() : &zero;
+  if (send_off) *send_off = H ? H->send_off.data() : &zero;
+  if (send_idx) *send_idx = H ? H->send_idx.data() : nullptr;
+  if (nboundary_rows) *nboundary_rows = H ? H->nboundary : 0;
+  return 0;
+}
+
+// MatCreateOneRow: src/mat/impls/onerow/onerow.c:97-113
+PetscErrorCode MatCreateOneRow(Vec a, Mat *A_new)
+{
+  _p_Mat *A = new _p_Mat;
+  A->comm = a->comm;
+  A->kind = MK_ONEROW;
+  A->row  = a;
+  pb::ref(a);
+  A->m = (a->comm->rank == 0) ? 1 : 0;
+  A->M = 1;
+  A->n = a->n;
+  A->N = a->N;
+  *A_new = A;
+  return 0;
+}
+
+// MatCreateProd: src/mat/impls/composite/matprod.c:42-48 -- product mats[nmat-1]*...*mats[0]
+PetscErrorCode MatCreateProd(MPI_Comm comm, PetscInt nmat, const Mat *mats, Mat *mat)
+{
+  if (nmat == 1) {
+    *mat = mats[0];
+    pb::ref(mats[0]);
+    return 0;
+  }
+  if (nmat != 2) return err(PETSC_ERR_SUP, "MatCreateProd: at most two factors");
+  if (comm->size > 1) return err(PETSC_ERR_SUP, "product operators are single-GPU in this round");
+  Mat M2 = mats[0], M1 = mats[1];
+  if (M1->kind != MK_AIJ || M2->kind != MK_AIJ) return err(PETSC_ERR_SUP, "MatCreateProd: AIJ factors only");
+  if (M1->n != M2->m) return err(PETSC_ERR_ARG_SIZ, "MatCreateProd: inner dimensions differ (%d vs %d)", (int)M1->n, (int)M2->m);
+  _p_Mat *A = new _p_Mat;
+  A->comm = comm;
+  A->kind = MK_PROD;
+  A->M1   = M1;
+  A->M2   = M2;
+  pb::ref(M1);
+  pb::ref(M2);
+  A->m = M1->m;
+  A->M = M1->M;
+  A->n = M2->n;
+  A->N = M2->N;
+  PB_CHK(vec_create(comm, M2->m, M2->m, &A->twork));
+  *mat = A;
+  return 0;
+}
+
+PetscErrorCode MatDestroy(Mat *A)
+{
+  if (!A || !*A) return 0;
+  pb::unref(*A);
+  return 0;
+}
+PetscErrorCode MatGetSize(Mat A, PetscInt *M, PetscInt *N)
+{
+  if (M) *M = A->M;
+  if (N) *N = A->N;
+  return 0;
+}
+PetscErrorCode MatGetLocalSize(Mat A, PetscInt *m, PetscInt *n)
+{
+  if (m) *m = A->m;
+  if (n) *n = A->n;
+  return 0;
+}
+PetscErrorCode MatGetOwnershipRange(Mat A, PetscInt *low, PetscInt *high)
+{
+  if (low) *low = A->rstart;
+  if (high) *high = A->rstart + A->m;
+  return 0;
+}
+PetscErrorCode MatCreateVecs(Mat A, Vec *right, Vec *left)
+{
+  if (right) PB_CHK(vec_create(A->comm, A->n, A->comm->size > 1 ? PETSC_DECIDE : A->n, right));
+  if (left) PB_CHK(vec_create(A->comm, A->m, A->comm->size > 1 ? PETSC_DECIDE : A->m, left));
+  return 0;
+}
+
+namespace pb {
+
+int mat_halo_begin(Mat A, const double *x)
+{
+  HaloPlan *H = A->halo;
+  if (!H || A->comm->size == 1) return 0;
+  DevCtx &c = ctx();
+  if (!H->send_idx.empty()) PB_CHK(k_pack((int)H->send_idx.size(), H->d_send_idx, x, H->d_send));
+  PB_CUDA(cudaEventRecord(H->ev_packed, c.stream));
+  PB_CUDA(cudaStreamWaitEvent(c.comm_stream, H->ev_packed, 0));
+  ncclComm_t nc = (ncclComm_t)A->comm->nccl;
+  if (!nc) return err(PETSC_ERR_ARG_WRONGSTATE, "halo exchange needs NCCL");
+  c.launches++;
+  PB_NCCL(ncclGroupStart());
+  for (size_t q = 0; q < H->neigh.size(); q++) {
+    PB_NCCL(ncclSend(H->d_send + H->send_off[q], (size_t)(H->send_off[q + 1] - H->send_off[q]), ncclDouble, H->neigh[q], nc, c.comm_stream));
+    PB_NCCL(ncclRecv(H->d_ghost + H->recv_off[q], (size_t)(H->recv_off[q + 1] - H->recv_off[q]), ncclDouble, H->neigh[q], nc, c.comm_stream));
+  }
+  PB_NCCL(ncclGroupEnd());
+  PB_CUDA(cudaEventRecord(H->ev_arrived, c.comm_stream));
+  return 0;
+}
+int mat_halo_end(Mat A)
+{
+  HaloPlan *H = A->halo;
+  if (!H || A->comm->size == 1) return 0;
+  PB_CUDA(cudaStreamWaitEvent(ctx().stream, H->ev_arrived, 0));
+  return 0;
+}
+
+int qppf_dense_rows(QPPF pf, const double **Bd, int *m);
+
+int mat_mult_dev(Mat A, const double *x, double *y)
+{
+  switch (A->kind) {
+  case MK_AIJ:
+    PB_CHK(mat_halo_begin(A, x));
+    PB_CHK(k_spmv(A->Ad, x, y, 0));
+    if (A->halo && A->comm->size > 1) {
+      PB_CHK(mat_halo_end(A));
+      PB_CHK(k_spmv(A->Ao, A->halo->d_ghost, y, 1));
+    }
+    return 0;
+  case MK_PROD: {
+    double *t;
+    PB_CHK(vec_dev_write(A->twork, &t));
+    PB_CHK(mat_mult_dev(A->M2, x, t));
+    return mat_mult_dev(A->M1, t, y);
+  }
+  case MK_PENALIZED: {
+    // MatMult_Penalized (src/qp/utils/matpenalized.c:12-22): y = BtB x; y *= rho; y += A x
+    const double *Bd;
+    int           m;
+    PB_CHK(qppf_dense_rows(A->pf, &Bd, &m));
+    Reducer &R = reducer(A->comm);
+    PB_CHK(k_dense_rows_mult(A->n, m, Bd, x, R.rb));
+    PB_CHK(R.gather());
+    // rank-ordered sum of the gathered records on the device is what the fused path does; here: host
+    PB_CHK(R.fetch());
+    double t[PB_MAXEQ];
+    for (int j = 0; j < m; j++) t[j] = R.sum(j);
+    double *dt = R.d_all;   // reuse as device scratch for the m coefficients
+    PB_CUDA(cudaMemcpyAsync(dt, t, sizeof(double) * m, cudaMemcpyHostToDevice, ctx().stream));
+    PB_CHK(mat_mult_dev(A->A, x, y));
+    return k_dense_rows_multT_add(A->n, m, Bd, dt, A->rho, y, 1);
+  }
+  default: return err(PETSC_ERR_SUP, "MatMult: unsupported matrix kind for device vectors");
+  }
+}
+
+int mat_mult(Mat A, Vec x, Vec y)
+{
+  if (A->kind == MK_ONEROW) {   // MatMult_OneRow onerow.c:5-17: z = a . x
+    double d;
+    PB_CHK(vec_dot(A->row, x, &d));
+    if (y->n > 0) {
+      double *h;
+      PB_CHK(vec_host_write(y, &h));
+      h[0] = d;
+    }
+    return 0;
+  }
+  if (x->n != A->n || y->n != A->m) return err(PETSC_ERR_ARG_SIZ, "MatMult: size mismatch (A %dx%d, x %d, y %d)", (int)A->m, (int)A->n, (int)x->n, (int)y->n);
+  const double *dx;
+  double       *dy;
+  PB_CHK(vec_dev_read(x, &dx));
+  PB_CHK(vec_dev_write(y, &dy));
+  return mat_mult_dev(A, dx, dy);
+}
+
+}  // namespace pb
+
+PetscErrorCode MatMult(Mat A, Vec x, Vec y) { return mat_mult(A, x, y); }
+PetscErrorCode MatMultAdd(Mat A, Vec x, Vec y, Vec z)
+{
+  Vec w;
+  PB_CHK(VecDuplicate(z, &w));
+  int ierr = mat_mult(A, x, w);
+  if (!ierr) ierr = VecWAXPY(z, 1.0, w, y);
+  VecDestroy(&w);
+  return ierr;
+}
+PetscErrorCode MatMultTranspose(Mat A, Vec x, Vec y)
+{
+  if (A->kind != MK_ONEROW) return err(PETSC_ERR_SUP, "MatMultTranspose: only MatCreateOneRow matrices");
+  // MatMultTranspose_OneRow onerow.c:41-57: z = a * x[0]  (x broadcast from rank 0)
+  double xv = 0.0;
+  if (A->comm->size == 1) {
+    const double *h;
+    PB_CHK(vec_host_read(x, &h));
+    xv = h[0];
+  } else {
+    double v = 0.0;
+    if (x->n > 0) {
+      const double *h;
+      PB_CHK(vec_host_read(x, &h));
+      v = h[0];
+    }
+    std::vector<int64_t> all(A->comm->size);
+    int64_t              bits;
+    memcpy(&bits, &v, 8);
+    if (A->comm->agi(A->comm->agctx, bits, all.data())) return err(PETSC_ERR_LIB, "host all-gather failed");
+    memcpy(&xv, &all[0], 8);
+  }
+  PB_CHK(VecCopy(A->row, y));
+  return VecScale(y, xv);
+}
+
+// MatGetMaxEigenvalue: src/mat/interface/permonmatutils.c:442-522 (power method, v0 = 1)
+PetscErrorCode MatGetMaxEigenvalue(Mat A, Vec v, PetscReal *lambda_out, PetscReal tol, PetscInt maxits)
+{
+  Vec    Av = nullptr;
+  bool   destroy_v = false;
+  double lambda = 0.0, lambda0, err_, relerr, vAv, vv;
+  if (tol == PETSC_DECIDE || tol == PETSC_DEFAULT) tol = 1e-4;            /* :473 */
+  if (maxits == PETSC_DECIDE || maxits == PETSC_DEFAULT) maxits = 50;     /* :474 */
+  if (!v) {
+    PB_CHK(MatCreateVecs(A, &v, NULL));
+    PB_CHK(VecSet(v, 1.0));                                               /* :477 */
+    destroy_v = true;
+  }
+  PB_CHK(VecDuplicate(v, &Av));
+  for (PetscInt i = 1; i <= maxits; i++) {                                /* :484 */
+    lambda0 = lambda;
+    PB_CHK(mat_mult(A, v, Av));                                           /* :487 */
+    PB_CHK(vec_mdot2(v, Av, v, &vAv, &vv));                               /* :491 */
+    lambda = vAv / vv;                                                    /* :492 */
+    err_   = fabs(lambda - lambda0);                                      /* :504 */
+    relerr = err_ / fabs(lambda);
+    if (relerr < tol) break;                                              /* :506 */
+    PB_CHK(VecCopy(Av, v));                                               /* :509 */
+    PB_CHK(VecScale(v, 1.0 / sqrt(vv)));                                  /* :510 */
+  }
+  if (lambda_out) *lambda_out = lambda;
+  if (destroy_v) VecDestroy(&v);
+  VecDestroy(&Av);
+  return 0;
+}
