@@ -52,7 +52,10 @@ struct CsrDev {
   const int    *ja     = nullptr;  // [nnz] local column ids
   const double *a      = nullptr;  // [nnz]
   const int    *rows   = nullptr;  // optional compressed row list (off-diagonal block): row id of each stored row
-  int           kind   = 0;        // 0: tile-streamed (short rows), 1: vector (W lanes per row)
+  int64_t       nnz_alloc = 0;     // elements of ja / a that may be read (allocation incl. padding)
+  int           ia_alloc = 0;      // entries of ia that may be read
+  int           stages = 2;        // shared-memory stages of the TMA kernel
+  int           kind   = 0;        // 0: tile-streamed plain loads, 1: vector (W lanes per row), 2: TMA-staged tiles
   int           W      = 32;
   int           tile_cap = 0;      // max nnz of a 256-row tile (stream kind)
   int           grid   = 0;        // persistent grid size (fixed => reproducible reductions)

@@ -24,6 +24,7 @@
 #include <string.h>
 
 #include <string>
+#include <type_traits>
 #include <vector>
 
 #include "device.h"
@@ -361,6 +362,164 @@ __global__ void __launch_bounds__(NT) k_spmv_vector(CsrDev A, const double *__re
   epi.finalize(acc);
 }
 
+
+// ---- Blackwell/Hopper async-copy primitives (PTX): mbarrier + 1-D bulk copy global -> shared (TMA engine) -------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+{
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+{
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
+{
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src), "r"(bytes),
+               "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+  uint32_t       ok = 0;
+  const uint32_t addr = smem_u32(bar);
+  for (unsigned spin = 0;; spin++) {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
+    if (ok) break;
+    if (spin > (1u << 24)) __trap();   // a lost transaction must abort the launch, never hang the GPU
+  }
+}
+
+// TMA-staged CSR ("CSR-stream" with the DRAM streams on the copy engine): a producer warp feeds a ring of
+// shared-memory stages with 1-D bulk copies (cp.async.bulk -> UBLKCP) of the tile's values, column indices, row
+// pointers and the row slices of the epilogue vectors; 256 consumer threads (one per row) wait on the stage's
+// mbarrier, gather x through L1/L2, add their segment in storage order and run the fused epilogue.  No LSU address
+// generation for the streamed operands, loads of tile t+1.. overlap the compute of tile t.
+struct TmaStage {   // byte offsets inside one stage
+  int a_off, v_off, ja_off, ia_off, bytes;
+};
+__host__ __device__ inline TmaStage tma_stage_layout(int cap, int nv)
+{
+  TmaStage L;
+  L.a_off  = 0;
+  L.v_off  = cap * 8;
+  L.ja_off = L.v_off + nv * TR * 8;
+  L.ia_off = L.ja_off + cap * 4;
+  L.bytes  = L.ia_off + (TR + 4) * 4;
+  L.bytes  = (L.bytes + 127) & ~127;
+  return L;
+}
+static constexpr int TMA_MAX_STAGES = 4;
+
+template <class Epi>
+__global__ void __launch_bounds__(NT + 32) k_spmv_tma(CsrDev A, const double *__restrict__ x, Epi epi, int cap, int nstages)
+{
+  if (!epi.active()) return;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  __shared__ uint64_t full_bar[TMA_MAX_STAGES], empty_bar[TMA_MAX_STAGES];
+  __shared__ int      meta_k0a[TMA_MAX_STAGES];
+  const int      nv = epi.nvec();
+  const TmaStage L = tma_stage_layout(cap, nv);
+  const int      ntiles = (A.n + TR - 1) / TR;
+  const int      warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  typename Epi::Acc acc;
+  epi.init(acc);
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < nstages; s++) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], NT / 32);
+    }
+    mbar_fence_init();
+  }
+  __syncthreads();
+
+  if (warp == NT / 32) {
+    // ------------------------------ producer warp ------------------------------
+    int k0n = 0, k1n = 0;
+    if (blockIdx.x < ntiles) {
+      const int r0 = blockIdx.x * TR, r1 = min(r0 + TR, A.n);
+      k0n = __ldg(A.ia + r0);
+      k1n = __ldg(A.ia + r1);
+    }
+    int i = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, i++) {
+      const int s = i % nstages;
+      const int k0 = k0n, k1 = k1n;
+      const int nt = tile + gridDim.x;
+      if (nt < ntiles) {   // metadata of the next tile: in flight while this one is issued
+        const int q0 = nt * TR, q1 = min(q0 + TR, A.n);
+        k0n = __ldg(A.ia + q0);
+        k1n = __ldg(A.ia + q1);
+      }
+      if (i >= nstages) mbar_wait(&empty_bar[s], ((i / nstages) & 1) ^ 1);
+      unsigned char *st = smem_raw + (size_t)s * L.bytes;
+      const int      r0 = tile * TR, r1 = min(r0 + TR, A.n);
+      const int      k0a = k0 & ~3;
+      const int      na = (k1 - k0a + 3) & ~3;
+      const bool     tma = (r1 - r0 == TR) && ((int64_t)k0a + na <= A.nnz_alloc) && (r0 + TR + 4 <= A.ia_alloc) && (na <= cap);
+      if (tma) {
+        if (lane == 0) {
+          meta_k0a[s] = k0a;
+          const uint32_t bytes = (uint32_t)na * 12u + (uint32_t)(TR + 4) * 4u + (uint32_t)nv * TR * 8u;
+          mbar_arrive_expect_tx(&full_bar[s], bytes);
+          if (na > 0) {
+            bulk_g2s(st + L.a_off, A.a + k0a, (uint32_t)na * 8u, &full_bar[s]);
+            bulk_g2s(st + L.ja_off, A.ja + k0a, (uint32_t)na * 4u, &full_bar[s]);
+          }
+          bulk_g2s(st + L.ia_off, A.ia + r0, (uint32_t)(TR + 4) * 4u, &full_bar[s]);
+          for (int v = 0; v < nv; v++) bulk_g2s(st + L.v_off + (size_t)v * TR * 8, epi.vsrc(v) + r0, (uint32_t)TR * 8u, &full_bar[s]);
+        }
+      } else {
+        // boundary tile (partial rows / end of the arrays): the warp loads it with plain loads
+        double *a_s = (double *)(st + L.a_off);
+        int    *ja_s = (int *)(st + L.ja_off), *ia_s = (int *)(st + L.ia_off);
+        for (int k = k0 + lane; k < k1; k += 32) {
+          a_s[k - k0a]  = __ldg(A.a + k);
+          ja_s[k - k0a] = __ldg(A.ja + k);
+        }
+        for (int t = lane; t <= r1 - r0; t += 32) ia_s[t] = __ldg(A.ia + r0 + t);
+        for (int v = 0; v < nv; v++) {
+          double       *vs = (double *)(st + L.v_off) + (size_t)v * TR;
+          const double *src = epi.vsrc(v) + r0;
+          for (int t = lane; t < r1 - r0; t += 32) vs[t] = src[t];
+        }
+        __syncwarp();
+        if (lane == 0) {
+          meta_k0a[s] = k0a;
+          mbar_arrive(&full_bar[s]);
+        }
+      }
+    }
+  } else {
+    // ------------------------------ consumer warps: one thread per row ------------------------------
+    int i = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, i++) {
+      const int s = i % nstages;
+      mbar_wait(&full_bar[s], (i / nstages) & 1);
+      unsigned char *st = smem_raw + (size_t)s * L.bytes;
+      const double  *a_s = (const double *)(st + L.a_off);
+      const int     *ja_s = (const int *)(st + L.ja_off), *ia_s = (const int *)(st + L.ia_off);
+      const double  *vs = (const double *)(st + L.v_off);
+      const int      k0a = meta_k0a[s];
+      const int      r = tile * TR + threadIdx.x;
+      if (r < A.n) {
+        const int ks = ia_s[threadIdx.x] - k0a, ke = ia_s[threadIdx.x + 1] - k0a;
+        double    sum = 0.0;
+        for (int k = ks; k < ke; k++) sum += a_s[k] * __ldg(x + ja_s[k]);
+        epi.row_s(r, threadIdx.x, sum, vs, acc);
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty_bar[s]);
+    }
+  }
+  epi.finalize(acc);
+}
+
 template <class K>
 static int occ_blocks(K kernel, size_t smem)
 {
@@ -382,6 +541,62 @@ static void launch_vector(const CsrDev &A, const double *x, const Epi &epi)
   k_spmv_vector<Epi, W><<<(int)grid, NT, 0, g_ctx.stream>>>(A, x, epi);
 }
 
+
+template <class Epi, class = void>
+struct EpiHasStaged : std::false_type {};
+template <class Epi>
+struct EpiHasStaged<Epi, std::void_t<decltype(std::declval<const Epi &>().nvec())>> : std::true_type {};
+
+static bool aligned16(const void *p) { return (((uintptr_t)p) & 15) == 0; }
+
+template <class Epi>
+static void launch_tma(const CsrDev &A, const double *x, const Epi &epi)
+{
+  if constexpr (!EpiHasStaged<Epi>::value) {
+    // epilogues without a staged-vector interface (ghost pass) use the plain streamed kernel
+    size_t smem = (size_t)A.tile_cap * sizeof(double);
+    int    occ = occ_blocks(k_spmv_stream<Epi>, smem);
+    int    ntiles = (A.n + TR - 1) / TR, grid = g_ctx.sm_count * occ;
+    if (grid > ntiles) grid = ntiles;
+    k_spmv_stream<Epi><<<grid, NT, smem, g_ctx.stream>>>(A, x, epi);
+  } else {
+    // host mirror of the epilogue's vector list: all sources must be 16-byte aligned for cp.async.bulk
+    const int nv = epi.nvec_host();
+    bool      ok = aligned16(A.a) && aligned16(A.ja) && aligned16(A.ia);
+    for (int v = 0; v < nv && ok; v++) ok = aligned16(epi.vsrc_host(v));
+    const int      cap = A.tile_cap;
+    const TmaStage L = tma_stage_layout(cap, nv);
+    int            nstages = A.stages > 0 ? A.stages : 2;
+    if (nstages > TMA_MAX_STAGES) nstages = TMA_MAX_STAGES;
+    size_t smem = (size_t)L.bytes * nstages;
+    if (!ok || smem > 200 * 1024) {
+      size_t sm1 = (size_t)A.tile_cap * sizeof(double);
+      int    occ = occ_blocks(k_spmv_stream<Epi>, sm1);
+      int    ntiles = (A.n + TR - 1) / TR, grid = g_ctx.sm_count * occ;
+      if (grid > ntiles) grid = ntiles;
+      k_spmv_stream<Epi><<<grid, NT, sm1, g_ctx.stream>>>(A, x, epi);
+      return;
+    }
+    static size_t attr_smem = 0;
+    if (smem > attr_smem) {
+      cudaFuncSetAttribute(k_spmv_tma<Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      attr_smem = smem;
+    }
+    static int    occ = 0;
+    static size_t occ_smem = (size_t)-1;
+    if (!occ || occ_smem != smem) {
+      int nb = 0;
+      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_spmv_tma<Epi>, NT + 32, smem) != cudaSuccess || nb < 1) nb = 1;
+      occ      = nb;
+      occ_smem = smem;
+    }
+    int ntiles = (A.n + TR - 1) / TR, grid = g_ctx.sm_count * occ;
+    if (grid > ntiles) grid = ntiles;
+    if (grid > max_red_blocks()) grid = max_red_blocks();
+    k_spmv_tma<Epi><<<grid, NT + 32, smem, g_ctx.stream>>>(A, x, epi, cap, nstages);
+  }
+}
+
 template <class Epi>
 static int launch_spmv(const CsrDev &A, const double *x, const Epi &epi, int family, double bytes)
 {
@@ -389,6 +604,8 @@ static int launch_spmv(const CsrDev &A, const double *x, const Epi &epi, int fam
   if (A.n == 0) {
     // still run one CTA so that reductions publish their (identity) record
     k_spmv_vector<Epi, 32><<<1, NT, 0, g_ctx.stream>>>(A, x, epi);
+  } else if (A.kind == 2) {
+    launch_tma(A, x, epi);
   } else if (A.kind == 0) {
     static int    occ = 0;
     static size_t occ_smem = (size_t)-1;
@@ -435,9 +652,12 @@ int spmv_config(CsrDev &A, const int *h_ia)
   bool         stream = (cap <= 5632 && maxrow <= 64);   // <= 44 KB of products per tile
   if (force && !strcmp(force, "vector")) stream = false;
   if (stream) {
-    A.kind     = 0;
-    A.tile_cap = (cap + 31) & ~31;
+    A.kind     = 2;   // TMA-staged; "stream" forces the plain-load variant for A/B measurements
+    if ((force && !strcmp(force, "stream")) || A.rows) A.kind = 0;
+    A.tile_cap = (cap + 3 + 31) & ~31;   // +3: the tile copy starts at a 16-byte aligned element
     if (A.tile_cap < 32) A.tile_cap = 32;
+    const char *st = getenv("PERMON_B200_STAGES");
+    A.stages = st ? atoi(st) : 2;
   } else {
     A.kind = 1;
     int W  = 32;
@@ -459,6 +679,11 @@ struct EpiPlain {
   __device__ void init(Acc &) const {}
   __device__ void row(int r, double ax, Acc &) const { y[r] = accumulate ? y[r] + ax : ax; }
   __device__ void finalize(Acc &) const {}
+  __host__ __device__ int  nvec() const { return 0; }
+  __host__ __device__ const double *vsrc(int) const { return nullptr; }
+  int nvec_host() const { return nvec(); }
+  const double *vsrc_host(int i) const { return vsrc(i); }
+  __device__ void row_s(int r, int, double ax, const double *, Acc &a) const { row(r, ax, a); }
 };
 
 struct EpiGated {   // plain SpMV that only runs in the right phase of the device-driven iteration
@@ -474,6 +699,11 @@ struct EpiGated {   // plain SpMV that only runs in the right phase of the devic
   __device__ void init(Acc &) const {}
   __device__ void row(int r, double ax, Acc &) const { y[r] = ax; }
   __device__ void finalize(Acc &) const {}
+  __host__ __device__ int  nvec() const { return 0; }
+  __host__ __device__ const double *vsrc(int) const { return nullptr; }
+  int nvec_host() const { return nvec(); }
+  const double *vsrc_host(int i) const { return vsrc(i); }
+  __device__ void row_s(int r, int, double ax, const double *, Acc &a) const { row(r, ax, a); }
 };
 
 struct AccRed {
@@ -513,6 +743,42 @@ struct EpiA {
     epilogue(r, ax, a);
   }
   __device__ void finalize(Acc &a) const { grid_reduce8<(1 << RA_FEAS)>(a.v, rb, nullptr); }
+  // staged row vectors for the TMA kernel: p, g, x, [lb], [ub], [B_0..B_{m-1}]
+  __host__ __device__ int nvec() const { return 3 + (bx.lb ? 1 : 0) + (bx.ub ? 1 : 0) + m; }
+  int nvec_host() const { return nvec(); }
+  const double *vsrc_host(int i) const { return vsrc(i); }
+  __host__ __device__ const double *vsrc(int i) const
+  {
+    if (i == 0) return p;
+    if (i == 1) return g;
+    if (i == 2) return x;
+    int k = 3;
+    if (bx.lb) {
+      if (i == k) return bx.lb;
+      k++;
+    }
+    if (bx.ub) {
+      if (i == k) return bx.ub;
+      k++;
+    }
+    return B + (size_t)(i - k) * n;
+  }
+  __device__ void row_s(int r, int t, double ax, const double *vs, Acc &a) const
+  {
+    Ap[r] = ax;
+    if (skip && skip[r]) return;
+    const double pr = vs[t];
+    a.v[RA_PAP] += pr * ax;
+    a.v[RA_GP] += vs[TR + t] * pr;
+    BoxVal b;
+    int    k = 3;
+    b.has_lb = bx.lb != nullptr;
+    b.has_ub = bx.ub != nullptr;
+    b.lb     = b.has_lb ? vs[(k++) * TR + t] : 0.0;
+    b.ub     = b.has_ub ? vs[(k++) * TR + t] : 0.0;
+    for (int j = 0; j < m; j++) a.v[RA_BP + j] += vs[(k + j) * TR + t] * pr;
+    a.v[RA_FEAS] = box_feas(vs[2 * TR + t], pr, b, a.v[RA_FEAS]);
+  }
 };
 
 // K_A' epilogue: g_r = (A x)_r + rho (B^T Bu)_r - b_r ; split ; p = gf ; |gP|^2 |gc|^2 |gf|^2
@@ -559,6 +825,53 @@ struct EpiA2 {
     epilogue(r, ax, a);
   }
   __device__ void finalize(Acc &a) const { grid_reduce8<0>(a.v, rb, nullptr); }
+  // staged row vectors for the TMA kernel: x, b, [lb], [ub], [B_0..B_{m-1}]
+  __host__ __device__ int nvec() const { return 2 + (bx.lb ? 1 : 0) + (bx.ub ? 1 : 0) + m; }
+  int nvec_host() const { return nvec(); }
+  const double *vsrc_host(int i) const { return vsrc(i); }
+  __host__ __device__ const double *vsrc(int i) const
+  {
+    if (i == 0) return x;
+    if (i == 1) return b;
+    int k = 2;
+    if (bx.lb) {
+      if (i == k) return bx.lb;
+      k++;
+    }
+    if (bx.ub) {
+      if (i == k) return bx.ub;
+      k++;
+    }
+    return B + (size_t)(i - k) * n;
+  }
+  __device__ void row_s(int r, int t, double ax, const double *vs, Acc &a) const
+  {
+    if (skip && skip[r]) {
+      g[r] = ax;
+      return;
+    }
+    BoxVal bv;
+    int    k = 2;
+    bv.has_lb = bx.lb != nullptr;
+    bv.has_ub = bx.ub != nullptr;
+    bv.lb     = bv.has_lb ? vs[(k++) * TR + t] : 0.0;
+    bv.ub     = bv.has_ub ? vs[(k++) * TR + t] : 0.0;
+    double gr = ax;
+    if (m > 0) {
+      double tt = 0.0;
+      for (int j = 0; j < m; j++) tt += vs[(k + j) * TR + t] * S->Bu[j];
+      gr += S->rho * tt;
+    }
+    gr -= vs[TR + t];
+    double gf, gc;
+    box_split(vs[t], gr, bv, bx.astol, gf, gc);
+    g[r] = gr;
+    p[r] = gf;
+    const double gP = gf + gc;
+    a.v[RB_GP2] += gP * gP;
+    a.v[RB_GC2] += gc * gc;
+    a.v[RB_GF2] += gf * gf;
+  }
 };
 
 // ghost pass (multi-GPU): add the off-diagonal block product to the parked partial result, then run the

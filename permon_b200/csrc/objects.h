@@ -64,6 +64,13 @@ struct HaloPlan {
   unsigned char        *d_skip = nullptr;   // [n] 1 for rows with ghost columns
   PetscInt              nboundary = 0;
   cudaEvent_t           ev_packed = nullptr, ev_arrived = nullptr, ev_consumed = nullptr;
+  // host copy of the split matrix, kept until the first device use (lets the plan be built and inspected
+  // without a GPU; the arithmetic still needs one)
+  struct HostSplit {
+    std::vector<int>           dia, dja, oia, oja, orow;
+    std::vector<double>        da, oa;
+    std::vector<unsigned char> skip;
+  } *host = nullptr;
 };
 
 enum MatKind { MK_AIJ = 0, MK_ONEROW, MK_PROD, MK_PENALIZED };
@@ -223,6 +230,7 @@ int  vec_norm2(Vec x, double *val);
 int  vec_mdot2(Vec x, Vec y0, Vec y1, double *v0, double *v1);
 int  mat_mult(Mat A, Vec x, Vec y);
 int  mat_mult_dev(Mat A, const double *x, double *y);        // raw device pointers (local lengths)
+int  mat_ensure_device(Mat A);                               // upload a lazily kept host split (multi-rank AIJ)
 int  mat_halo_begin(Mat A, const double *x);                 // pack + post send/recv on the comm stream
 int  mat_halo_end(Mat A);                                    // make the compute stream wait for the ghosts
 int  box_dev(QPC qpc, BoxDev *bx);

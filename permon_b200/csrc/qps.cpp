@@ -633,6 +633,7 @@ int MpgpImpl::solve_fused(QPS qps)
   QP  qp = qps->solQP;
   Mat A = qp->A, base = A;
   PB_CHK(engine_init(qps));
+  PB_CHK(mat_ensure_device(A));
   cudaStream_t s = ctx().stream;
 
   MpgpVecs v;

@@ -835,6 +835,7 @@ _p_Mat::~_p_Mat()
     if (halo->ev_packed) cudaEventDestroy(halo->ev_packed);
     if (halo->ev_arrived) cudaEventDestroy(halo->ev_arrived);
     if (halo->ev_consumed) cudaEventDestroy(halo->ev_consumed);
+    delete halo->host;
     delete halo;
   }
   pb::unref(row);
@@ -853,9 +854,15 @@ static int upload_csr(pb::CsrDev &C, int nrows, int ncols, const int *ia, const 
   C.nnz   = nnz;
   int *dia, *dja;
   double *da;
-  PB_CUDA(cudaMalloc(&dia, sizeof(int) * (size_t)(nrows + 1)));
-  PB_CUDA(cudaMalloc(&dja, sizeof(int) * (size_t)std::max<int64_t>(nnz, 1)));
-  PB_CUDA(cudaMalloc(&da, sizeof(double) * (size_t)std::max<int64_t>(nnz, 1)));
+  // 8 elements of padding: the TMA kernel copies 16-byte aligned, 16-byte granular tile ranges
+  PB_CUDA(cudaMalloc(&dia, sizeof(int) * (size_t)(nrows + 1 + 8)));
+  PB_CUDA(cudaMalloc(&dja, sizeof(int) * (size_t)(nnz + 8)));
+  PB_CUDA(cudaMalloc(&da, sizeof(double) * (size_t)(nnz + 8)));
+  PB_CUDA(cudaMemsetAsync(dia + nrows + 1, 0, sizeof(int) * 8, ctx().stream));
+  PB_CUDA(cudaMemsetAsync(dja + nnz, 0, sizeof(int) * 8, ctx().stream));
+  PB_CUDA(cudaMemsetAsync(da + nnz, 0, sizeof(double) * 8, ctx().stream));
+  C.nnz_alloc = nnz + 8;
+  C.ia_alloc  = nrows + 1 + 8;
   cudaStream_t s = ctx().stream;
   PB_CUDA(cudaMemcpyAsync(dia, ia, sizeof(int) * (size_t)(nrows + 1), cudaMemcpyHostToDevice, s));
   PB_CUDA(cudaMemcpyAsync(dja, ja, sizeof(int) * (size_t)nnz, cudaMemcpyHostToDevice, s));
@@ -912,6 +919,8 @@ PetscErrorCode MatCreateSeqAIJCUSPARSEWithArrays(MPI_Comm comm, PetscInt m, Pets
   A->Ad.ia = di;
   A->Ad.ja = dj;
   A->Ad.a  = da;
+  A->Ad.nnz_alloc = hia[m];   // caller-owned arrays: nothing beyond the last entry may be touched
+  A->Ad.ia_alloc  = m + 1;
   PB_CHK(spmv_config(A->Ad, hia.data()));
   *mat = A;
   return 0;
@@ -959,9 +968,13 @@ PetscErrorCode MatCreateMPIAIJWithArrays(MPI_Comm comm, PetscInt m, PetscInt n, 
   gh.erase(std::unique(gh.begin(), gh.end()), gh.end());
   H->garray = gh;
   // split
-  std::vector<int>    dia(m + 1, 0), dja, oia(1, 0), oja, orow;
-  std::vector<double> da, oa;
-  std::vector<unsigned char> skip(std::max<PetscInt>(m, 1), 0);
+  H->host = new HaloPlan::HostSplit;
+  std::vector<int>    &dia = H->host->dia, &dja = H->host->dja, &oia = H->host->oia, &oja = H->host->oja, &orow = H->host->orow;
+  std::vector<double> &da = H->host->da, &oa = H->host->oa;
+  std::vector<unsigned char> &skip = H->host->skip;
+  dia.assign(m + 1, 0);
+  oia.assign(1, 0);
+  skip.assign(std::max<PetscInt>(m, 1), 0);
   dja.reserve(nnz);
   da.reserve(nnz);
   for (PetscInt r = 0; r < m; r++) {
@@ -1027,26 +1040,43 @@ PetscErrorCode MatCreateMPIAIJWithArrays(MPI_Comm comm, PetscInt m, PetscInt n, 
     H->send_off = soff;
     H->send_idx = sidx;
   }
-  PB_CHK(dev_init());
-  int ierr = upload_csr(A->Ad, m, n, dia.data(), dja.data(), da.data(), nullptr);
-  if (!ierr) ierr = upload_csr(A->Ao, (int)orow.size(), (int)gh.size(), oia.data(), oja.data(), oa.data(), orow.data());
-  if (ierr) {
-    delete A;
-    return ierr;
+  A->Ad.n = m;   // sizes are known; the arrays reach the device on first use (mat_ensure_device)
+  A->Ad.ncols = n;
+  A->Ad.nnz = (int64_t)dja.size();
+  *mat = A;
+  return 0;
+}
+
+namespace pb {
+int mat_ensure_device(Mat A)
+{
+  if (A->kind == MK_PROD) {
+    PB_CHK(mat_ensure_device(A->M1));
+    return mat_ensure_device(A->M2);
   }
+  if (A->kind == MK_PENALIZED) return mat_ensure_device(A->A);
+  if (A->kind != MK_AIJ || !A->halo || !A->halo->host) return 0;
+  HaloPlan            *H = A->halo;
+  HaloPlan::HostSplit *S = H->host;
+  PB_CHK(dev_init());
+  const PetscInt m = A->m;
+  PB_CHK(upload_csr(A->Ad, m, A->n, S->dia.data(), S->dja.data(), S->da.data(), nullptr));
+  PB_CHK(upload_csr(A->Ao, (int)S->orow.size(), (int)H->garray.size(), S->oia.data(), S->oja.data(), S->oa.data(), S->orow.data()));
   PB_CUDA(cudaMalloc(&H->d_send_idx, sizeof(int) * std::max<size_t>(H->send_idx.size(), 1)));
   PB_CUDA(cudaMalloc(&H->d_send, sizeof(double) * std::max<size_t>(H->send_idx.size(), 1)));
-  PB_CUDA(cudaMalloc(&H->d_ghost, sizeof(double) * std::max<size_t>(gh.size(), 1)));
+  PB_CUDA(cudaMalloc(&H->d_ghost, sizeof(double) * std::max<size_t>(H->garray.size(), 1)));
   PB_CUDA(cudaMalloc(&H->d_skip, std::max<PetscInt>(m, 1)));
   PB_CUDA(cudaMemcpyAsync(H->d_send_idx, H->send_idx.data(), sizeof(int) * H->send_idx.size(), cudaMemcpyHostToDevice, ctx().stream));
-  PB_CUDA(cudaMemcpyAsync(H->d_skip, skip.data(), (size_t)m, cudaMemcpyHostToDevice, ctx().stream));
+  PB_CUDA(cudaMemcpyAsync(H->d_skip, S->skip.data(), (size_t)m, cudaMemcpyHostToDevice, ctx().stream));
   PB_CUDA(cudaEventCreateWithFlags(&H->ev_packed, cudaEventDisableTiming));
   PB_CUDA(cudaEventCreateWithFlags(&H->ev_arrived, cudaEventDisableTiming));
   PB_CUDA(cudaEventCreateWithFlags(&H->ev_consumed, cudaEventDisableTiming));
   PB_CUDA(cudaStreamSynchronize(ctx().stream));
-  *mat = A;
+  delete S;
+  H->host = nullptr;
   return 0;
 }
+}  // namespace pb
 
 PetscErrorCode MatB200GetHaloInfo(Mat A, PetscInt *nghost, const PetscInt **garray, PetscInt *nneigh, const PetscInt **neigh_rank, const PetscInt **recv_off,
                                   const PetscInt **send_off, const PetscInt **send_idx, PetscInt *nboundary_rows)
@@ -1176,6 +1206,7 @@ int mat_mult_dev(Mat A, const double *x, double *y)
 {
   switch (A->kind) {
   case MK_AIJ:
+    PB_CHK(mat_ensure_device(A));
     PB_CHK(mat_halo_begin(A, x));
     PB_CHK(k_spmv(A->Ad, x, y, 0));
     if (A->halo && A->comm->size > 1) {
