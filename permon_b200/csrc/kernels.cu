@@ -157,6 +157,8 @@ int prof_get(int f, int64_t *launches, double *ms, double *bytes_per_launch)
     if (e_ != cudaSuccess) return cuda_fail(e_, "kernel launch", __FILE__, __LINE__); \
   } while (0)
 
+static bool aligned16(const void *p) { return (((uintptr_t)p) & 15) == 0; }
+
 static constexpr int NT = 256;   // threads per CTA everywhere
 static constexpr int TR = 256;   // rows per SpMV tile (stream kind)
 
@@ -547,7 +549,6 @@ struct EpiHasStaged : std::false_type {};
 template <class Epi>
 struct EpiHasStaged<Epi, std::void_t<decltype(std::declval<const Epi &>().nvec())>> : std::true_type {};
 
-static bool aligned16(const void *p) { return (((uintptr_t)p) & 15) == 0; }
 
 template <class Epi>
 static void launch_tma(const CsrDev &A, const double *x, const Epi &epi)
@@ -955,65 +956,131 @@ int k_fused_A_ghost(const CsrDev &Ao, const double *ghost, const MpgpVecs &v, co
 // =====================================================================================================
 // K_B: fused step  (mpgp.c:553-555 CG, :633-638 proportioning, :316-321 expansion std/fixed)
 // =====================================================================================================
-__global__ void __launch_bounds__(NT) k_update_B(MpgpVecs v, const MpgpCtl *__restrict__ S, RedBuf rb)
+// one element of the c / p update (mpgp.c:553-558 CG, :633-638 proportioning)
+template <bool EQ>
+__device__ __forceinline__ void update_cp_elem(int step, double acg, double astol, double xr, double pr, double g0, double apr, const BoxVal &b, const double *brow, int m,
+                                               double &xn, double &gn, double &gf, double *acc)
+{
+  double gc;
+  xn = xr - acg * pr;
+  gn = g0 - acg * apr;
+  box_split(xn, gn, b, astol, gf, gc);
+  if (step == 'c') acc[RB_APGF] += apr * gf;
+  const double gP = gf + gc;
+  acc[RB_GP2] += gP * gP;
+  acc[RB_GC2] += gc * gc;
+  acc[RB_GF2] += gf * gf;
+  if (EQ) {
+#pragma unroll
+    for (int j = 0; j < PB_MAXEQ; j++)
+      if (j < m) acc[RB_BU + j] += brow[j] * xn;
+  }
+}
+// one element of the expansion half step + reduced-gradient step (mpgp.c:316-321, std / fixed length)
+template <bool EQ>
+__device__ __forceinline__ double update_e_elem(double afeas, double alpha, double astol, double xr, double pr, double g0, double apr, const BoxVal &b, const double *brow, int m,
+                                                double *acc)
+{
+  const double xh = xr - afeas * pr;
+  const double gh = g0 - afeas * apr;
+  double       gf, gc;
+  box_split(xh, gh, b, astol, gf, gc);
+  const double grd = box_reduced(xh, gf, b, alpha);
+  const double xn  = xh - alpha * grd;
+  if (EQ) {
+#pragma unroll
+    for (int j = 0; j < PB_MAXEQ; j++)
+      if (j < m) acc[RB_BU + j] += brow[j] * xn;
+  }
+  return xn;
+}
+template <bool EQ>
+__device__ __forceinline__ double penal_apr(double apr, double rho, const double *B, int n, int r, int m, const double *bp, double *brow)
+{   // A_rho p = A p + rho B^T (B p)   (matpenalized.c:12-22)
+  if (!EQ) return apr;
+  double t = 0.0;
+#pragma unroll
+  for (int j = 0; j < PB_MAXEQ; j++) {
+    brow[j] = (j < m) ? B[(size_t)j * n + r] : 0.0;
+    t += brow[j] * bp[j];
+  }
+  return apr + rho * t;
+}
+
+// K_B.  EQ: equality rows present (SMALXE inner solve).  VEC2: 16-byte accesses (n even, pointers 16-byte aligned).
+template <bool EQ, bool VEC2>
+__global__ void __launch_bounds__(NT, EQ ? 3 : 5) k_update_B(MpgpVecs v, const MpgpCtl *__restrict__ S, RedBuf rb)
 {
   if (S->reason != 0) return;
   const int    step = S->step;
   const double acg = S->acg, afeas = S->afeas, alpha = S->alpha, rho = S->rho, astol = v.bx.astol;
   const int    m = v.m, n = v.n;
-  double       bp[PB_MAXEQ];
+  double       bp[PB_MAXEQ] = {0.0, 0.0, 0.0, 0.0};
+  if (EQ) {
 #pragma unroll
-  for (int j = 0; j < PB_MAXEQ; j++) bp[j] = (j < m) ? S->Bp[j] : 0.0;
+    for (int j = 0; j < PB_MAXEQ; j++) bp[j] = (j < m) ? S->Bp[j] : 0.0;
+  }
   double acc[PB_NRED];
 #pragma unroll
   for (int k = 0; k < PB_NRED; k++) acc[k] = 0.0;
+  const bool has_lb = v.bx.lb != nullptr, has_ub = v.bx.ub != nullptr;
+  const int  stride = gridDim.x * NT;
 
-  const int stride = gridDim.x * NT;
-  for (int r = blockIdx.x * NT + threadIdx.x; r < n; r += stride) {
-    const double xr = v.x[r], pr = v.p[r], gr0 = v.g[r];
-    double       apr = v.Ap[r];
-    double       brow[PB_MAXEQ] = {0.0, 0.0, 0.0, 0.0};
-    if (m > 0) {   // A_rho p = A p + rho B^T (B p)
-      double t = 0.0;
-#pragma unroll
-      for (int j = 0; j < PB_MAXEQ; j++) {
-        brow[j] = (j < m) ? v.B[(size_t)j * n + r] : 0.0;
-        t += brow[j] * bp[j];
+  if (VEC2) {
+    const int      n2 = n >> 1;
+    const double2 *x2 = reinterpret_cast<const double2 *>(v.x), *p2 = reinterpret_cast<const double2 *>(v.p), *g2 = reinterpret_cast<const double2 *>(v.g),
+                  *A2 = reinterpret_cast<const double2 *>(v.Ap), *l2 = reinterpret_cast<const double2 *>(v.bx.lb), *u2 = reinterpret_cast<const double2 *>(v.bx.ub);
+    double2 *xo = reinterpret_cast<double2 *>(v.x), *go = reinterpret_cast<double2 *>(v.g), *fo = reinterpret_cast<double2 *>(v.gf), *po = reinterpret_cast<double2 *>(v.p);
+    for (int i = blockIdx.x * NT + threadIdx.x; i < n2; i += stride) {
+      const double2 xr = x2[i], pr = p2[i], g0 = g2[i], ap = A2[i];
+      BoxVal        b0, b1;
+      b0.has_lb = b1.has_lb = has_lb;
+      b0.has_ub = b1.has_ub = has_ub;
+      b0.lb = b1.lb = b0.ub = b1.ub = 0.0;
+      if (has_lb) {
+        const double2 t = l2[i];
+        b0.lb = t.x;
+        b1.lb = t.y;
       }
-      apr += rho * t;
-    }
-    const BoxVal b = load_box(v.bx, r);
-    if (step == 'e') {
-      const double xh = xr - afeas * pr;          // mpgp.c:316
-      const double gh = gr0 - afeas * apr;        // mpgp.c:317
-      double       gf, gc;
-      box_split(xh, gh, b, astol, gf, gc);        // mpgp.c:318
-      const double grd = box_reduced(xh, gf, b, alpha);
-      const double xn  = xh - alpha * grd;        // mpgp.c:321
-      v.x[r]           = xn;
-#pragma unroll
-      for (int j = 0; j < PB_MAXEQ; j++)
-        if (j < m) acc[RB_BU + j] += brow[j] * xn;
-    } else {
-      const double xn = xr - acg * pr;            // mpgp.c:553 / :633
-      const double gn = gr0 - acg * apr;          // mpgp.c:554 / :634
-      double       gf, gc;
-      box_split(xn, gn, b, astol, gf, gc);        // mpgp.c:555 / :635
-      v.x[r] = xn;
-      v.g[r] = gn;
-      if (step == 'c') {
-        v.gf[r] = gf;
-        acc[RB_APGF] += apr * gf;                 // mpgp.c:558
+      if (has_ub) {
+        const double2 t = u2[i];
+        b0.ub = t.x;
+        b1.ub = t.y;
+      }
+      double br0[PB_MAXEQ], br1[PB_MAXEQ];
+      const double a0 = penal_apr<EQ>(ap.x, rho, v.B, n, 2 * i, m, bp, br0);
+      const double a1 = penal_apr<EQ>(ap.y, rho, v.B, n, 2 * i + 1, m, bp, br1);
+      if (step == 'e') {
+        double2 xn;
+        xn.x  = update_e_elem<EQ>(afeas, alpha, astol, xr.x, pr.x, g0.x, a0, b0, br0, m, acc);
+        xn.y  = update_e_elem<EQ>(afeas, alpha, astol, xr.y, pr.y, g0.y, a1, b1, br1, m, acc);
+        xo[i] = xn;
       } else {
-        v.p[r] = gf;                              // mpgp.c:638
+        double2 xn, gn, gf;
+        update_cp_elem<EQ>(step, acg, astol, xr.x, pr.x, g0.x, a0, b0, br0, m, xn.x, gn.x, gf.x, acc);
+        update_cp_elem<EQ>(step, acg, astol, xr.y, pr.y, g0.y, a1, b1, br1, m, xn.y, gn.y, gf.y, acc);
+        xo[i] = xn;
+        go[i] = gn;
+        if (step == 'c') fo[i] = gf;   // mpgp.c:555: gf kept for the direction update
+        else po[i] = gf;               // mpgp.c:638: p = gf
       }
-      const double gP = gf + gc;
-      acc[RB_GP2] += gP * gP;
-      acc[RB_GC2] += gc * gc;
-      acc[RB_GF2] += gf * gf;
-#pragma unroll
-      for (int j = 0; j < PB_MAXEQ; j++)
-        if (j < m) acc[RB_BU + j] += brow[j] * xn;
+    }
+  } else {
+    for (int r = blockIdx.x * NT + threadIdx.x; r < n; r += stride) {
+      const double xr = v.x[r], pr = v.p[r], g0 = v.g[r];
+      double       brow[PB_MAXEQ];
+      const double apr = penal_apr<EQ>(v.Ap[r], rho, v.B, n, r, m, bp, brow);
+      const BoxVal b = load_box(v.bx, r);
+      if (step == 'e') {
+        v.x[r] = update_e_elem<EQ>(afeas, alpha, astol, xr, pr, g0, apr, b, brow, m, acc);
+      } else {
+        double xn, gn, gf;
+        update_cp_elem<EQ>(step, acg, astol, xr, pr, g0, apr, b, brow, m, xn, gn, gf, acc);
+        v.x[r] = xn;
+        v.g[r] = gn;
+        if (step == 'c') v.gf[r] = gf;
+        else v.p[r] = gf;
+      }
     }
   }
   grid_reduce8<0>(acc, rb, nullptr);
@@ -1021,13 +1088,21 @@ __global__ void __launch_bounds__(NT) k_update_B(MpgpVecs v, const MpgpCtl *__re
 
 int k_fused_B(const MpgpVecs &v, const MpgpCtl *S, RedBuf rb)
 {
-  int grid = elementwise_grid();
-  int need = (v.n + NT - 1) / NT;
+  const bool vec2 = (v.n % 2 == 0) && aligned16(v.x) && aligned16(v.p) && aligned16(v.g) && aligned16(v.Ap) && aligned16(v.gf) && aligned16(v.bx.lb) && aligned16(v.bx.ub) &&
+                    !getenv("PERMON_B200_NOVEC");
+  int        grid = elementwise_grid();
+  int        need = ((vec2 ? v.n / 2 : v.n) + NT - 1) / NT;
   if (need < 1) need = 1;
   if (grid > need) grid = need;
   // x p g Ap lb[ub] read, x g gf written (CG step)
   prof_pre(KF_UPDATE_B, 8.0 * v.n * (7 + (v.bx.lb ? 1 : 0) + (v.bx.ub ? 1 : 0) + v.m));
-  k_update_B<<<grid, NT, 0, g_ctx.stream>>>(v, S, rb);
+  if (v.m > 0) {
+    if (vec2) k_update_B<true, true><<<grid, NT, 0, g_ctx.stream>>>(v, S, rb);
+    else k_update_B<true, false><<<grid, NT, 0, g_ctx.stream>>>(v, S, rb);
+  } else {
+    if (vec2) k_update_B<false, true><<<grid, NT, 0, g_ctx.stream>>>(v, S, rb);
+    else k_update_B<false, false><<<grid, NT, 0, g_ctx.stream>>>(v, S, rb);
+  }
   prof_post(KF_UPDATE_B);
   LAUNCH_CHECK();
   return 0;

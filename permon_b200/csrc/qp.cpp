@@ -464,12 +464,32 @@ static int qppf_Gt_mult(QPPF cp, const double *t, Vec y)
   return k_dense_rows_multT_add(cp->n, cp->m, cp->Bd, R.d_all, 1.0, dy, 0);
 }
 static int mvec_get(Vec x, int m, double *t)
-{   // m-vector on the host (rank 0 owns it in the reference's layout; values are replicated here)
-  if (x->comm->size > 1) return err(PETSC_ERR_SUP, "m-vector input on multi-rank communicators");
-  const double *h;
-  PB_CHK(vec_host_read(x, &h));
-  if (x->n != m) return err(PETSC_ERR_ARG_SIZ, "expected a vector of length %d", m);
-  memcpy(t, h, sizeof(double) * m);
+{   // m-vector on the host.  In the reference's layout rank 0 owns the m entries (MatCreateOneRow, onerow.c:97-113);
+    // the values are replicated here with the set-up-time host exchange (MPI_Bcast in onerow.c:52).
+  MPI_Comm c = x->comm;
+  if (c->size == 1) {
+    const double *h;
+    PB_CHK(vec_host_read(x, &h));
+    if (x->n != m) return err(PETSC_ERR_ARG_SIZ, "expected a vector of length %d", m);
+    memcpy(t, h, sizeof(double) * m);
+    return 0;
+  }
+  if (x->N != m) return err(PETSC_ERR_ARG_SIZ, "expected a vector of global length %d (got %d)", m, (int)x->N);
+  if (!c->agi) return err(PETSC_ERR_ARG_WRONGSTATE, "communicator has no host exchange");
+  const double *h = nullptr;
+  if (x->n > 0) PB_CHK(vec_host_read(x, &h));
+  std::vector<int64_t> all(c->size);
+  for (int j = 0; j < m; j++) {
+    // entry j lives on the rank whose ownership range contains it
+    const bool mine = (j >= x->rstart && j < x->rstart + x->n);
+    int64_t    bits = 0;
+    if (mine) memcpy(&bits, &h[j - x->rstart], 8);
+    if (c->agi(c->agctx, mine ? bits : 0, all.data())) return err(PETSC_ERR_LIB, "host all-gather failed");
+    std::vector<int64_t> own(c->size);
+    if (c->agi(c->agctx, mine ? 1 : 0, own.data())) return err(PETSC_ERR_LIB, "host all-gather failed");
+    for (int r = 0; r < c->size; r++)
+      if (own[r]) memcpy(&t[j], &all[r], 8);
+  }
   return 0;
 }
 static int mvec_put(Vec y, int m, const double *t)

@@ -1,0 +1,94 @@
+"""Multi-GPU worker: launched once per GPU (torchrun or torch.multiprocessing) by tests/test_gpu_multi.py.
+Each rank owns a contiguous row block of the problem, solves it through the C ABI on its GPU (NCCL halo + all-gathers),
+rank 0 gathers the solution and checks it against the single-address-space CPU oracle."""
+import json
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def build_problem(kind, rank, size):
+    from permon_b200 import problems as PR
+    if kind == "obstacle2d":
+        N = 192
+        starts = PR.row_partition(N * N, size, align=N)
+        return PR.obstacle2d(N, -100.0), PR.obstacle2d(N, -100.0, rows=(starts[rank], starts[rank + 1])), starts, "-qps_rtol 1e-8 -qps_max_it 100000", dict(rtol=1e-8, max_it=100000)
+    if kind == "obstacle3d":
+        N = 40
+        starts = PR.row_partition(N ** 3, size, align=N * N)
+        return PR.obstacle3d(N), PR.obstacle3d(N, rows=(starts[rank], starts[rank + 1])), starts, "-qps_rtol 1e-8", dict(rtol=1e-8)
+    if kind == "varcoef3d":
+        N = 24
+        starts = PR.row_partition(N ** 3, size, align=N * N)
+        return PR.varcoef3d(N), PR.varcoef3d(N, rows=(starts[rank], starts[rank + 1])), starts, "-qps_rtol 1e-8 -qps_max_it 100000", dict(rtol=1e-8, max_it=100000)
+    if kind == "smalxe":
+        N = 64
+        starts = PR.row_partition(N * N, size, align=N)
+        full = PR.obstacle2d(N)
+        loc = PR.obstacle2d(N, rows=(starts[rank], starts[rank + 1]))
+        n = N * N
+        full.B = np.full((1, n), 1.0 / np.sqrt(n))
+        full.c = np.array([-0.05 * np.sqrt(n)])
+        loc.B = full.B[:, starts[rank]:starts[rank + 1]].copy()
+        loc.c = full.c if rank == 0 else np.zeros(0)   # rank 0 owns the single equality row (MatCreateOneRow layout)
+        return full, loc, starts, "-qps_rtol 1e-9", dict(rtol=1e-9)
+    raise ValueError(kind)
+
+
+def main():
+    import torch
+    import torch.distributed as dist
+    rank, size = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    local = int(os.environ.get("LOCAL_RANK", rank))
+    kinds = sys.argv[1].split(",")
+    from permon_b200 import api as P
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    P.call("PermonB200SetDevice", local)
+    P.initialize()
+    dist.init_process_group("nccl", device_id=dev)
+    idt = torch.zeros(128, dtype=torch.uint8, device=dev)
+    if rank == 0:
+        idt.copy_(torch.frombuffer(bytearray(P.get_unique_id()), dtype=torch.uint8))
+    dist.broadcast(idt, 0)
+    P.comm_init_rank(size, rank, idt.cpu().numpy().tobytes())
+    out = {}
+    for kind in kinds:
+        full, loc, starts, opts, okw = build_problem(kind, rank, size)
+        qtype = "smalxe" if kind == "smalxe" else "mpgp"
+        r = P.solve_problem(loc, qtype, opts)
+        xs = [torch.zeros(starts[q + 1] - starts[q], dtype=torch.float64, device=dev) for q in range(size)]
+        dist.all_gather(xs, torch.from_numpy(r.x).to(dev))
+        x = torch.cat(xs).cpu().numpy()
+        if rank == 0:
+            from oracle import oracle_py as O
+            op = O.Operator(full.ia, full.ja, full.a)
+            bx = O.BoxC(full.n, full.lb, full.ub)
+            if kind == "smalxe":
+                xr, ro = O.smalxe_solve(op, full.b, bx, full.B, full.c, full.x0, O.smalxe_opts(**okw))
+                op.c.m = 0
+                its_ref, its = ro["inner_its_accu"], r.stats["inner_iter_accu"]
+            else:
+                xr, ro = O.mpgp_solve(op, full.b, bx, full.x0, O.mpgp_opts(**okw))
+                its_ref, its = ro["its"], r.its
+                band = [its_ref]
+                for t in (2, 3, 5, 8):
+                    _, rb = O.mpgp_solve(op, full.b, bx, full.x0, O.mpgp_opts(nthreads=t, **okw))
+                    band.append(rb["its"])
+                ro["band"] = band
+            relx = float(np.linalg.norm(x - xr) / np.linalg.norm(xr))
+            fo, fg = O.objective(op, full.b, xr), O.objective(op, full.b, x)
+            out[kind] = dict(its=its, its_ref=its_ref, band=ro.get("band"), reason=r.reason, reason_ref=ro["reason"], relx=relx,
+                             relf=float(abs(fg - fo) / abs(fo)), counts=r.counts)
+        dist.barrier()
+    if rank == 0:
+        print("MGPU_RESULT " + json.dumps(out), flush=True)
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,33 @@
+"""2-GPU (or more) parity: row-partitioned MPGP / SMALXE over NCCL against the CPU oracle.  Skipped on 1-GPU boxes."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _ngpu():
+    from permon_b200 import api
+    return api.device_count()
+
+
+@pytest.mark.parametrize("nproc", [2, 4])
+def test_row_partitioned_solves_match_oracle(nproc):
+    if _ngpu() < nproc:
+        pytest.skip(f"needs {nproc} GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nproc}", "--master-addr", "127.0.0.1", "--master-port", "29613",
+           os.path.join(ROOT, "tests", "mgpu_worker.py"), "obstacle2d,obstacle3d,varcoef3d,smalxe"]
+    p = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+    assert p.returncode == 0, p.stdout[-3000:] + p.stderr[-3000:]
+    line = [l for l in p.stdout.splitlines() if l.startswith("MGPU_RESULT ")][-1]
+    res = json.loads(line[len("MGPU_RESULT "):])
+    for kind, r in res.items():
+        assert r["reason"] == r["reason_ref"], (kind, r)
+        band = r["band"] or [r["its_ref"]]
+        assert min(band) * 0.97 - 3 <= r["its"] <= max(band) * 1.03 + 3, (kind, r)
+        assert r["relx"] <= (1e-7 if kind != "varcoef3d" else 1e-5), (kind, r)
+        assert r["relf"] <= 1e-10 or kind == "varcoef3d", (kind, r)
