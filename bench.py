@@ -60,24 +60,25 @@ def workload_spec(name, n_gpus):
 
 
 def generate(spec, rank, size):
+    """this rank's row block, generated in ~2M-row chunks on a thread pool (numpy releases the GIL)"""
+    from concurrent.futures import ThreadPoolExecutor
     from permon_b200 import problems as PR
     if spec["kind"] == "2d":
         N = spec["N"]
         starts = PR.row_partition(N * N, size, align=N)
-        rows = (starts[rank], starts[rank + 1])
-        chunks = []
         step = max(N, (2_000_000 // N) * N)
-        for r0 in range(rows[0], rows[1], step):
-            chunks.append(PR.obstacle2d(N, spec["bscale"], rows=(r0, min(r0 + step, rows[1]))))
+        make = lambda r0, r1: PR.obstacle2d(N, spec["bscale"], rows=(r0, r1))
     else:
         N = spec["N"]
         P = N * N
         starts = PR.row_partition(N ** 3, size, align=P)
-        rows = (starts[rank], starts[rank + 1])
-        chunks = []
         step = max(P, (2_000_000 // P) * P)
-        for r0 in range(rows[0], rows[1], step):
-            chunks.append(PR.obstacle3d(N, rows=(r0, min(r0 + step, rows[1]))))
+        make = lambda r0, r1: PR.obstacle3d(N, rows=(r0, r1))
+    rows = (starts[rank], starts[rank + 1])
+    ranges = [(r0, min(r0 + step, rows[1])) for r0 in range(rows[0], rows[1], step)]
+    workers = max(1, min(len(ranges), (os.cpu_count() or 1) // max(1, min(size, 8))))
+    with ThreadPoolExecutor(workers) as ex:
+        chunks = list(ex.map(lambda ab: make(*ab), ranges))
     ia = [np.zeros(1, np.int64)]
     off = 0
     for c in chunks:

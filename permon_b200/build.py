@@ -19,7 +19,7 @@ SOURCES = ["kernels.cu", "shim.cpp", "qp.cpp", "qps.cpp"]
 HEADERS = ["device.h", "mpgp_ctl.h", "objects.h", os.path.join("..", "..", "include", "permon_b200.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
-COMMON = ["-std=c++17", "-O3", "-lineinfo", "--extended-lambda", "-Xcompiler", "-fPIC,-fvisibility=hidden,-Wall,-Wno-maybe-uninitialized",
+COMMON = ["-std=c++17", "-O3", "-lineinfo", "--extended-lambda", "-Xcompiler", "-fPIC,-fvisibility=hidden,-Wall,-Wno-maybe-uninitialized,-fopenmp",
           "-ccbin", "/usr/bin/g++"]
 
 
@@ -43,7 +43,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
             subprocess.check_call(cmd)
             relink = True
     if relink:
-        cmd = [NVCC, *ARCH, "-shared", "-ccbin", "/usr/bin/g++", "-o", LIB, *objs, "-lnccl", "-Xlinker", "--no-undefined"]
+        cmd = [NVCC, *ARCH, "-shared", "-ccbin", "/usr/bin/g++", "-o", LIB, *objs, "-lnccl", "-lgomp", "-Xlinker", "--no-undefined"]
         if verbose:
             print(" ".join(cmd), flush=True)
         subprocess.check_call(cmd)

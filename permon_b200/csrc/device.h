@@ -19,6 +19,7 @@ struct DevCtx {
   int64_t      launches    = 0;         // kernels launched by this library (bench.py: gpu_launches)
 };
 DevCtx &ctx();
+extern int g_p2p_size;
 int     dev_init();                      // 0 on success, PETSC_ERR_GPU otherwise
 void    set_error(const char *fmt, ...);
 const char *last_error();
@@ -66,10 +67,43 @@ struct BoxDev {
   double        astol = 0.0;
 };
 
+// Peer-memory window of the communicator (multi-GPU): every rank owns a small buffer that all peers map through
+// CUDA IPC.  Reduction records are PUSHED by the last CTA of the producing kernel straight into every peer's window
+// over NVLink, followed by a sequence-number flag; the ctrl kernels spin on their local flags.  No NCCL call, no
+// host round trip, no extra kernel for the scalar "all-gathers" of the iteration.
+#define PB_NKINDS 3      // 0: after K_A, 1: after K_B / projection, 2: after K_A'
+#define PB_MAXNEIGH 16
+#define PB_FLAG_STRIDE 16   // unsigned long long per flag slot (128 bytes: one line per flag)
+struct P2PWin {
+  int                 rank = 0, size = 1;
+  double             *slot[PB_MAXRANKS];   // peer q: [PB_NKINDS][2 parities][PB_MAXRANKS][PB_NRED]
+  unsigned long long *flag[PB_MAXRANKS];   // peer q: [PB_NKINDS][PB_MAXRANKS] * PB_FLAG_STRIDE
+};
+__host__ __device__ inline size_t p2p_slot_index(int kind, unsigned long long seq, int rank) { return (((size_t)kind * 2 + (seq & 1)) * PB_MAXRANKS + rank) * PB_NRED; }
+__host__ __device__ inline size_t p2p_flag_index(int kind, int rank) { return ((size_t)kind * PB_MAXRANKS + rank) * PB_FLAG_STRIDE; }
+
 struct RedBuf {
   double   *partials = nullptr;   // [maxblocks][PB_NRED]
   unsigned *counter  = nullptr;
   double   *out      = nullptr;   // where the last block stores the record (PB_NRED doubles)
+  const P2PWin      *win = nullptr;   // when set: also publish the record to every peer (kind, seq)
+  int                kind = 0;
+  unsigned long long seq = 0;
+};
+
+// halo exchange by direct peer stores ("pack + send" in one kernel) and the matching wait of the ghost pass
+struct HaloPush {
+  int                 nneigh = 0, total = 0;
+  int                 send_off[PB_MAXNEIGH + 1];
+  double             *dst[PB_MAXNEIGH];    // neighbour q's ghost buffer at the offset reserved for this rank
+  unsigned long long *flag[PB_MAXNEIGH];   // neighbour q's flag slot for this rank
+  const int          *send_idx = nullptr;
+  unsigned           *counter = nullptr;
+};
+struct HaloWait {
+  const unsigned long long *flags = nullptr;   // local: one flag slot (PB_FLAG_STRIDE apart) per neighbour
+  int                       n = 0;
+  unsigned long long        seq = 0;
 };
 
 // ---- kernels: generic vector ops (deterministic) -----------------------------------------------------
@@ -113,7 +147,13 @@ int k_fused_A(const CsrDev &A, const double *xin, const MpgpVecs &v, const MpgpC
 // K_A' : g = A xin - b (+rho B^T Bu), split, p = gf, [|gP|^2, |gc|^2, |gf|^2]; runs when step=='e' or init
 int k_fused_A2(const CsrDev &A, const double *xin, const MpgpVecs &v, const MpgpCtl *S, RedBuf rb, const unsigned char *skip_epilogue);
 // off-diagonal (ghost) contribution + deferred epilogue for boundary rows (multi-GPU)
-int k_fused_A_ghost(const CsrDev &Ao, const double *ghost, const MpgpVecs &v, const MpgpCtl *S, RedBuf rb, int second);
+int k_fused_A_ghost(const CsrDev &Ao, const double *ghost, const MpgpVecs &v, const MpgpCtl *S, RedBuf rb, int second, HaloWait hw);
+// peer-memory halo push (which: 0 = p before K_A, 1 = x before K_A' [gated on step 'e' / init])
+int k_halo_push(const HaloPush &hp, const double *vec, int gated, unsigned long long seq, const MpgpCtl *S);
+// ctrl kernels that first wait for every rank's pushed record (peer-memory all-gather)
+int k_ctrl_A_p2p(MpgpCtl *S, const P2PWin *win, const double *my_slot, const unsigned long long *my_flag, unsigned long long seq);
+int k_ctrl_E_p2p(MpgpCtl *S, const P2PWin *win, const double *my_slot, const unsigned long long *my_flag, unsigned long long seq);
+int k_ctrl_B_p2p(MpgpCtl *S, const P2PWin *win, const double *my_slot, const unsigned long long *my_flag, unsigned long long seq1, unsigned long long seq2);
 // K_B  : the c / p / e update of x, g (+ split, reductions)
 int k_fused_B(const MpgpVecs &v, const MpgpCtl *S, RedBuf rb);
 // K_C  : direction update p = gf - bcg p | p = gc | nothing

@@ -35,6 +35,7 @@ namespace pb {
 // context, errors, profiling
 // =====================================================================================================
 static DevCtx      g_ctx;
+int                g_p2p_size = 1;   // ranks of the peer-memory window (set by the communicator)
 static std::string g_err;
 DevCtx            &ctx() { return g_ctx; }
 const char        *last_error() { return g_err.c_str(); }
@@ -231,10 +232,38 @@ __device__ void grid_reduce8(double (&v)[PB_NRED], RedBuf rb, const double *prev
     block_reduce8<MINMASK>(w, sm);
     if (threadIdx.x == 0) {
 #pragma unroll
-      for (int k = 0; k < PB_NRED; k++) rb.out[k] = prev ? red_op<MINMASK>(k, prev[k], w[k]) : w[k];
+      for (int k = 0; k < PB_NRED; k++) {
+        const double f = prev ? red_op<MINMASK>(k, prev[k], w[k]) : w[k];
+        rb.out[k]      = f;
+        sm[k][0]       = f;
+      }
       *rb.counter = 0u;
     }
+    if (rb.win) {   // peer-memory all-gather: push the record + sequence flag into every rank's window (NVLink stores)
+      __syncthreads();
+      const P2PWin *W = rb.win;
+      if ((int)threadIdx.x < W->size) {
+        const int        q = threadIdx.x;
+        volatile double *dst = W->slot[q] + p2p_slot_index(rb.kind, rb.seq, W->rank);
+#pragma unroll
+        for (int k = 0; k < PB_NRED; k++) dst[k] = sm[k][0];
+        __threadfence_system();
+        *(volatile unsigned long long *)(W->flag[q] + p2p_flag_index(rb.kind, W->rank)) = rb.seq;
+      }
+    }
   }
+}
+
+// spin until a flag in LOCAL memory (written by a peer over NVLink) reaches seq; a dead peer traps instead of hanging
+__device__ __forceinline__ void wait_flag(const unsigned long long *f, unsigned long long seq)
+{
+  const volatile unsigned long long *vf = f;
+  const long long                    t0 = clock64();
+  while (*vf < seq) {
+    if (clock64() - t0 > 20000000000LL) __trap();   // ~10 s
+    __nanosleep(64);
+  }
+  __threadfence_system();
 }
 
 // =====================================================================================================
@@ -312,10 +341,21 @@ __device__ __forceinline__ double box_project(double x, const BoxVal &b)
 // tile-streamed CSR ("CSR-stream"): the CTA reads the nnz range of a 256-row tile with unit-stride loads,
 // multiplies with the gathered x on the fly and parks the products in shared memory; then one thread per
 // row adds its segment in storage order (== the reference's running sum) and runs the fused epilogue.
+template <class Epi, class = void>
+struct EpiHasWait : std::false_type {};
+template <class Epi>
+struct EpiHasWait<Epi, std::void_t<decltype(std::declval<const Epi &>().wait())>> : std::true_type {};
+template <class Epi>
+__device__ __forceinline__ void epi_wait(const Epi &epi)
+{
+  if constexpr (EpiHasWait<Epi>::value) epi.wait();
+}
+
 template <class Epi>
 __global__ void __launch_bounds__(NT) k_spmv_stream(CsrDev A, const double *__restrict__ x, Epi epi)
 {
   if (!epi.active()) return;
+  epi_wait(epi);
   extern __shared__ double s_prod[];
   typename Epi::Acc acc;
   epi.init(acc);
@@ -343,6 +383,7 @@ template <class Epi, int W>
 __global__ void __launch_bounds__(NT) k_spmv_vector(CsrDev A, const double *__restrict__ x, Epi epi)
 {
   if (!epi.active()) return;
+  epi_wait(epi);
   typename Epi::Acc acc;
   epi.init(acc);
   const int lane    = threadIdx.x & (W - 1);
@@ -882,7 +923,15 @@ struct EpiGhost {
   EpiA          ea;
   EpiA2         e2;
   const double *prev;   // record of the diagonal pass, combined by the last CTA
+  HaloWait      hw;     // peer-memory halo: wait for the neighbours' pushes before touching the ghost buffer
   typedef AccRed Acc;
+  __device__ void wait() const
+  {
+    if (hw.n > 0) {
+      if ((int)threadIdx.x < hw.n) wait_flag(hw.flags + (size_t)threadIdx.x * PB_FLAG_STRIDE, hw.seq);
+      __syncthreads();
+    }
+  }
   __device__ bool active() const { return SECOND ? e2.active() : ea.active(); }
   __device__ void init(Acc &a) const
   {
@@ -939,18 +988,59 @@ int k_fused_A2(const CsrDev &A, const double *xin, const MpgpVecs &v, const Mpgp
   return launch_spmv(A, xin, e, KF_SPMV_A2, bytes_A2(A, v));
 }
 
-int k_fused_A_ghost(const CsrDev &Ao, const double *ghost, const MpgpVecs &v, const MpgpCtl *S, RedBuf rb, int second)
+int k_fused_A_ghost(const CsrDev &Ao, const double *ghost, const MpgpVecs &v, const MpgpCtl *S, RedBuf rb, int second, HaloWait hw)
 {
   // rb.out: final record; the diagonal pass left its record in rb.out as well -> read it as `prev`
-  EpiA  ea{v.p, v.g, v.x, v.Ap, v.bx, v.B, v.m, v.n, S, rb, nullptr};
-  EpiA2 e2{v.x, v.b, v.g, v.p, v.bx, v.B, v.m, v.n, S, rb, nullptr};
+  RedBuf rd = rb;
+  EpiA  ea{v.p, v.g, v.x, v.Ap, v.bx, v.B, v.m, v.n, S, rd, nullptr};
+  EpiA2 e2{v.x, v.b, v.g, v.p, v.bx, v.B, v.m, v.n, S, rd, nullptr};
   double bytes = 12.0 * (double)Ao.nnz + 8.0 * Ao.n * 8;
   if (second) {
-    EpiGhost<true> e{ea, e2, rb.out};
+    EpiGhost<true> e{ea, e2, rb.out, hw};
     return launch_spmv(Ao, ghost, e, KF_SPMV_A2, bytes);
   }
-  EpiGhost<false> e{ea, e2, rb.out};
+  EpiGhost<false> e{ea, e2, rb.out, hw};
   return launch_spmv(Ao, ghost, e, KF_SPMV_A, bytes);
+}
+
+// peer-memory halo push: dst_q[k] = vec[send_idx[k]] written straight into the neighbours' ghost buffers, then a
+// sequence flag per neighbour once every CTA's stores are fenced (threadfence + ticket, last CTA signals)
+__global__ void __launch_bounds__(NT) k_halo_push_kernel(HaloPush hp, const double *__restrict__ vec, int gated, unsigned long long seq, const MpgpCtl *__restrict__ S)
+{
+  if (S) {
+    if (S->reason != 0) return;
+    if (gated && !(S->step == 'e' || S->init)) return;
+  }
+  __shared__ int s_last;
+  const int      stride = gridDim.x * NT;
+  for (int k = blockIdx.x * NT + threadIdx.x; k < hp.total; k += stride) {
+    int q = 0;
+    while (q + 1 < hp.nneigh && k >= hp.send_off[q + 1]) q++;
+    hp.dst[q][k - hp.send_off[q]] = vec[hp.send_idx[k]];
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned t = atomicAdd(hp.counter, 1u);
+    s_last     = (t == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (s_last) {
+    __threadfence_system();
+    if ((int)threadIdx.x < hp.nneigh) *(volatile unsigned long long *)hp.flag[threadIdx.x] = seq;
+    if (threadIdx.x == 0) *hp.counter = 0u;
+  }
+}
+int k_halo_push(const HaloPush &hp, const double *vec, int gated, unsigned long long seq, const MpgpCtl *S)
+{
+  int grid = (hp.total + NT - 1) / NT;
+  if (grid < 1) grid = 1;
+  if (grid > g_ctx.sm_count * 2) grid = g_ctx.sm_count * 2;
+  prof_pre(KF_HALO, 20.0 * hp.total);
+  k_halo_push_kernel<<<grid, NT, 0, g_ctx.stream>>>(hp, vec, gated, seq, S);
+  prof_post(KF_HALO);
+  LAUNCH_CHECK();
+  return 0;
 }
 
 // =====================================================================================================
@@ -1176,6 +1266,60 @@ int k_fused_project(const MpgpVecs &v, const MpgpCtl *S, RedBuf rb)
 __global__ void k_ctrl_A_kernel(MpgpCtl *S, const double *ra) { mpgp_ctrl_A(S, ra); }
 __global__ void k_ctrl_E_kernel(MpgpCtl *S, const double *rb) { mpgp_ctrl_E(S, rb); }
 __global__ void k_ctrl_B_kernel(MpgpCtl *S, const double *rb) { mpgp_ctrl_B(S, rb); }
+
+// peer-memory variants: one warp; lane q waits for rank q's record, lane 0 then runs the control step
+__global__ void k_ctrl_A_p2p_kernel(MpgpCtl *S, int size, const double *my_slot, const unsigned long long *my_flag, unsigned long long seq)
+{
+  if (S->reason != 0) return;
+  if ((int)threadIdx.x < size) wait_flag(my_flag + p2p_flag_index(0, threadIdx.x), seq);
+  __syncwarp();
+  if (threadIdx.x == 0) mpgp_ctrl_A(S, my_slot + p2p_slot_index(0, seq, 0));
+}
+__global__ void k_ctrl_E_p2p_kernel(MpgpCtl *S, int size, const double *my_slot, const unsigned long long *my_flag, unsigned long long seq)
+{
+  if (S->reason != 0) return;
+  if (!(S->step == 'e' || S->init)) return;
+  if ((int)threadIdx.x < size) wait_flag(my_flag + p2p_flag_index(1, threadIdx.x), seq);
+  __syncwarp();
+  if (threadIdx.x == 0) mpgp_ctrl_E(S, my_slot + p2p_slot_index(1, seq, 0));
+}
+__global__ void k_ctrl_B_p2p_kernel(MpgpCtl *S, int size, const double *my_slot, const unsigned long long *my_flag, unsigned long long seq1, unsigned long long seq2)
+{
+  if (S->reason != 0) return;
+  const bool second = (S->step == 'e' || S->init);   // the record comes from K_A' (kind 2) or from K_B (kind 1)
+  const int  kind = second ? 2 : 1;
+  const unsigned long long seq = second ? seq2 : seq1;
+  if ((int)threadIdx.x < size) wait_flag(my_flag + p2p_flag_index(kind, threadIdx.x), seq);
+  __syncwarp();
+  if (threadIdx.x == 0) mpgp_ctrl_B(S, my_slot + p2p_slot_index(kind, seq, 0));
+}
+int k_ctrl_A_p2p(MpgpCtl *S, const P2PWin *win, const double *my_slot, const unsigned long long *my_flag, unsigned long long seq)
+{
+  (void)win;
+  prof_pre(KF_CTRL, 0);
+  k_ctrl_A_p2p_kernel<<<1, 32, 0, g_ctx.stream>>>(S, g_p2p_size, my_slot, my_flag, seq);
+  prof_post(KF_CTRL);
+  LAUNCH_CHECK();
+  return 0;
+}
+int k_ctrl_E_p2p(MpgpCtl *S, const P2PWin *win, const double *my_slot, const unsigned long long *my_flag, unsigned long long seq)
+{
+  (void)win;
+  prof_pre(KF_CTRL, 0);
+  k_ctrl_E_p2p_kernel<<<1, 32, 0, g_ctx.stream>>>(S, g_p2p_size, my_slot, my_flag, seq);
+  prof_post(KF_CTRL);
+  LAUNCH_CHECK();
+  return 0;
+}
+int k_ctrl_B_p2p(MpgpCtl *S, const P2PWin *win, const double *my_slot, const unsigned long long *my_flag, unsigned long long seq1, unsigned long long seq2)
+{
+  (void)win;
+  prof_pre(KF_CTRL, 0);
+  k_ctrl_B_p2p_kernel<<<1, 32, 0, g_ctx.stream>>>(S, g_p2p_size, my_slot, my_flag, seq1, seq2);
+  prof_post(KF_CTRL);
+  LAUNCH_CHECK();
+  return 0;
+}
 
 int k_ctrl_A(MpgpCtl *S, const double *ra)
 {

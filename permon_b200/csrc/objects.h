@@ -20,6 +20,14 @@ struct _p_PermonComm {
   PermonB200AllGatherI64 agi = nullptr;   // host exchange (set-up only)
   PermonB200AllGatherV   agv = nullptr;
   void                  *agctx = nullptr;
+  // peer-memory window (CUDA IPC over NVLink): reduction records are pushed, not all-gathered by NCCL
+  bool                   p2p = false;
+  void                  *win_base = nullptr;
+  pb::P2PWin            *d_win = nullptr;
+  double                *my_slot = nullptr;
+  unsigned long long    *my_flag = nullptr;
+  unsigned long long     seq[PB_NKINDS] = {0, 0, 0};
+  std::vector<void *>    peer_bases;
 };
 
 struct PObj {
@@ -64,6 +72,14 @@ struct HaloPlan {
   unsigned char        *d_skip = nullptr;   // [n] 1 for rows with ghost columns
   PetscInt              nboundary = 0;
   cudaEvent_t           ev_packed = nullptr, ev_arrived = nullptr, ev_consumed = nullptr;
+  // peer-memory halo: neighbours store their boundary values straight into my ghost window
+  bool                  p2p = false;
+  void                 *gwin = nullptr;
+  double               *d_ghost2[2] = {nullptr, nullptr};      // [0]: ghosts of p, [1]: ghosts of x
+  unsigned long long   *my_hflags[2] = {nullptr, nullptr};
+  pb::HaloPush          push[2];
+  unsigned long long    hseq[2] = {0, 0};
+  std::vector<void *>   peer_gwins;
   // host copy of the split matrix, kept until the first device use (lets the plan be built and inspected
   // without a GPU; the arithmetic still needs one)
   struct HostSplit {

@@ -686,17 +686,52 @@ int MpgpImpl::solve_fused(QPS qps)
   *hS = S;
   PB_CUDA(cudaMemcpyAsync(dS, hS, sizeof(MpgpCtl), cudaMemcpyHostToDevice, s));
 
+  // multi-GPU plumbing: peer-memory pushes (CUDA IPC over NVLink) when available, NCCL otherwise
+  MPI_Comm   comm = qps->comm;
+  const bool p2p = multi && comm->p2p && H && H->p2p;
+  auto red = [&](Reducer &R, int kind, bool publish) -> RedBuf {
+    RedBuf rb = R.rb;
+    if (p2p && publish) {
+      rb.win  = comm->d_win;
+      rb.kind = kind;
+      rb.seq  = ++comm->seq[kind];
+    }
+    return rb;
+  };
+  auto gather_ctrl_A = [&]() -> int {
+    if (p2p) return k_ctrl_A_p2p(dS, comm->d_win, comm->my_slot, comm->my_flag, comm->seq[0]);
+    PB_CHK(RA.gather());
+    return k_ctrl_A(dS, RA.d_all);
+  };
+  auto gather_ctrl_E = [&]() -> int {
+    if (p2p) return k_ctrl_E_p2p(dS, comm->d_win, comm->my_slot, comm->my_flag, comm->seq[1]);
+    PB_CHK(RB.gather());
+    return k_ctrl_E(dS, RB.d_all);
+  };
+  auto gather_ctrl_B = [&]() -> int {
+    if (p2p) return k_ctrl_B_p2p(dS, comm->d_win, comm->my_slot, comm->my_flag, comm->seq[1], comm->seq[2]);
+    PB_CHK(RB.gather());
+    return k_ctrl_B(dS, RB.d_all);
+  };
   auto second_spmv = [&]() -> int {   // K_A' with its halo / product plumbing
     const double *xin = v.x;
     if (prod) {
       PB_CHK(k_spmv_gated(M2->Ad, v.x, v.t, dS, 1));
       xin = v.t;
     }
-    if (H) PB_CHK(mat_halo_begin(M1, v.x));
-    PB_CHK(k_fused_A2(M1->Ad, xin, v, dS, RB.rb, skip));
     if (H) {
-      PB_CHK(mat_halo_end(M1));
-      PB_CHK(k_fused_A_ghost(M1->Ao, H->d_ghost, v, dS, RB.rb, 1));
+      if (p2p) PB_CHK(k_halo_push(H->push[1], v.x, 1, ++H->hseq[1], dS));
+      else PB_CHK(mat_halo_begin(M1, v.x));
+    }
+    PB_CHK(k_fused_A2(M1->Ad, xin, v, dS, red(RB, 2, !H), skip));
+    if (H) {
+      if (p2p) {
+        HaloWait hw{H->my_hflags[1], (int)H->neigh.size(), H->hseq[1]};
+        PB_CHK(k_fused_A_ghost(M1->Ao, H->d_ghost2[1], v, dS, red(RB, 2, true), 1, hw));
+      } else {
+        PB_CHK(mat_halo_end(M1));
+        PB_CHK(k_fused_A_ghost(M1->Ao, H->d_ghost, v, dS, RB.rb, 1, HaloWait()));
+      }
     }
     return 0;
   };
@@ -720,14 +755,10 @@ int MpgpImpl::solve_fused(QPS qps)
   };
 
   // ---- initial phase: x = P(x); g = A x - b; split; p = gf  (mpgp.c:497-507)
-  PB_CHK(k_fused_project(v, dS, RB.rb));
-  if (v.m > 0) {
-    PB_CHK(RB.gather());
-    PB_CHK(k_ctrl_E(dS, RB.d_all));
-  }
+  PB_CHK(k_fused_project(v, dS, red(RB, 1, true)));
+  if (v.m > 0) PB_CHK(gather_ctrl_E());
   PB_CHK(second_spmv());
-  PB_CHK(RB.gather());
-  PB_CHK(k_ctrl_B(dS, RB.d_all));
+  PB_CHK(gather_ctrl_B());
   bool stop = false;
   if (host_conv) PB_CHK(host_step(&stop));
   if (!stop) PB_CHK(k_fused_C(v, dS));
@@ -741,22 +772,25 @@ int MpgpImpl::solve_fused(QPS qps)
         PB_CHK(k_spmv_gated(M2->Ad, v.p, v.t, dS, 0));
         xin = v.t;
       }
-      if (H) PB_CHK(mat_halo_begin(M1, v.p));
-      PB_CHK(k_fused_A(M1->Ad, xin, v, dS, RA.rb, skip));
       if (H) {
-        PB_CHK(mat_halo_end(M1));
-        PB_CHK(k_fused_A_ghost(M1->Ao, H->d_ghost, v, dS, RA.rb, 0));
+        if (p2p) PB_CHK(k_halo_push(H->push[0], v.p, 0, ++H->hseq[0], dS));
+        else PB_CHK(mat_halo_begin(M1, v.p));
       }
-      PB_CHK(RA.gather());
-      PB_CHK(k_ctrl_A(dS, RA.d_all));
-      PB_CHK(k_fused_B(v, dS, RB.rb));
-      if (v.m > 0) {
-        PB_CHK(RB.gather());
-        PB_CHK(k_ctrl_E(dS, RB.d_all));
+      PB_CHK(k_fused_A(M1->Ad, xin, v, dS, red(RA, 0, !H), skip));
+      if (H) {
+        if (p2p) {
+          HaloWait hw{H->my_hflags[0], (int)H->neigh.size(), H->hseq[0]};
+          PB_CHK(k_fused_A_ghost(M1->Ao, H->d_ghost2[0], v, dS, red(RA, 0, true), 0, hw));
+        } else {
+          PB_CHK(mat_halo_end(M1));
+          PB_CHK(k_fused_A_ghost(M1->Ao, H->d_ghost, v, dS, RA.rb, 0, HaloWait()));
+        }
       }
+      PB_CHK(gather_ctrl_A());
+      PB_CHK(k_fused_B(v, dS, red(RB, 1, true)));
+      if (v.m > 0) PB_CHK(gather_ctrl_E());
       PB_CHK(second_spmv());
-      PB_CHK(RB.gather());
-      PB_CHK(k_ctrl_B(dS, RB.d_all));
+      PB_CHK(gather_ctrl_B());
       if (host_conv) {
         PB_CHK(host_step(&stop));
         if (stop) break;

@@ -9,6 +9,8 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <omp.h>
+
 #include <algorithm>
 #include <fstream>
 #include <sstream>
@@ -479,6 +481,54 @@ static int nccl_agv(void *vctx, const void *sendbuf, int64_t sendbytes, void *re
   return 0;
 }
 
+// Peer-memory window of the communicator: one small cudaMalloc per rank, mapped by every peer through CUDA IPC.
+static const size_t kWinSlotBytes = sizeof(double) * PB_NKINDS * 2 * PB_MAXRANKS * PB_NRED;
+static const size_t kWinFlagBytes = sizeof(unsigned long long) * PB_NKINDS * PB_MAXRANKS * PB_FLAG_STRIDE;
+static int comm_p2p_setup(MPI_Comm c)
+{
+  const int size = c->size, rank = c->rank;
+  PB_CUDA(cudaMalloc(&c->win_base, kWinSlotBytes + kWinFlagBytes));
+  PB_CUDA(cudaMemset(c->win_base, 0, kWinSlotBytes + kWinFlagBytes));
+  PB_CUDA(cudaDeviceSynchronize());
+  cudaIpcMemHandle_t mine;
+  int                ok = (cudaIpcGetMemHandle(&mine, c->win_base) == cudaSuccess);
+  std::vector<cudaIpcMemHandle_t> all(size);
+  std::vector<int64_t>            bytes(size, (int64_t)sizeof(cudaIpcMemHandle_t));
+  if (c->agv(c->agctx, &mine, sizeof mine, all.data(), bytes.data())) return err(PETSC_ERR_LIB, "host all-gather failed");
+  c->peer_bases.assign(size, nullptr);
+  for (int q = 0; q < size && ok; q++) {
+    if (q == rank) {
+      c->peer_bases[q] = c->win_base;
+      continue;
+    }
+    if (cudaIpcOpenMemHandle(&c->peer_bases[q], all[q], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+      cudaGetLastError();
+      ok = 0;
+    }
+  }
+  std::vector<int64_t> oks(size);
+  if (c->agi(c->agctx, ok, oks.data())) return err(PETSC_ERR_LIB, "host all-gather failed");
+  for (int q = 0; q < size; q++) ok = ok && oks[q];
+  if (!ok) {   // no peer access between some pair of devices: keep the NCCL path
+    c->p2p = false;
+    return 0;
+  }
+  P2PWin W;
+  W.rank = rank;
+  W.size = size;
+  for (int q = 0; q < PB_MAXRANKS; q++) {
+    W.slot[q] = q < size ? (double *)c->peer_bases[q] : nullptr;
+    W.flag[q] = q < size ? (unsigned long long *)((char *)c->peer_bases[q] + kWinSlotBytes) : nullptr;
+  }
+  PB_CUDA(cudaMalloc(&c->d_win, sizeof(P2PWin)));
+  PB_CUDA(cudaMemcpy(c->d_win, &W, sizeof W, cudaMemcpyHostToDevice));
+  c->my_slot = (double *)c->win_base;
+  c->my_flag = (unsigned long long *)((char *)c->win_base + kWinSlotBytes);
+  g_p2p_size = size;
+  c->p2p     = true;
+  return 0;
+}
+
 PetscErrorCode PermonB200CommInitRank(int nranks, int rank, const void *id128)
 {
   if (nranks < 1 || rank < 0 || rank >= nranks) return err(PETSC_ERR_ARG_OUTOFRANGE, "bad rank %d of %d", rank, nranks);
@@ -495,6 +545,8 @@ PetscErrorCode PermonB200CommInitRank(int nranks, int rank, const void *id128)
   g_world.agi   = nccl_agi;
   g_world.agv   = nccl_agv;
   g_world.agctx = &g_world;
+  const char *pe = getenv("PERMON_B200_P2P");
+  if (!pe || strcmp(pe, "0")) PB_CHK(comm_p2p_setup(&g_world));
   return 0;
 }
 
@@ -960,40 +1012,68 @@ PetscErrorCode MatCreateMPIAIJWithArrays(MPI_Comm comm, PetscInt m, PetscInt n, 
   const int64_t  nnz = i[m];
   HaloPlan      *H = new HaloPlan;
   A->halo          = H;
-  // ghosts
+  // ghosts (host threads: the split is O(nnz) and sits inside the e2e path of multi-GPU runs)
   std::vector<PetscInt> gh;
-  for (int64_t k = 0; k < nnz; k++)
-    if (j[k] < c0 || j[k] >= c1) gh.push_back(j[k]);
+  {
+    std::vector<std::vector<PetscInt>> part;
+#pragma omp parallel
+    {
+#pragma omp single
+      part.resize(omp_get_num_threads());
+      std::vector<PetscInt> &mine = part[omp_get_thread_num()];
+#pragma omp for schedule(static)
+      for (int64_t k = 0; k < nnz; k++)
+        if (j[k] < c0 || j[k] >= c1) mine.push_back(j[k]);
+      std::sort(mine.begin(), mine.end());
+      mine.erase(std::unique(mine.begin(), mine.end()), mine.end());
+    }
+    for (auto &v : part) gh.insert(gh.end(), v.begin(), v.end());
+  }
   std::sort(gh.begin(), gh.end());
   gh.erase(std::unique(gh.begin(), gh.end()), gh.end());
   H->garray = gh;
-  // split
+  // split: count, prefix-sum, fill
   H->host = new HaloPlan::HostSplit;
   std::vector<int>    &dia = H->host->dia, &dja = H->host->dja, &oia = H->host->oia, &oja = H->host->oja, &orow = H->host->orow;
   std::vector<double> &da = H->host->da, &oa = H->host->oa;
   std::vector<unsigned char> &skip = H->host->skip;
   dia.assign(m + 1, 0);
-  oia.assign(1, 0);
   skip.assign(std::max<PetscInt>(m, 1), 0);
-  dja.reserve(nnz);
-  da.reserve(nnz);
+  std::vector<int> ocnt(m + 1, 0);
+#pragma omp parallel for schedule(static)
   for (PetscInt r = 0; r < m; r++) {
-    bool has = false;
+    int nd = 0, no = 0;
+    for (PetscInt k = i[r]; k < i[r + 1]; k++) {
+      if (j[k] >= c0 && j[k] < c1) nd++;
+      else no++;
+    }
+    dia[r + 1]  = nd;
+    ocnt[r + 1] = no;
+    skip[r]     = no > 0;
+  }
+  for (PetscInt r = 0; r < m; r++) {
+    dia[r + 1] += dia[r];
+    ocnt[r + 1] += ocnt[r];
+  }
+  dja.resize(dia[m]);
+  da.resize(dia[m]);
+  oja.resize(ocnt[m]);
+  oa.resize(ocnt[m]);
+  for (PetscInt r = 0; r < m; r++)
+    if (skip[r]) orow.push_back(r);
+  oia.assign(orow.size() + 1, 0);
+  for (size_t q = 0; q < orow.size(); q++) oia[q + 1] = ocnt[orow[q] + 1];
+#pragma omp parallel for schedule(static)
+  for (PetscInt r = 0; r < m; r++) {
+    int pd = dia[r], po = ocnt[r];
     for (PetscInt k = i[r]; k < i[r + 1]; k++) {
       if (j[k] >= c0 && j[k] < c1) {
-        dja.push_back(j[k] - c0);
-        da.push_back(a[k]);
+        dja[pd] = j[k] - c0;
+        da[pd++] = a[k];
       } else {
-        oja.push_back((int)(std::lower_bound(gh.begin(), gh.end(), j[k]) - gh.begin()));
-        oa.push_back(a[k]);
-        has = true;
+        oja[po] = (int)(std::lower_bound(gh.begin(), gh.end(), j[k]) - gh.begin());
+        oa[po++] = a[k];
       }
-    }
-    dia[r + 1] = (int)dja.size();
-    if (has) {
-      orow.push_back(r);
-      oia.push_back((int)oja.size());
-      skip[r] = 1;
     }
   }
   H->nboundary = (PetscInt)orow.size();
@@ -1047,6 +1127,83 @@ PetscErrorCode MatCreateMPIAIJWithArrays(MPI_Comm comm, PetscInt m, PetscInt n, 
   return 0;
 }
 
+// Peer-memory halo: every rank allocates a ghost window (ghosts of p, ghosts of x, one flag per neighbour and vector),
+// publishes its IPC handle + neighbour table, and resolves where in each neighbour's window its own boundary values go.
+struct HaloExch {
+  cudaIpcMemHandle_t h;
+  int                nneigh, ng_pad;
+  int                neigh[PB_MAXNEIGH];
+  int                recv_off[PB_MAXNEIGH + 1];
+};
+static int halo_p2p_setup(Mat A)
+{
+  HaloPlan *H = A->halo;
+  MPI_Comm  c = A->comm;
+  const int size = c->size, rank = c->rank;
+  int       ok = ((int)H->neigh.size() <= PB_MAXNEIGH);
+  const int ng = (int)H->garray.size(), ng_pad = ((ng + 15) / 16) * 16 + 16;
+  const size_t gbytes = sizeof(double) * 2 * (size_t)ng_pad, fbytes = sizeof(unsigned long long) * 2 * PB_MAXNEIGH * PB_FLAG_STRIDE;
+  PB_CUDA(cudaMalloc(&H->gwin, gbytes + fbytes));
+  PB_CUDA(cudaMemset(H->gwin, 0, gbytes + fbytes));
+  PB_CUDA(cudaDeviceSynchronize());
+  HaloExch me;
+  memset(&me, 0, sizeof me);
+  if (cudaIpcGetMemHandle(&me.h, H->gwin) != cudaSuccess) ok = 0;
+  me.nneigh = ok ? (int)H->neigh.size() : 0;
+  me.ng_pad = ng_pad;
+  for (int q = 0; q < me.nneigh; q++) me.neigh[q] = H->neigh[q];
+  for (int q = 0; q <= me.nneigh; q++) me.recv_off[q] = H->recv_off[q];
+  std::vector<HaloExch> all(size);
+  std::vector<int64_t>  bytes(size, (int64_t)sizeof(HaloExch));
+  if (c->agv(c->agctx, &me, sizeof me, all.data(), bytes.data())) return err(PETSC_ERR_LIB, "host all-gather failed");
+  H->peer_gwins.assign(H->neigh.size(), nullptr);
+  for (int w = 0; w < 2; w++) {
+    H->push[w]          = HaloPush();
+    H->push[w].nneigh   = (int)H->neigh.size();
+    H->push[w].total    = (int)H->send_idx.size();
+    H->push[w].send_idx = H->d_send_idx;
+    for (size_t q = 0; q <= H->neigh.size() && q <= PB_MAXNEIGH; q++) H->push[w].send_off[q] = H->send_off[q];
+  }
+  for (size_t iq = 0; iq < H->neigh.size() && ok; iq++) {
+    const int       q = H->neigh[iq];
+    const HaloExch &E = all[q];
+    int             jq = -1;
+    for (int t = 0; t < E.nneigh; t++)
+      if (E.neigh[t] == rank) jq = t;
+    if (jq < 0 || E.recv_off[jq + 1] - E.recv_off[jq] != H->send_off[iq + 1] - H->send_off[iq]) {
+      ok = 0;
+      break;
+    }
+    if (cudaIpcOpenMemHandle(&H->peer_gwins[iq], E.h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+      cudaGetLastError();
+      ok = 0;
+      break;
+    }
+    char *base = (char *)H->peer_gwins[iq];
+    for (int w = 0; w < 2; w++) {
+      H->push[w].dst[iq]  = (double *)base + (size_t)w * E.ng_pad + E.recv_off[jq];
+      H->push[w].flag[iq] = (unsigned long long *)(base + sizeof(double) * 2 * (size_t)E.ng_pad) + ((size_t)w * PB_MAXNEIGH + jq) * PB_FLAG_STRIDE;
+    }
+  }
+  std::vector<int64_t> oks(size);
+  if (c->agi(c->agctx, ok, oks.data())) return err(PETSC_ERR_LIB, "host all-gather failed");
+  for (int q = 0; q < size; q++) ok = ok && oks[q];
+  if (!ok) {
+    H->p2p = false;
+    return 0;
+  }
+  unsigned *cnt;
+  PB_CUDA(cudaMalloc(&cnt, 2 * sizeof(unsigned)));
+  PB_CUDA(cudaMemset(cnt, 0, 2 * sizeof(unsigned)));
+  for (int w = 0; w < 2; w++) {
+    H->push[w].counter = cnt + w;
+    H->d_ghost2[w]     = (double *)H->gwin + (size_t)w * ng_pad;
+    H->my_hflags[w]    = (unsigned long long *)((char *)H->gwin + gbytes) + (size_t)w * PB_MAXNEIGH * PB_FLAG_STRIDE;
+  }
+  H->p2p = true;
+  return 0;
+}
+
 namespace pb {
 int mat_ensure_device(Mat A)
 {
@@ -1074,6 +1231,7 @@ int mat_ensure_device(Mat A)
   PB_CUDA(cudaStreamSynchronize(ctx().stream));
   delete S;
   H->host = nullptr;
+  if (A->comm->p2p) PB_CHK(halo_p2p_setup(A));
   return 0;
 }
 }  // namespace pb
