@@ -320,6 +320,8 @@ def main():
     P.profile_begin()
     P.QPSSolve(h["qps"])
     prof = P.profile_end()
+    if os.environ.get("PERMON_B200_TIMELINE"):
+        P.call("PermonB200ProfileDump", (os.environ["PERMON_B200_TIMELINE"] + f".rank{rank}.csv").encode())
     barrier()
     peak, peak_src = peaks()
     ka = prof.get("K_A spmv+dots+feas", dict(launches=0, total_ms=0.0, bytes_per_launch=0.0))

@@ -41,6 +41,7 @@ const char *family_name(int f);
 void        prof_begin();
 int         prof_end();
 int         prof_get(int family, int64_t *launches, double *ms, double *bytes_per_launch);
+int         prof_dump(const char *path);
 void        prof_pre(int family, double bytes);
 void        prof_post(int family);
 

@@ -143,6 +143,20 @@ int prof_end()
   }
   return KF_COUNT;
 }
+int prof_dump(const char *path)
+{   // per-launch timeline (ms since the first recorded launch) -- a poor man's nsys for gap analysis
+  FILE *f = fopen(path, "w");
+  if (!f) return 65;
+  fprintf(f, "family,start_ms,stop_ms\n");
+  for (size_t i = 0; i < g_prof_used; i++) {
+    float a = 0.f, b = 0.f;
+    cudaEventElapsedTime(&a, g_prof[0].a, g_prof[i].a);
+    cudaEventElapsedTime(&b, g_prof[0].a, g_prof[i].b);
+    fprintf(f, "%s,%.4f,%.4f\n", family_name(g_prof[i].fam), a, b);
+  }
+  fclose(f);
+  return 0;
+}
 int prof_get(int f, int64_t *launches, double *ms, double *bytes_per_launch)
 {
   if (f < 0 || f >= KF_COUNT) return 63;

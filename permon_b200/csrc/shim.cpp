@@ -394,6 +394,16 @@ PetscErrorCode PermonFinalize(void)
 {
   for (auto &kv : g_reducers) kv.second.destroy();
   g_reducers.clear();
+  if (g_world.p2p) {
+    for (int q = 0; q < g_world.size; q++)
+      if (q != g_world.rank && g_world.peer_bases[q]) cudaIpcCloseMemHandle(g_world.peer_bases[q]);
+    cudaFree(g_world.d_win);
+    g_world.p2p = false;
+  }
+  if (g_world.win_base) {
+    cudaFree(g_world.win_base);
+    g_world.win_base = nullptr;
+  }
   if (g_world.nccl) {
     ncclCommDestroy((ncclComm_t)g_world.nccl);
     g_world.nccl = nullptr;
@@ -577,6 +587,7 @@ PetscErrorCode PermonB200ProfileGet(int family, const char **name, int64_t *laun
   if (name) *name = family_name(family);
   return prof_get(family, launches, total_ms, bytes_per_launch);
 }
+PetscErrorCode PermonB200ProfileDump(const char *path) { return prof_dump(path); }
 PetscErrorCode PermonB200GetLaunchCount(int64_t *launches)
 {
   *launches = ctx().launches;
@@ -887,6 +898,10 @@ _p_Mat::~_p_Mat()
     if (halo->ev_packed) cudaEventDestroy(halo->ev_packed);
     if (halo->ev_arrived) cudaEventDestroy(halo->ev_arrived);
     if (halo->ev_consumed) cudaEventDestroy(halo->ev_consumed);
+    for (void *pw : halo->peer_gwins)
+      if (pw) cudaIpcCloseMemHandle(pw);
+    if (halo->push[0].counter) cudaFree(halo->push[0].counter);
+    if (halo->gwin) cudaFree(halo->gwin);
     delete halo->host;
     delete halo;
   }
