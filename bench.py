@@ -54,6 +54,8 @@ def workload_spec(name, n_gpus):
         "c2x": dict(kind="2d", N=4096, bscale=-100.0, label="C2x expansion-heavy 2-D obstacle 4096^2, b=-100h^2"),
         "c3": dict(kind="3d", N=512, label="C3 3-D obstacle 512^3 (134M dofs), 7-point Laplacian, lower bound, z-slab row partition"),
         "c3s": dict(kind="3d", N=256, label="3-D obstacle 256^3 (16.7M dofs) stand-in"),
+        "c5": dict(kind="var", N=256, label="C5 variable-coefficient 3-D Laplacian 256^3 (16.7M dofs, contrast 1e4), lb and ub arrays, ~50% active at the solution"),
+        "c5s": dict(kind="var", N=128, label="variable-coefficient 3-D Laplacian 128^3 stand-in"),
     }[name]
     spec["name"] = name
     return spec
@@ -73,7 +75,10 @@ def generate(spec, rank, size):
         P = N * N
         starts = PR.row_partition(N ** 3, size, align=P)
         step = max(P, (2_000_000 // P) * P)
-        make = lambda r0, r1: PR.obstacle3d(N, rows=(r0, r1))
+        if spec["kind"] == "var":
+            make = lambda r0, r1: PR.varcoef3d(N, rows=(r0, r1))
+        else:
+            make = lambda r0, r1: PR.obstacle3d(N, rows=(r0, r1))
     rows = (starts[rank], starts[rank + 1])
     ranges = [(r0, min(r0 + step, rows[1])) for r0 in range(rows[0], rows[1], step)]
     workers = max(1, min(len(ranges), (os.cpu_count() or 1) // max(1, min(size, 8))))
@@ -90,6 +95,7 @@ def generate(spec, rank, size):
     pr.a = np.concatenate([c.a for c in chunks])
     pr.b = np.concatenate([c.b for c in chunks])
     pr.lb = np.concatenate([c.lb for c in chunks])
+    pr.ub = np.concatenate([c.ub for c in chunks]) if chunks[0].ub is not None else None
     pr.x0 = np.zeros(rows[1] - rows[0])
     pr.r0, pr.r1 = rows
     return pr
@@ -239,7 +245,9 @@ def main():
     t_gen = time.time() - t_gen
     n_loc, nnz_loc = pr.n, pr.nnz
     # pinned host buffers (the e2e leg copies from these)
-    host = {k: torch.from_numpy(np.ascontiguousarray(getattr(pr, k))).pin_memory() for k in ("ia", "ja", "a", "b", "lb")}
+    vec_keys = ("b", "lb") + (("ub",) if pr.ub is not None else ())
+    host = {k: torch.from_numpy(np.ascontiguousarray(getattr(pr, k))).pin_memory() for k in ("ia", "ja", "a") + vec_keys}
+    both = pr.ub is not None
 
     def make_solver(device_resident, keep):
         """QP + QPS through the C ABI; returns handles"""
@@ -250,27 +258,25 @@ def main():
                 d["x"] = torch.zeros(n_loc, dtype=torch.float64, device=dev)
                 torch.cuda.synchronize()
                 h["A"] = P.MatCreateAIJFromDevicePointers(n_loc, n_loc, d["ia"].data_ptr(), d["ja"].data_ptr(), d["a"].data_ptr())
-                h["b"] = P.VecFromDevicePointer(d["b"].data_ptr(), n_loc)
-                h["lb"] = P.VecFromDevicePointer(d["lb"].data_ptr(), n_loc)
-                h["x"] = P.VecFromDevicePointer(d["x"].data_ptr(), n_loc)
+                for k in vec_keys + ("x",):
+                    h[k] = P.VecFromDevicePointer(d[k].data_ptr(), n_loc)
                 h["dev"] = d
             else:
                 # row-partitioned: the library splits diagonal / off-diagonal blocks on the host, then everything is resident
                 h["A"] = P.MatCreateAIJ(pr.ia, pr.ja, pr.a, ncols_local=n_loc)
-                d = {k: host[k].to(dev) for k in ("b", "lb")}
+                d = {k: host[k].to(dev) for k in vec_keys}
                 d["x"] = torch.zeros(n_loc, dtype=torch.float64, device=dev)
-                h["b"] = P.VecFromDevicePointer(d["b"].data_ptr(), n_loc)
-                h["lb"] = P.VecFromDevicePointer(d["lb"].data_ptr(), n_loc)
-                h["x"] = P.VecFromDevicePointer(d["x"].data_ptr(), n_loc)
+                for k in vec_keys + ("x",):
+                    h[k] = P.VecFromDevicePointer(d[k].data_ptr(), n_loc)
                 h["dev"] = d
         else:
             h["xh"] = torch.zeros(n_loc, dtype=torch.float64).pin_memory()
             h["A"] = P.MatCreateAIJ(host["ia"].numpy(), host["ja"].numpy(), host["a"].numpy(), ncols_local=n_loc)
-            h["b"] = P.VecFromArray(host["b"].numpy())
-            h["lb"] = P.VecFromArray(host["lb"].numpy())
+            for k in vec_keys:
+                h[k] = P.VecFromArray(host[k].numpy())
             h["x"] = P.VecFromArray(h["xh"].numpy())
         qp = P.QPCreate()
-        P.QPSetOperator(qp, h["A"]); P.QPSetRhs(qp, h["b"]); P.QPSetInitialVector(qp, h["x"]); P.QPSetBox(qp, None, h["lb"], None)
+        P.QPSetOperator(qp, h["A"]); P.QPSetRhs(qp, h["b"]); P.QPSetInitialVector(qp, h["x"]); P.QPSetBox(qp, None, h["lb"], h.get("ub"))
         qps = P.QPSCreate()
         P.QPSSetType(qps, "mpgp")
         P.QPSSetQP(qps, qp)
@@ -281,7 +287,7 @@ def main():
 
     def destroy(h):
         P.QPSDestroy(h["qps"]); P.QPDestroy(h["qp"])
-        for k in ("x", "b", "lb"):
+        for k in ("x",) + vec_keys:
             P.VecDestroy(h[k])
         P.MatDestroy(h["A"])
 
@@ -333,7 +339,7 @@ def main():
                     frac=round(achieved / peak, 4), traffic=None, peak_source=peak_src, launches=ka["launches"], avg_launch_ms=round(ka_ms, 5),
                     algorithmic_bytes_per_launch=ka["bytes_per_launch"], kernel_share_of_step=round(ka["total_ms"] / total_prof_ms, 4) if total_prof_ms else None,
                     family_ms=fam_ms)
-    step_bytes, b_cg, b_exp = algorithmic_bytes(n_loc, nnz_loc, counts)
+    step_bytes, b_cg, b_exp = algorithmic_bytes(n_loc, nnz_loc, counts, both_bounds=both)
     whole_iter_gbs = step_bytes / (ms * 1e-3) / 1e9
     destroy(h)
     keep.clear()

@@ -186,3 +186,22 @@ def test_unaligned_device_arrays_use_plain_load_path(P):
     for v in (b, lb, x):
         P.VecDestroy(v)
     P.MatDestroy(A)
+
+
+@pytest.mark.parametrize("prob,opt,okw", [
+    ("ex1", "-qps_mpgp_fallback 1 -qps_mpgp_expansion_type g -qps_mpgp_alpha 3.0", dict(fallback=1, exptype="g", alpha_user=3.0)),                      # 1 fallback taken
+    ("ex1", "-qps_mpgp_fallback2 1 -qps_mpgp_expansion_type g -qps_mpgp_expansion_length_type opt", dict(fallback2=1, exptype="g", explengthtype="opt")),  # 10 cost increases
+    ("ob32", "-qps_mpgp_fallback2 1 -qps_mpgp_expansion_type gf -qps_mpgp_alpha 3.5", dict(fallback2=1, exptype="gf", alpha_user=3.5)),
+    ("ex1", "-qps_mpgp_expansion_type ggr -qps_mpgp_expansion_length_type bb", dict(exptype="ggr", explengthtype="bb")),                                 # the reference diverges (DTOL)
+    ("ex1", "-qps_mpgp_expansion_type gfgr -qps_mpgp_expansion_length_type optapprox", dict(exptype="gfgr", explengthtype="optapprox"))])
+def test_fallback_and_remaining_expansion_variants(P, prob, opt, okw):
+    """mpgp.c:582-611 (fallback / fallback2) and the remaining expansion-type x length-type pairs, generic GPU driver;
+    whatever the reference does on these inputs (including diverging) the GPU path must do too"""
+    pr = PR.tutorial_ex1(100) if prob == "ex1" else PR.obstacle2d(32, -100.0)
+    r = P.solve_problem(pr, "mpgp", opt)
+    xr, ro = oracle(pr, **okw)
+    assert r.reason == ro["reason"], (r.reason, ro["reason"])
+    assert abs(r.its - ro["its"]) <= max(5, 0.08 * ro["its"]), (r.its, ro["its"])
+    assert abs(r.counts["nmv"] - ro["nmv"]) <= max(8, 0.08 * ro["nmv"])
+    if ro["reason"] > 0:
+        assert np.linalg.norm(r.x - xr) <= 1e-4 * np.linalg.norm(xr)
