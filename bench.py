@@ -102,17 +102,20 @@ def generate(spec, rank, size):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md clocks line)."""
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md clocks line).  The sampler is
+    started before the warm-up so that it is already running when the (possibly very short) timed window opens; samples
+    are selected by wall-clock time stamps, falling back to warm-up + timed when the window caught none."""
     Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
     def __init__(self, index):
         self.index = index
         self.rows = []
         self.proc = None
+        self.t0 = self.t1 = None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -121,31 +124,47 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append(line.strip())
+            self.rows.append((time.time(), line.strip()))
+
+    def window_open(self):
+        self.t0 = time.time()
+
+    def window_close(self):
+        self.t1 = time.time()
 
     def stop(self):
         if not self.proc:
             return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        time.sleep(0.05)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
-        sm, mx, reasons, pw = [], [], set(), []
-        for r in self.rows:
-            f = [t.strip() for t in r.split(",")]
-            if len(f) < 7:
-                continue
-            try:
-                sm.append(float(f[0])); mx.append(float(f[1])); pw.append(float(f[2]))
-            except ValueError:
-                continue
-            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
-                if val.lower().startswith("active"):
-                    reasons.add(name)
+
+        def parse(rows):
+            sm, mx, reasons, pw = [], [], set(), []
+            for _, r in rows:
+                f = [t.strip() for t in r.split(",")]
+                if len(f) < 7:
+                    continue
+                try:
+                    sm.append(float(f[0])); mx.append(float(f[1])); pw.append(float(f[2]))
+                except ValueError:
+                    continue
+                for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                    if val.lower().startswith("active"):
+                        reasons.add(name)
+            return sm, mx, reasons, pw
+
+        inwin = [r for r in self.rows if self.t0 is not None and self.t1 is not None and self.t0 <= r[0] <= self.t1 + 0.03]
+        window = "timed"
+        if not inwin:
+            inwin, window = self.rows, "warmup+timed (timed window shorter than the sampling period)"
+        sm, mx, reasons, pw = parse(inwin)
         if not sm:
             return dict(sm_mhz=None, sm_max_mhz=None, reasons=["no samples"])
-        return dict(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), power_w_max=float(max(pw)), samples=len(sm), reasons=sorted(reasons))
+        return dict(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), power_w_max=float(max(pw)), samples=len(sm), window=window, reasons=sorted(reasons))
 
 
 def algorithmic_bytes(n, nnz, counts, both_bounds=False):
@@ -297,20 +316,22 @@ def main():
     P.QPSSetTolerances(h["qps"], rtol=1e-30, atol=1e-300, maxits=W - 1)     # never converge inside the window
     P.QPSSetUp(h["qps"])                                                      # upload done, power method done
     maxeig = P.QPSMPGPGetOperatorMaxEigenvalue(h["qps"])
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     P.QPSSolve(h["qps"])                                                      # W warm-up iterations
     assert P.QPSGetIterationNumber(h["qps"]) == W, (P.QPSGetIterationNumber(h["qps"]), W)
     x_after_warmup = h["dev"]["x"].clone()
     c_warm = P.QPSMPGPGetStepCounts(h["qps"])
     P.QPSSetTolerances(h["qps"], maxits=K - 1)
-    sampler = ClockSampler(local_rank)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     launches0 = P.launch_count()
     barrier()
-    sampler.start()
+    sampler.window_open()
     e0.record(stream)
     P.QPSSolve(h["qps"])                                                      # exactly K timed iterations
     e1.record(stream)
     barrier()
+    sampler.window_close()
     clocks = sampler.stop()
     ms = max_over_ranks(e0.elapsed_time(e1))
     launches = P.launch_count() - launches0

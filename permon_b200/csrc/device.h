@@ -101,6 +101,26 @@ struct HaloPush {
   const int          *send_idx = nullptr;
   unsigned           *counter = nullptr;
 };
+// control step folded into the prologue of K_B (ctrl_A) / K_C (ctrl_B): every CTA recomputes the (tiny, deterministic)
+// scalar logic from the reduction records into shared memory; CTA 0 stores the new state for the following kernels.
+struct CtrlFold {
+  int                       fold = 0;
+  const MpgpCtl            *Sin = nullptr;    // fold: state before the control step; else: state after it
+  MpgpCtl                  *Sout = nullptr;   // fold: where CTA 0 stores the updated state
+  const double             *rec0 = nullptr, *rec1 = nullptr;       // rank-0 record (K_B: rec0 = after K_A; K_C: rec0 = after K_B, rec1 = after K_A')
+  const unsigned long long *flags0 = nullptr, *flags1 = nullptr;   // peer-memory mode: local flags to wait on (one per rank)
+  unsigned long long        seq0 = 0, seq1 = 0;
+  int                       size = 1;
+};
+// halo push fused into the kernel that produces the vector (contiguous boundary ranges, e.g. slab partitions)
+struct PushRanges {
+  int                 n = 0;
+  int                 lo[PB_MAXNEIGH], hi[PB_MAXNEIGH];
+  double             *dst[PB_MAXNEIGH];
+  unsigned long long *flag[PB_MAXNEIGH];
+  unsigned           *counter = nullptr;
+  int                 gap_lo = 0, gap_hi = 0;   // largest run of rows outside every range
+};
 struct HaloWait {
   const unsigned long long *flags = nullptr;   // local: one flag slot (PB_FLAG_STRIDE apart) per neighbour
   int                       n = 0;
@@ -156,9 +176,9 @@ int k_ctrl_A_p2p(MpgpCtl *S, const P2PWin *win, const double *my_slot, const uns
 int k_ctrl_E_p2p(MpgpCtl *S, const P2PWin *win, const double *my_slot, const unsigned long long *my_flag, unsigned long long seq);
 int k_ctrl_B_p2p(MpgpCtl *S, const P2PWin *win, const double *my_slot, const unsigned long long *my_flag, unsigned long long seq1, unsigned long long seq2);
 // K_B  : the c / p / e update of x, g (+ split, reductions)
-int k_fused_B(const MpgpVecs &v, const MpgpCtl *S, RedBuf rb);
+int k_fused_B(const MpgpVecs &v, const CtrlFold &cf, RedBuf rb, const PushRanges *d_push_x, unsigned long long push_seq);   // d_push_x: device memory or NULL
 // K_C  : direction update p = gf - bcg p | p = gc | nothing
-int k_fused_C(const MpgpVecs &v, const MpgpCtl *S);
+int k_fused_C(const MpgpVecs &v, const CtrlFold &cf, const PushRanges *d_push_p, unsigned long long push_seq);
 // initial projection x = P(x) (+ B u)
 int k_fused_project(const MpgpVecs &v, const MpgpCtl *S, RedBuf rb);
 // plain product-operator first factor, device-driven: t = M2 xin when the phase is active

@@ -18,6 +18,7 @@
 //   QPCGrads_Box        src/qpc/impls/box/qpcbox.c:41-55      QPCGradReduced_Box  :86-92
 //   QPCFeas_Box         src/qpc/impls/box/qpcbox.c:125-137    QPCProject_Box      :298-303
 //   MPGP step formulas  src/qps/impls/mpgp/mpgp.c:299-323 (expansion), :553-560 (CG), :623-638 (proportioning)
+#include <climits>
 #include <cuda_runtime.h>
 #include <stdarg.h>
 #include <stdio.h>
@@ -1060,6 +1061,48 @@ int k_halo_push(const HaloPush &hp, const double *vec, int gated, unsigned long 
 // =====================================================================================================
 // K_B: fused step  (mpgp.c:553-555 CG, :633-638 proportioning, :316-321 expansion std/fixed)
 // =====================================================================================================
+// control-step prologues, kept out of line so that their register needs do not set the budget of the streaming loops
+__device__ __noinline__ void fold_ctrl_A(const CtrlFold &cf, MpgpCtl *sS)
+{
+  *sS = *cf.Sin;
+  mpgp_ctrl_A(sS, cf.rec0);
+  if (blockIdx.x == 0) *cf.Sout = *sS;
+}
+__device__ __noinline__ void fold_ctrl_B(const CtrlFold &cf, MpgpCtl *sS, bool second)
+{
+  *sS = *cf.Sin;
+  mpgp_ctrl_B(sS, second ? cf.rec1 : cf.rec0);
+  if (blockIdx.x == 0) *cf.Sout = *sS;
+}
+
+// fused halo push helpers: the thread that produces a boundary value also stores it into the neighbours' ghost windows
+__device__ __forceinline__ void push_boundary(const PushRanges *hp, int r, double val)
+{
+  const int n = hp->n;
+  for (int q = 0; q < n; q++) {
+    const int lo = hp->lo[q];
+    if (r >= lo && r < hp->hi[q]) hp->dst[q][r - lo] = val;
+  }
+}
+// rows in [gap_lo, gap_hi) belong to no send range (the interior of the block): two register compares per element keep the
+// fused push off the hot loop
+// after all CTAs fenced their peer stores, the last one raises the neighbours' flags (called by every thread of every CTA)
+__device__ __forceinline__ void push_signal(const PushRanges *hp, unsigned long long seq, int *s_last)
+{
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned t = atomicAdd(hp->counter, 1u);
+    *s_last    = (t == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (*s_last) {
+    __threadfence_system();
+    if ((int)threadIdx.x < hp->n) *(volatile unsigned long long *)hp->flag[threadIdx.x] = seq;
+    if (threadIdx.x == 0) *hp->counter = 0u;
+  }
+}
+
 // one element of the c / p update (mpgp.c:553-558 CG, :633-638 proportioning)
 template <bool EQ>
 __device__ __forceinline__ void update_cp_elem(int step, double acg, double astol, double xr, double pr, double g0, double apr, const BoxVal &b, const double *brow, int m,
@@ -1112,11 +1155,29 @@ __device__ __forceinline__ double penal_apr(double apr, double rho, const double
 }
 
 // K_B.  EQ: equality rows present (SMALXE inner solve).  VEC2: 16-byte accesses (n even, pointers 16-byte aligned).
-template <bool EQ, bool VEC2>
-__global__ void __launch_bounds__(NT, EQ ? 3 : 5) k_update_B(MpgpVecs v, const MpgpCtl *__restrict__ S, RedBuf rb)
+template <bool EQ, bool VEC2, bool PUSH>
+__global__ void __launch_bounds__(NT, EQ ? 3 : 4) k_update_B(MpgpVecs v, CtrlFold cf, RedBuf rb, const PushRanges *__restrict__ hp, unsigned long long push_seq)
 {
-  if (S->reason != 0) return;
+  __shared__ MpgpCtl sS;
+  __shared__ int     s_plast;
+  const MpgpCtl     *S = cf.Sin;
+  if (cf.fold) {   // ctrl_A in the prologue: step selection from the K_A records (mpgp.c:541-547,617-621)
+    if (cf.Sin->reason != 0) {
+      if (blockIdx.x == 0 && threadIdx.x == 0) *cf.Sout = *cf.Sin;   // hand the stop on to K_A' / K_C
+      return;
+    }
+    if (cf.flags0) {
+      if ((int)threadIdx.x < cf.size) wait_flag(cf.flags0 + (size_t)threadIdx.x * PB_FLAG_STRIDE, cf.seq0);
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) fold_ctrl_A(cf, &sS);
+    __syncthreads();
+    S = &sS;
+  } else if (S->reason != 0) {
+    return;
+  }
   const int    step = S->step;
+  const bool   pushx = PUSH && (step == 'e');
   const double acg = S->acg, afeas = S->afeas, alpha = S->alpha, rho = S->rho, astol = v.bx.astol;
   const int    m = v.m, n = v.n;
   double       bp[PB_MAXEQ] = {0.0, 0.0, 0.0, 0.0};
@@ -1135,6 +1196,11 @@ __global__ void __launch_bounds__(NT, EQ ? 3 : 5) k_update_B(MpgpVecs v, const M
     const double2 *x2 = reinterpret_cast<const double2 *>(v.x), *p2 = reinterpret_cast<const double2 *>(v.p), *g2 = reinterpret_cast<const double2 *>(v.g),
                   *A2 = reinterpret_cast<const double2 *>(v.Ap), *l2 = reinterpret_cast<const double2 *>(v.bx.lb), *u2 = reinterpret_cast<const double2 *>(v.bx.ub);
     double2 *xo = reinterpret_cast<double2 *>(v.x), *go = reinterpret_cast<double2 *>(v.g), *fo = reinterpret_cast<double2 *>(v.gf), *po = reinterpret_cast<double2 *>(v.p);
+    int glo = INT_MAX, ghi = INT_MAX;
+    if (PUSH && pushx) {
+      glo = hp->gap_lo;
+      ghi = hp->gap_hi;
+    }
     for (int i = blockIdx.x * NT + threadIdx.x; i < n2; i += stride) {
       const double2 xr = x2[i], pr = p2[i], g0 = g2[i], ap = A2[i];
       BoxVal        b0, b1;
@@ -1159,6 +1225,10 @@ __global__ void __launch_bounds__(NT, EQ ? 3 : 5) k_update_B(MpgpVecs v, const M
         xn.x  = update_e_elem<EQ>(afeas, alpha, astol, xr.x, pr.x, g0.x, a0, b0, br0, m, acc);
         xn.y  = update_e_elem<EQ>(afeas, alpha, astol, xr.y, pr.y, g0.y, a1, b1, br1, m, acc);
         xo[i] = xn;
+        if (PUSH && (2 * i < glo || 2 * i + 1 >= ghi)) {
+          push_boundary(hp, 2 * i, xn.x);
+          push_boundary(hp, 2 * i + 1, xn.y);
+        }
       } else {
         double2 xn, gn, gf;
         update_cp_elem<EQ>(step, acg, astol, xr.x, pr.x, g0.x, a0, b0, br0, m, xn.x, gn.x, gf.x, acc);
@@ -1170,13 +1240,20 @@ __global__ void __launch_bounds__(NT, EQ ? 3 : 5) k_update_B(MpgpVecs v, const M
       }
     }
   } else {
+    int glo = INT_MAX, ghi = INT_MAX;
+    if (PUSH && pushx) {
+      glo = hp->gap_lo;
+      ghi = hp->gap_hi;
+    }
     for (int r = blockIdx.x * NT + threadIdx.x; r < n; r += stride) {
       const double xr = v.x[r], pr = v.p[r], g0 = v.g[r];
       double       brow[PB_MAXEQ];
       const double apr = penal_apr<EQ>(v.Ap[r], rho, v.B, n, r, m, bp, brow);
       const BoxVal b = load_box(v.bx, r);
       if (step == 'e') {
-        v.x[r] = update_e_elem<EQ>(afeas, alpha, astol, xr, pr, g0, apr, b, brow, m, acc);
+        const double xn = update_e_elem<EQ>(afeas, alpha, astol, xr, pr, g0, apr, b, brow, m, acc);
+        v.x[r]          = xn;
+        if (PUSH && (r < glo || r >= ghi)) push_boundary(hp, r, xn);
       } else {
         double xn, gn, gf;
         update_cp_elem<EQ>(step, acg, astol, xr, pr, g0, apr, b, brow, m, xn, gn, gf, acc);
@@ -1188,9 +1265,16 @@ __global__ void __launch_bounds__(NT, EQ ? 3 : 5) k_update_B(MpgpVecs v, const M
     }
   }
   grid_reduce8<0>(acc, rb, nullptr);
+  if (PUSH && pushx) push_signal(hp, push_seq, &s_plast);
 }
 
-int k_fused_B(const MpgpVecs &v, const MpgpCtl *S, RedBuf rb)
+template <bool EQ, bool VEC2>
+static void launch_B(int grid, const MpgpVecs &v, const CtrlFold &cf, RedBuf rb, const PushRanges *hp, unsigned long long seq)
+{
+  if (hp) k_update_B<EQ, VEC2, true><<<grid, NT, 0, g_ctx.stream>>>(v, cf, rb, hp, seq);
+  else k_update_B<EQ, VEC2, false><<<grid, NT, 0, g_ctx.stream>>>(v, cf, rb, nullptr, 0);
+}
+int k_fused_B(const MpgpVecs &v, const CtrlFold &cf, RedBuf rb, const PushRanges *hp, unsigned long long push_seq)
 {
   const bool vec2 = (v.n % 2 == 0) && aligned16(v.x) && aligned16(v.p) && aligned16(v.g) && aligned16(v.Ap) && aligned16(v.gf) && aligned16(v.bx.lb) && aligned16(v.bx.ub) &&
                     !getenv("PERMON_B200_NOVEC");
@@ -1201,11 +1285,11 @@ int k_fused_B(const MpgpVecs &v, const MpgpCtl *S, RedBuf rb)
   // x p g Ap lb[ub] read, x g gf written (CG step)
   prof_pre(KF_UPDATE_B, 8.0 * v.n * (7 + (v.bx.lb ? 1 : 0) + (v.bx.ub ? 1 : 0) + v.m));
   if (v.m > 0) {
-    if (vec2) k_update_B<true, true><<<grid, NT, 0, g_ctx.stream>>>(v, S, rb);
-    else k_update_B<true, false><<<grid, NT, 0, g_ctx.stream>>>(v, S, rb);
+    if (vec2) launch_B<true, true>(grid, v, cf, rb, hp, push_seq);
+    else launch_B<true, false>(grid, v, cf, rb, hp, push_seq);
   } else {
-    if (vec2) k_update_B<false, true><<<grid, NT, 0, g_ctx.stream>>>(v, S, rb);
-    else k_update_B<false, false><<<grid, NT, 0, g_ctx.stream>>>(v, S, rb);
+    if (vec2) launch_B<false, true>(grid, v, cf, rb, hp, push_seq);
+    else launch_B<false, false>(grid, v, cf, rb, hp, push_seq);
   }
   prof_post(KF_UPDATE_B);
   LAUNCH_CHECK();
@@ -1215,31 +1299,84 @@ int k_fused_B(const MpgpVecs &v, const MpgpCtl *S, RedBuf rb)
 // =====================================================================================================
 // K_C: direction update  (mpgp.c:560 p = gf - bcg p ; :623 p = gc)
 // =====================================================================================================
-__global__ void __launch_bounds__(NT) k_direction_C(MpgpVecs v, const MpgpCtl *__restrict__ S)
+template <bool PUSH>
+__global__ void __launch_bounds__(NT, 8) k_direction_C(MpgpVecs v, CtrlFold cf, const PushRanges *__restrict__ hp, unsigned long long push_seq, int vec2)
 {
-  const int pmode = S->pmode;
-  if (S->reason != 0 || pmode == 0) return;
+  __shared__ MpgpCtl sS;
+  __shared__ int     s_plast;
+  const MpgpCtl     *S = cf.Sin;
+  if (cf.fold) {   // ctrl_B in the prologue: norms, stopping test, beta, next step kind (mpgp.c:514-535,558-559)
+    if (cf.Sin->reason != 0) return;
+    const bool                second = (cf.Sin->step == 'e' || cf.Sin->init);   // record of K_A' or of K_B
+    const unsigned long long *fl = second ? cf.flags1 : cf.flags0;
+    if (fl) {
+      if ((int)threadIdx.x < cf.size) wait_flag(fl + (size_t)threadIdx.x * PB_FLAG_STRIDE, second ? cf.seq1 : cf.seq0);
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) fold_ctrl_B(cf, &sS, second);
+    __syncthreads();
+    S = &sS;
+  }
+  if (S->reason != 0) return;
+  const int    pmode = S->pmode;
   const double bcg = S->bcg, astol = v.bx.astol;
   const int    stride = gridDim.x * NT;
   if (pmode == 1) {
-    for (int r = blockIdx.x * NT + threadIdx.x; r < v.n; r += stride) v.p[r] = v.gf[r] - bcg * v.p[r];
-  } else {
+    if (vec2) {
+      const double2 *f2 = reinterpret_cast<const double2 *>(v.gf);
+      double2       *p2 = reinterpret_cast<double2 *>(v.p);
+      const int      n2 = v.n >> 1;
+      int            glo = INT_MAX, ghi = INT_MAX;
+      if (PUSH) {
+        glo = hp->gap_lo;
+        ghi = hp->gap_hi;
+      }
+      for (int i = blockIdx.x * NT + threadIdx.x; i < n2; i += stride) {
+        const double2 f = f2[i], q = p2[i];
+        double2       pn;
+        pn.x  = f.x - bcg * q.x;
+        pn.y  = f.y - bcg * q.y;
+        p2[i] = pn;
+        if (PUSH && (2 * i < glo || 2 * i + 1 >= ghi)) {
+          push_boundary(hp, 2 * i, pn.x);
+          push_boundary(hp, 2 * i + 1, pn.y);
+        }
+      }
+    } else {
+      for (int r = blockIdx.x * NT + threadIdx.x; r < v.n; r += stride) {
+        const double pn = v.gf[r] - bcg * v.p[r];
+        v.p[r]          = pn;
+        if (PUSH) push_boundary(hp, r, pn);
+      }
+    }
+  } else if (pmode == 2) {
     for (int r = blockIdx.x * NT + threadIdx.x; r < v.n; r += stride) {
       double gf, gc;
       box_split(v.x[r], v.g[r], load_box(v.bx, r), astol, gf, gc);
       v.p[r] = gc;
+      if (PUSH) push_boundary(hp, r, gc);
+    }
+  } else if (PUSH) {   // p is already final (written by K_B or K_A'): only the boundary values travel
+    const int nq = hp->n;
+    for (int q = 0; q < nq; q++) {
+      const int lo = hp->lo[q], hi = hp->hi[q];
+      double   *dst = hp->dst[q];
+      for (int r = lo + blockIdx.x * NT + threadIdx.x; r < hi; r += stride) dst[r - lo] = v.p[r];
     }
   }
+  if (PUSH) push_signal(hp, push_seq, &s_plast);
 }
 
-int k_fused_C(const MpgpVecs &v, const MpgpCtl *S)
+int k_fused_C(const MpgpVecs &v, const CtrlFold &cf, const PushRanges *hp, unsigned long long push_seq)
 {
   int grid = elementwise_grid();
   int need = (v.n + NT - 1) / NT;
   if (need < 1) need = 1;
   if (grid > need) grid = need;
+  const int vec2 = (v.n % 2 == 0) && aligned16(v.gf) && aligned16(v.p) && !getenv("PERMON_B200_NOVEC");
   prof_pre(KF_DIR_C, 8.0 * v.n * 3);
-  k_direction_C<<<grid, NT, 0, g_ctx.stream>>>(v, S);
+  if (hp) k_direction_C<true><<<grid, NT, 0, g_ctx.stream>>>(v, cf, hp, push_seq, vec2);
+  else k_direction_C<false><<<grid, NT, 0, g_ctx.stream>>>(v, cf, nullptr, 0, vec2);
   prof_post(KF_DIR_C);
   LAUNCH_CHECK();
   return 0;

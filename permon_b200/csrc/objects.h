@@ -80,6 +80,9 @@ struct HaloPlan {
   pb::HaloPush          push[2];
   unsigned long long    hseq[2] = {0, 0};
   std::vector<void *>   peer_gwins;
+  bool                  contig = false;                       // every pack list is one ascending run of rows
+  std::vector<PetscInt> send_lo;                              // first row of each run
+  pb::PushRanges       *d_ranges = nullptr;                   // device copies [2] (p, x) for the fused pushes
   // host copy of the split matrix, kept until the first device use (lets the plan be built and inspected
   // without a GPU; the arithmetic still needs one)
   struct HostSplit {

@@ -619,7 +619,7 @@ int MpgpImpl::engine_init(QPS qps)
 {
   if (engine_ready) return 0;
   PB_CHK(dev_init());
-  PB_CUDA(cudaMalloc(&dS, sizeof(MpgpCtl)));
+  PB_CUDA(cudaMalloc(&dS, 2 * sizeof(MpgpCtl)));
   PB_CUDA(cudaMallocHost(&hS, sizeof(MpgpCtl)));
   PB_CHK(RA.init(qps->comm));
   PB_CHK(RB.init(qps->comm));
@@ -686,9 +686,18 @@ int MpgpImpl::solve_fused(QPS qps)
   *hS = S;
   PB_CUDA(cudaMemcpyAsync(dS, hS, sizeof(MpgpCtl), cudaMemcpyHostToDevice, s));
 
+  // Two copies of the control block: S0 = state at the top of the iteration (after ctrl_B), S1 = state after
+  // ctrl_A.  In the device-driven mode ctrl_A / ctrl_B run in the prologues of K_B / K_C (every CTA recomputes the
+  // scalar step from the records into shared memory, CTA 0 stores the other copy).  With host callbacks
+  // (fold == false) the stand-alone ctrl kernels update S0 in place and S1 aliases S0.
+  const bool fold = !host_conv && !getenv("PERMON_B200_NOFOLD");
+  MpgpCtl   *S0 = dS, *S1 = fold ? dS + 1 : dS;
+  if (fold) PB_CUDA(cudaMemcpyAsync(dS + 1, hS, sizeof(MpgpCtl), cudaMemcpyHostToDevice, s));
+
   // multi-GPU plumbing: peer-memory pushes (CUDA IPC over NVLink) when available, NCCL otherwise
   MPI_Comm   comm = qps->comm;
   const bool p2p = multi && comm->p2p && H && H->p2p;
+  const bool fused_push = p2p && H->contig && !getenv("PERMON_B200_NOFUSEDPUSH");
   auto red = [&](Reducer &R, int kind, bool publish) -> RedBuf {
     RedBuf rb = R.rb;
     if (p2p && publish) {
@@ -698,45 +707,81 @@ int MpgpImpl::solve_fused(QPS qps)
     }
     return rb;
   };
-  auto gather_ctrl_A = [&]() -> int {
-    if (p2p) return k_ctrl_A_p2p(dS, comm->d_win, comm->my_slot, comm->my_flag, comm->seq[0]);
-    PB_CHK(RA.gather());
-    return k_ctrl_A(dS, RA.d_all);
+  auto rec_ptr = [&](Reducer &R, int kind) -> const double * {   // rank-0 record of the current sequence number
+    return p2p ? comm->my_slot + p2p_slot_index(kind, comm->seq[kind], 0) : R.d_all;
   };
-  auto gather_ctrl_E = [&]() -> int {
-    if (p2p) return k_ctrl_E_p2p(dS, comm->d_win, comm->my_slot, comm->my_flag, comm->seq[1]);
+  auto flag_ptr = [&](int kind) -> const unsigned long long * { return p2p ? comm->my_flag + p2p_flag_index(kind, 0) : nullptr; };
+  auto gather_ctrl_E = [&]() -> int {   // B u of the new iterate for the second SpMV (SMALXE only)
+    if (p2p) return k_ctrl_E_p2p(S1, comm->d_win, comm->my_slot, comm->my_flag, comm->seq[1]);
     PB_CHK(RB.gather());
-    return k_ctrl_E(dS, RB.d_all);
+    return k_ctrl_E(S1, RB.d_all);
   };
-  auto gather_ctrl_B = [&]() -> int {
-    if (p2p) return k_ctrl_B_p2p(dS, comm->d_win, comm->my_slot, comm->my_flag, comm->seq[1], comm->seq[2]);
-    PB_CHK(RB.gather());
-    return k_ctrl_B(dS, RB.d_all);
-  };
-  auto second_spmv = [&]() -> int {   // K_A' with its halo / product plumbing
+  auto second_spmv = [&](bool x_already_pushed) -> int {   // K_A' with its halo / product plumbing
     const double *xin = v.x;
     if (prod) {
-      PB_CHK(k_spmv_gated(M2->Ad, v.x, v.t, dS, 1));
+      PB_CHK(k_spmv_gated(M2->Ad, v.x, v.t, S1, 1));
       xin = v.t;
     }
     if (H) {
-      if (p2p) PB_CHK(k_halo_push(H->push[1], v.x, 1, ++H->hseq[1], dS));
-      else PB_CHK(mat_halo_begin(M1, v.x));
+      if (p2p) {
+        if (!x_already_pushed) PB_CHK(k_halo_push(H->push[1], v.x, 1, ++H->hseq[1], S1));
+      } else {
+        PB_CHK(mat_halo_begin(M1, v.x));
+      }
     }
-    PB_CHK(k_fused_A2(M1->Ad, xin, v, dS, red(RB, 2, !H), skip));
+    PB_CHK(k_fused_A2(M1->Ad, xin, v, S1, red(RB, 2, !H), skip));
     if (H) {
       if (p2p) {
         HaloWait hw{H->my_hflags[1], (int)H->neigh.size(), H->hseq[1]};
-        PB_CHK(k_fused_A_ghost(M1->Ao, H->d_ghost2[1], v, dS, red(RB, 2, true), 1, hw));
+        PB_CHK(k_fused_A_ghost(M1->Ao, H->d_ghost2[1], v, S1, red(RB, 2, true), 1, hw));
       } else {
         PB_CHK(mat_halo_end(M1));
-        PB_CHK(k_fused_A_ghost(M1->Ao, H->d_ghost, v, dS, RB.rb, 1, HaloWait()));
+        PB_CHK(k_fused_A_ghost(M1->Ao, H->d_ghost, v, S1, RB.rb, 1, HaloWait()));
       }
     }
     return 0;
   };
+  auto step_B = [&]() -> int {   // [all-gather] -> ctrl_A -> K_B (+ x halo push in expansion steps)
+    if (!p2p) PB_CHK(RA.gather());
+    CtrlFold cf;
+    cf.fold = fold ? 1 : 0;
+    cf.Sin  = S0;
+    cf.Sout = S1;
+    cf.size = comm->size;
+    if (fold) {
+      cf.rec0   = rec_ptr(RA, 0);
+      cf.flags0 = flag_ptr(0);
+      cf.seq0   = comm->seq[0];
+    } else {
+      if (p2p) PB_CHK(k_ctrl_A_p2p(S0, comm->d_win, comm->my_slot, comm->my_flag, comm->seq[0]));
+      else PB_CHK(k_ctrl_A(S0, RA.d_all));
+    }
+    if (fused_push) return k_fused_B(v, cf, red(RB, 1, true), H->d_ranges + 1, ++H->hseq[1]);
+    return k_fused_B(v, cf, red(RB, 1, true), nullptr, 0);
+  };
+  auto step_C = [&](bool ctrl_done) -> int {   // [all-gather] -> ctrl_B -> K_C (+ p halo push)
+    CtrlFold cf;
+    cf.fold = (fold && !ctrl_done) ? 1 : 0;
+    cf.Sin  = fold ? S1 : S0;
+    cf.Sout = S0;
+    cf.size = comm->size;
+    if (cf.fold) {
+      cf.rec0   = rec_ptr(RB, 1);
+      cf.rec1   = rec_ptr(RB, 2);
+      cf.flags0 = flag_ptr(1);
+      cf.flags1 = flag_ptr(2);
+      cf.seq0   = comm->seq[1];
+      cf.seq1   = comm->seq[2];
+    }
+    if (fused_push) return k_fused_C(v, cf, H->d_ranges, ++H->hseq[0]);
+    return k_fused_C(v, cf, nullptr, 0);
+  };
+  auto ctrl_B_standalone = [&]() -> int {
+    if (p2p) return k_ctrl_B_p2p(S0, comm->d_win, comm->my_slot, comm->my_flag, comm->seq[1], comm->seq[2]);
+    return k_ctrl_B(S0, RB.d_all);
+  };
   auto host_step = [&](bool *stop) -> int {   // per-iteration host involvement (monitors / user test)
-    PB_CUDA(cudaMemcpyAsync(hS, dS, sizeof(MpgpCtl), cudaMemcpyDeviceToHost, s));
+    PB_CUDA(cudaMemcpyAsync(hS, S0, sizeof(MpgpCtl), cudaMemcpyDeviceToHost, s));
     PB_CUDA(cudaStreamSynchronize(s));
     qps->iteration  = hS->iteration;
     qps->rnorm      = hS->rnorm;
@@ -749,19 +794,22 @@ int MpgpImpl::solve_fused(QPS qps)
     *stop = (qps->reason != KSP_CONVERGED_ITERATING);
     if (*stop) {
       hS->reason = qps->reason;
-      PB_CUDA(cudaMemcpyAsync((char *)dS + offsetof(MpgpCtl, reason), &hS->reason, sizeof(int), cudaMemcpyHostToDevice, s));
+      PB_CUDA(cudaMemcpyAsync((char *)S0 + offsetof(MpgpCtl, reason), &hS->reason, sizeof(int), cudaMemcpyHostToDevice, s));
     }
     return 0;
   };
 
   // ---- initial phase: x = P(x); g = A x - b; split; p = gf  (mpgp.c:497-507)
-  PB_CHK(k_fused_project(v, dS, red(RB, 1, true)));
+  PB_CHK(k_fused_project(v, S1, red(RB, 1, true)));
   if (v.m > 0) PB_CHK(gather_ctrl_E());
-  PB_CHK(second_spmv());
-  PB_CHK(gather_ctrl_B());
+  PB_CHK(second_spmv(false));
+  if (!p2p) PB_CHK(RB.gather());
   bool stop = false;
-  if (host_conv) PB_CHK(host_step(&stop));
-  if (!stop) PB_CHK(k_fused_C(v, dS));
+  if (!fold) {
+    PB_CHK(ctrl_B_standalone());
+    if (host_conv) PB_CHK(host_step(&stop));
+  }
+  if (!stop) PB_CHK(step_C(!fold));
 
   // ---- main loop
   while (!stop) {
@@ -769,42 +817,47 @@ int MpgpImpl::solve_fused(QPS qps)
     for (int it = 0; it < nb && !stop; it++) {
       const double *xin = v.p;
       if (prod) {
-        PB_CHK(k_spmv_gated(M2->Ad, v.p, v.t, dS, 0));
+        PB_CHK(k_spmv_gated(M2->Ad, v.p, v.t, S0, 0));
         xin = v.t;
       }
       if (H) {
-        if (p2p) PB_CHK(k_halo_push(H->push[0], v.p, 0, ++H->hseq[0], dS));
-        else PB_CHK(mat_halo_begin(M1, v.p));
+        if (p2p) {
+          if (!fused_push) PB_CHK(k_halo_push(H->push[0], v.p, 0, ++H->hseq[0], S0));
+        } else {
+          PB_CHK(mat_halo_begin(M1, v.p));
+        }
       }
-      PB_CHK(k_fused_A(M1->Ad, xin, v, dS, red(RA, 0, !H), skip));
+      PB_CHK(k_fused_A(M1->Ad, xin, v, S0, red(RA, 0, !H), skip));
       if (H) {
         if (p2p) {
           HaloWait hw{H->my_hflags[0], (int)H->neigh.size(), H->hseq[0]};
-          PB_CHK(k_fused_A_ghost(M1->Ao, H->d_ghost2[0], v, dS, red(RA, 0, true), 0, hw));
+          PB_CHK(k_fused_A_ghost(M1->Ao, H->d_ghost2[0], v, S0, red(RA, 0, true), 0, hw));
         } else {
           PB_CHK(mat_halo_end(M1));
-          PB_CHK(k_fused_A_ghost(M1->Ao, H->d_ghost, v, dS, RA.rb, 0, HaloWait()));
+          PB_CHK(k_fused_A_ghost(M1->Ao, H->d_ghost, v, S0, RA.rb, 0, HaloWait()));
         }
       }
-      PB_CHK(gather_ctrl_A());
-      PB_CHK(k_fused_B(v, dS, red(RB, 1, true)));
+      PB_CHK(step_B());
       if (v.m > 0) PB_CHK(gather_ctrl_E());
-      PB_CHK(second_spmv());
-      PB_CHK(gather_ctrl_B());
-      if (host_conv) {
-        PB_CHK(host_step(&stop));
-        if (stop) break;
+      PB_CHK(second_spmv(fused_push));
+      if (!p2p) PB_CHK(RB.gather());
+      if (!fold) {
+        PB_CHK(ctrl_B_standalone());
+        if (host_conv) {
+          PB_CHK(host_step(&stop));
+          if (stop) break;
+        }
       }
-      PB_CHK(k_fused_C(v, dS));
+      PB_CHK(step_C(!fold));
     }
     if (!host_conv) {
-      PB_CUDA(cudaMemcpyAsync(hS, dS, sizeof(MpgpCtl), cudaMemcpyDeviceToHost, s));
+      PB_CUDA(cudaMemcpyAsync(hS, S0, sizeof(MpgpCtl), cudaMemcpyDeviceToHost, s));
       PB_CUDA(cudaStreamSynchronize(s));
       stop = (hS->reason != 0);
     }
   }
   if (host_conv) {
-    PB_CUDA(cudaMemcpyAsync(hS, dS, sizeof(MpgpCtl), cudaMemcpyDeviceToHost, s));
+    PB_CUDA(cudaMemcpyAsync(hS, S0, sizeof(MpgpCtl), cudaMemcpyDeviceToHost, s));
     PB_CUDA(cudaStreamSynchronize(s));
     hS->reason = qps->reason;
   }

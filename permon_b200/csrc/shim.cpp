@@ -902,6 +902,7 @@ _p_Mat::~_p_Mat()
       if (pw) cudaIpcCloseMemHandle(pw);
     if (halo->push[0].counter) cudaFree(halo->push[0].counter);
     if (halo->gwin) cudaFree(halo->gwin);
+    if (halo->d_ranges) cudaFree(halo->d_ranges);
     delete halo->host;
     delete halo;
   }
@@ -1214,6 +1215,43 @@ static int halo_p2p_setup(Mat A)
     H->push[w].counter = cnt + w;
     H->d_ghost2[w]     = (double *)H->gwin + (size_t)w * ng_pad;
     H->my_hflags[w]    = (unsigned long long *)((char *)H->gwin + gbytes) + (size_t)w * PB_MAXNEIGH * PB_FLAG_STRIDE;
+  }
+  // contiguous pack lists (slab partitions): the producing kernels can push the boundary values themselves
+  H->contig = true;
+  H->send_lo.assign(H->neigh.size(), 0);
+  for (size_t q = 0; q < H->neigh.size(); q++) {
+    const PetscInt a = H->send_off[q], b = H->send_off[q + 1];
+    H->send_lo[q] = (b > a) ? H->send_idx[a] : 0;
+    for (PetscInt k = a + 1; k < b; k++)
+      if (H->send_idx[k] != H->send_idx[k - 1] + 1) H->contig = false;
+  }
+  if (H->contig) {
+    PushRanges R[2];
+    for (int w = 0; w < 2; w++) {
+      R[w].n = (int)H->neigh.size();
+      for (int q = 0; q < R[w].n; q++) {
+        R[w].lo[q]   = H->send_lo[q];
+        R[w].hi[q]   = H->send_lo[q] + (H->send_off[q + 1] - H->send_off[q]);
+        R[w].dst[q]  = H->push[w].dst[q];
+        R[w].flag[q] = H->push[w].flag[q];
+      }
+      R[w].counter = H->push[w].counter;
+      // widest run of rows that no range covers: the kernels' cheap "interior" test
+      std::vector<std::pair<int, int>> iv;
+      for (int q = 0; q < R[w].n; q++)
+        if (R[w].hi[q] > R[w].lo[q]) iv.push_back({R[w].lo[q], R[w].hi[q]});
+      std::sort(iv.begin(), iv.end());
+      int best_lo = 0, best_hi = 0, cur = 0;
+      for (auto &I : iv) {
+        if (I.first - cur > best_hi - best_lo) best_lo = cur, best_hi = I.first;
+        cur = std::max(cur, I.second);
+      }
+      if ((int)A->m - cur > best_hi - best_lo) best_lo = cur, best_hi = (int)A->m;
+      R[w].gap_lo = best_lo;
+      R[w].gap_hi = best_hi;
+    }
+    PB_CUDA(cudaMalloc(&H->d_ranges, sizeof R));
+    PB_CUDA(cudaMemcpy(H->d_ranges, R, sizeof R, cudaMemcpyHostToDevice));
   }
   H->p2p = true;
   return 0;
