@@ -167,11 +167,13 @@ class ClockSampler:
         return dict(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), power_w_max=float(max(pw)), samples=len(sm), window=window, reasons=sorted(reasons))
 
 
-def algorithmic_bytes(n, nnz, counts, both_bounds=False):
-    """B_cg = 12 nnz + 4(n+1) + 8 n V ; B_exp = 2 [12 nnz + 4(n+1)] + 8 n V_e ; proportioning ~ B_cg"""
+def algorithmic_bytes(n, nnz, counts, both_bounds=False, matrix_bytes=None):
+    """B_cg = M + 8 n V ; B_exp = 2 M + 8 n V_e ; proportioning ~ B_cg, with M the matrix stream of one SpMV:
+    12 nnz + 4(n+1) for CSR (the survey's formula), or the bytes of the packed tile format the library actually keeps in HBM."""
     V, Ve = (18, 19) if both_bounds else (16, 16)
-    b_cg = 12 * nnz + 4 * (n + 1) + 8 * n * V
-    b_exp = 2 * (12 * nnz + 4 * (n + 1)) + 8 * n * Ve
+    M = 12 * nnz + 4 * (n + 1) if matrix_bytes is None else matrix_bytes
+    b_cg = M + 8 * n * V
+    b_exp = 2 * M + 8 * n * Ve
     return (counts["ncg"] + counts["nprop"]) * b_cg + counts["nexp"] * b_exp, b_cg, b_exp
 
 
@@ -272,22 +274,15 @@ def main():
         """QP + QPS through the C ABI; returns handles"""
         h = {}
         if device_resident:
-            if size == 1:
-                d = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
-                d["x"] = torch.zeros(n_loc, dtype=torch.float64, device=dev)
-                torch.cuda.synchronize()
-                h["A"] = P.MatCreateAIJFromDevicePointers(n_loc, n_loc, d["ia"].data_ptr(), d["ja"].data_ptr(), d["a"].data_ptr())
-                for k in vec_keys + ("x",):
-                    h[k] = P.VecFromDevicePointer(d[k].data_ptr(), n_loc)
-                h["dev"] = d
-            else:
-                # row-partitioned: the library splits diagonal / off-diagonal blocks on the host, then everything is resident
-                h["A"] = P.MatCreateAIJ(pr.ia, pr.ja, pr.a, ncols_local=n_loc)
-                d = {k: host[k].to(dev) for k in vec_keys}
-                d["x"] = torch.zeros(n_loc, dtype=torch.float64, device=dev)
-                for k in vec_keys + ("x",):
-                    h[k] = P.VecFromDevicePointer(d[k].data_ptr(), n_loc)
-                h["dev"] = d
+            # the matrix goes through the host constructor (the library re-codes it into its packed tile format and, when
+            # row-partitioned, splits diagonal / off-diagonal blocks) and is resident before the timed region; vectors are
+            # device arrays owned by the caller
+            h["A"] = P.MatCreateAIJ(pr.ia, pr.ja, pr.a, ncols_local=n_loc)
+            d = {k: host[k].to(dev) for k in vec_keys}
+            d["x"] = torch.zeros(n_loc, dtype=torch.float64, device=dev)
+            for k in vec_keys + ("x",):
+                h[k] = P.VecFromDevicePointer(d[k].data_ptr(), n_loc)
+            h["dev"] = d
         else:
             h["xh"] = torch.zeros(n_loc, dtype=torch.float64).pin_memory()
             h["A"] = P.MatCreateAIJ(host["ia"].numpy(), host["ja"].numpy(), host["a"].numpy(), ncols_local=n_loc)
@@ -316,6 +311,7 @@ def main():
     P.QPSSetTolerances(h["qps"], rtol=1e-30, atol=1e-300, maxits=W - 1)     # never converge inside the window
     P.QPSSetUp(h["qps"])                                                      # upload done, power method done
     maxeig = P.QPSMPGPGetOperatorMaxEigenvalue(h["qps"])
+    storage = P.MatStorageInfo(h["A"])
     sampler = ClockSampler(local_rank)
     sampler.start()
     P.QPSSolve(h["qps"])                                                      # W warm-up iterations
@@ -356,12 +352,18 @@ def main():
     achieved = ka["bytes_per_launch"] / (ka_ms * 1e-3) / 1e9 if ka_ms > 0 else 0.0
     fam_ms = {k: round(v["total_ms"], 3) for k, v in prof.items() if v["launches"]}
     total_prof_ms = sum(v["total_ms"] for v in prof.values())
+    V_A = 4 + (1 if both else 0)
+    ka_csr_bytes = 12 * nnz_loc + 4 * (n_loc + 1) + 8 * n_loc * (V_A + 1)
     roofline = dict(bound="hbm", kernel="K_A fused SpMV (Ap = A p, p.Ap, g.p, alpha_f)", achieved=round(achieved, 1), peak=peak, unit="GB/s",
                     frac=round(achieved / peak, 4), traffic=None, peak_source=peak_src, launches=ka["launches"], avg_launch_ms=round(ka_ms, 5),
-                    algorithmic_bytes_per_launch=ka["bytes_per_launch"], kernel_share_of_step=round(ka["total_ms"] / total_prof_ms, 4) if total_prof_ms else None,
-                    family_ms=fam_ms)
-    step_bytes, b_cg, b_exp = algorithmic_bytes(n_loc, nnz_loc, counts, both_bounds=both)
+                    algorithmic_bytes_per_launch=ka["bytes_per_launch"],
+                    bytes_note="bytes of the layout the kernel streams (packed matrix tiles + p, g, x, bounds, Ap); the CSR formula of SURVEY 8d would be csr_formula_bytes_per_launch",
+                    csr_formula_bytes_per_launch=ka_csr_bytes, csr_equivalent_gbs=round(ka_csr_bytes / (ka_ms * 1e-3) / 1e9, 1) if ka_ms > 0 else None,
+                    kernel_share_of_step=round(ka["total_ms"] / total_prof_ms, 4) if total_prof_ms else None, family_ms=fam_ms)
+    step_bytes, b_cg, b_exp = algorithmic_bytes(n_loc, nnz_loc, counts, both_bounds=both, matrix_bytes=storage["stream_bytes"])
+    step_bytes_csr, b_cg_csr, b_exp_csr = algorithmic_bytes(n_loc, nnz_loc, counts, both_bounds=both)
     whole_iter_gbs = step_bytes / (ms * 1e-3) / 1e9
+    whole_iter_gbs_csr = step_bytes_csr / (ms * 1e-3) / 1e9
     destroy(h)
     keep.clear()
     del h, x_after_warmup
@@ -399,8 +401,12 @@ def main():
     if rank == 0:
         line = dict(metric=METRIC, value=round(value, 2), unit=UNIT, n_gpus=size, steps=K, warmup=W, ms_per_step=round(ms / K, 5), higher_is_better=True,
                     scaling="strong", vs_baseline=None, dtype="f64", data="synthetic",
-                    config=dict(workload=spec["label"], n=pr.N, n_local=n_loc, nnz_local=nnz_loc, step_mix=counts, l2="inputs larger than L2 (CSR 1.0 GB + 134 MB vectors per pass vs 126 MB L2)",
-                                maxeig=maxeig, bytes_per_cg_step=b_cg, bytes_per_expansion_step=b_exp, achieved_gbs_whole_iteration=round(whole_iter_gbs * size, 1),
+                    config=dict(workload=spec["label"], n=pr.N, n_local=n_loc, nnz_local=nnz_loc, step_mix=counts,
+                                l2="inputs larger than L2 (every kernel streams >= 3 vectors of 8n bytes, n >= 8.4M per GPU, vs 126 MB L2)",
+                                matrix_storage=storage, maxeig=maxeig, bytes_per_cg_step=b_cg, bytes_per_expansion_step=b_exp,
+                                bytes_per_cg_step_csr_formula=b_cg_csr, bytes_per_expansion_step_csr_formula=b_exp_csr,
+                                csr_equivalent_gbs_whole_iteration=round(whole_iter_gbs_csr * size, 1),
+                                achieved_gbs_whole_iteration=round(whole_iter_gbs * size, 1),
                                 frac_of_measured_hbm_whole_iteration=round(whole_iter_gbs / peak, 4), frac_of_8tbs_whole_iteration=round(whole_iter_gbs / 8000.0, 4),
                                 generate_s=round(t_gen, 1)),
                     clocks=clocks, e2e=e2e, gpu_launches=int(launches), roofline=roofline, cpu_baseline=cpu)

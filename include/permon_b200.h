@@ -203,6 +203,15 @@ PERMON_EXTERN PetscErrorCode MatGetMaxEigenvalue(Mat A, Vec v, PetscReal *lambda
 /* halo-plan introspection (host data; used by the CPU multi-rank tests) */
 PERMON_EXTERN PetscErrorCode MatB200GetHaloInfo(Mat A, PetscInt *nghost, const PetscInt **garray, PetscInt *nneigh, const PetscInt **neigh_rank,
                                                 const PetscInt **recv_off, const PetscInt **send_off, const PetscInt **send_idx, PetscInt *nboundary_rows);
+/* device storage introspection: kind 0/1/2 = CSR (tile-streamed / vector / TMA-staged), 3 = packed dictionary-coded tiles;
+   stream_bytes = bytes one SpMV reads for the matrix itself (diagonal + off-diagonal block); coded_tiles / tiles of the packed form.
+   Uploads a row-partitioned matrix if it is not on the device yet. */
+PERMON_EXTERN PetscErrorCode MatB200GetStorageInfo(Mat A, PetscInt *kind, PetscReal *stream_bytes, PetscInt *coded_tiles, PetscInt *tiles);
+/* host-side packer of the device matrix format (permon_b200/csrc/pack.cpp), exposed so that the format can be checked without a
+   GPU: tile t occupies blob[16*tile_off[t] .. 16*tile_off[t+1]).  *blob == NULL when the matrix cannot be packed. */
+PERMON_EXTERN PetscErrorCode PermonB200PackTiles(PetscInt n, const PetscInt ia[], const PetscInt ja[], const PetscScalar a[], unsigned char **blob,
+                                                 unsigned **tile_off, PetscInt *ntiles, PetscInt *coded_tiles);
+PERMON_EXTERN PetscErrorCode PermonB200PackFree(unsigned char *blob, unsigned *tile_off);
 
 /* ===================================================================================================
  * QPC -- separable constraints (box): include/permonqpc.h:21-56, src/qpc

@@ -375,6 +375,14 @@ def MatGetHaloInfo(A):
                 send_idx=[si[i] for i in range(send_off[-1])], nboundary=nb.value)
 
 
+def MatStorageInfo(A):
+    """Device storage of an AIJ matrix: kind (3 = packed dictionary-coded tiles), matrix bytes streamed per SpMV, coded / all tiles."""
+    kind, coded, tiles = C.c_int(), C.c_int(), C.c_int()
+    nbytes = C.c_double()
+    call("MatB200GetStorageInfo", A, C.byref(kind), C.byref(nbytes), C.byref(coded), C.byref(tiles))
+    return dict(kind=kind.value, stream_bytes=nbytes.value, coded_tiles=coded.value, tiles=tiles.value)
+
+
 # ---- QPC ---------------------------------------------------------------------------------------------
 def QPCCreateBox(is_, lb, ub, comm=None):
     q = C.c_void_p()

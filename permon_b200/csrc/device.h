@@ -46,6 +46,19 @@ void        prof_pre(int family, double bytes);
 void        prof_post(int family);
 
 // ---- device CSR ------------------------------------------------------------------------------------
+static constexpr int TR = 256;   // rows per SpMV tile
+
+// one tile of the packed (dictionary-coded) matrix format, see pack.cpp
+struct PkHeader {
+  uint16_t kind;    // 1: coded (dictionary of (col - row, value) pairs + one byte per non-zero), 0: raw
+  uint16_t ndict;
+  uint32_t nnz;
+  uint16_t ulen;    // common row length, 0xFFFF when the rows differ (then rowoff[] is present)
+  uint16_t nrows;
+  uint32_t pad;
+};
+static_assert(sizeof(PkHeader) == 16, "tile header is one 16-byte line");
+
 struct CsrDev {
   int           n      = 0;        // rows
   int           ncols  = 0;
@@ -57,7 +70,13 @@ struct CsrDev {
   int64_t       nnz_alloc = 0;     // elements of ja / a that may be read (allocation incl. padding)
   int           ia_alloc = 0;      // entries of ia that may be read
   int           stages = 2;        // shared-memory stages of the TMA kernel
-  int           kind   = 0;        // 0: tile-streamed plain loads, 1: vector (W lanes per row), 2: TMA-staged tiles
+  int           kind   = 0;        // 0: tile-streamed plain loads, 1: vector (W lanes per row), 2: TMA-staged CSR tiles, 3: TMA-staged packed tiles
+  // packed tiles (kind 3): blob + tile directory (offsets in 16-byte units); the raw CSR arrays are then absent
+  const unsigned char *pk     = nullptr;
+  const unsigned      *pk_off = nullptr;
+  int                  pk_max = 0;      // largest tile blob in bytes
+  int64_t              pk_bytes = 0;    // blob + directory bytes (what one SpMV streams for the matrix)
+  int64_t              pk_coded = 0;    // tiles that are dictionary-coded
   int           W      = 32;
   int           tile_cap = 0;      // max nnz of a 256-row tile (stream kind)
   int           grid   = 0;        // persistent grid size (fixed => reproducible reductions)
@@ -190,6 +209,7 @@ int k_ctrl_B(MpgpCtl *S, const double *rb);
 // halo pack: buf[k] = x[idx[k]]
 int k_pack(int n, const int *idx, const double *x, double *buf);
 
+double csr_stream_bytes(const CsrDev &A);   // bytes one SpMV must read for the matrix itself (CSR: 12 nnz + 4(n+1); packed: blob + directory)
 int  spmv_config(CsrDev &A, const int *h_ia);   // picks kind / W / grid from the host row pointer
 int  elementwise_grid();
 int  max_red_blocks();

@@ -176,7 +176,6 @@ int prof_get(int f, int64_t *launches, double *ms, double *bytes_per_launch)
 static bool aligned16(const void *p) { return (((uintptr_t)p) & 15) == 0; }
 
 static constexpr int NT = 256;   // threads per CTA everywhere
-static constexpr int TR = 256;   // rows per SpMV tile (stream kind)
 
 int elementwise_grid() { return g_ctx.sm_count * 8; }
 int max_red_blocks() { return g_ctx.sm_count * 16; }
@@ -324,6 +323,28 @@ __device__ __forceinline__ double box_reduced(double x, double gf, const BoxVal 
   return gr;
 }
 // QPCFeas_Box (qpcbox.c:125-137)
+// Same minimum as box_feas, but the fp64 division (~25 instructions) only runs for candidates that can still lower the
+// running minimum: (x - lb)/d >= cur is certain when x - lb > cur*d (+ rounding margin), and then `a < cur` is false.
+__device__ __forceinline__ double box_feas_lazy(double x, double d, const BoxVal &b, double cur)
+{
+  const double PINF = 1.7976931348623157e+308 / 4.0;
+  if (d > 0. && b.has_lb && b.lb > -PINF) {
+    const double num = x - b.lb, thr = cur * d, mar = fabs(thr) * 4.5e-16;
+    if (!(num > thr + mar) || !(fabs(thr) > 1e-290)) {
+      double a = num / d;
+      if (a < cur) cur = a;
+    }
+  }
+  if (d < 0. && b.has_ub && b.ub < PINF) {
+    const double num = x - b.ub, thr = cur * d, mar = fabs(thr) * 4.5e-16;
+    if (!(num < thr - mar) || !(fabs(thr) > 1e-290)) {
+      double a = num / d;
+      if (a < cur) cur = a;
+    }
+  }
+  return cur;
+}
+
 __device__ __forceinline__ double box_feas(double x, double d, const BoxVal &b, double cur)
 {
   const double PINF = 1.7976931348623157e+308 / 4.0;
@@ -504,9 +525,9 @@ __global__ void __launch_bounds__(NT + 32) k_spmv_tma(CsrDev A, const double *__
       k0n = __ldg(A.ia + r0);
       k1n = __ldg(A.ia + r1);
     }
-    int i = 0;
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, i++) {
-      const int s = i % nstages;
+    int      s = 0, filled = 0;
+    uint32_t ph = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
       const int k0 = k0n, k1 = k1n;
       const int nt = tile + gridDim.x;
       if (nt < ntiles) {   // metadata of the next tile: in flight while this one is issued
@@ -514,7 +535,8 @@ __global__ void __launch_bounds__(NT + 32) k_spmv_tma(CsrDev A, const double *__
         k0n = __ldg(A.ia + q0);
         k1n = __ldg(A.ia + q1);
       }
-      if (i >= nstages) mbar_wait(&empty_bar[s], ((i / nstages) & 1) ^ 1);
+      if (filled >= nstages) mbar_wait(&empty_bar[s], ph ^ 1u);
+      else filled++;
       unsigned char *st = smem_raw + (size_t)s * L.bytes;
       const int      r0 = tile * TR, r1 = min(r0 + TR, A.n);
       const int      k0a = k0 & ~3;
@@ -552,27 +574,330 @@ __global__ void __launch_bounds__(NT + 32) k_spmv_tma(CsrDev A, const double *__
           mbar_arrive(&full_bar[s]);
         }
       }
+      if (++s == nstages) {
+        s = 0;
+        ph ^= 1u;
+      }
     }
   } else {
     // ------------------------------ consumer warps: one thread per row ------------------------------
-    int i = 0;
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, i++) {
-      const int s = i % nstages;
-      mbar_wait(&full_bar[s], (i / nstages) & 1);
+    const uint32_t smem_a = smem_u32(smem_raw);
+    int            s = 0;
+    uint32_t       ph = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      mbar_wait(&full_bar[s], ph);
       unsigned char *st = smem_raw + (size_t)s * L.bytes;
       const double  *a_s = (const double *)(st + L.a_off);
       const int     *ja_s = (const int *)(st + L.ja_off), *ia_s = (const int *)(st + L.ia_off);
-      const double  *vs = (const double *)(st + L.v_off);
+      const uint32_t vs_a = smem_a + (uint32_t)s * (uint32_t)L.bytes + (uint32_t)L.v_off + 8u * threadIdx.x;
       const int      k0a = meta_k0a[s];
       const int      r = tile * TR + threadIdx.x;
       if (r < A.n) {
         const int ks = ia_s[threadIdx.x] - k0a, ke = ia_s[threadIdx.x + 1] - k0a;
         double    sum = 0.0;
-        for (int k = ks; k < ke; k++) sum += a_s[k] * __ldg(x + ja_s[k]);
-        epi.row_s(r, threadIdx.x, sum, vs, acc);
+        for (int k = ks; k < ke; k += 8) {   // 8 gathers in flight, products added in storage order
+          double xv[8];
+#pragma unroll
+          for (int j = 0; j < 8; j++) xv[j] = (k + j < ke) ? __ldg(x + ja_s[k + j]) : 0.0;
+#pragma unroll
+          for (int j = 0; j < 8; j++)
+            if (k + j < ke) sum += a_s[k + j] * xv[j];
+        }
+        epi.row_s(r, vs_a, sum, acc);
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&empty_bar[s]);
+      if (++s == nstages) {
+        s = 0;
+        ph ^= 1u;
+      }
+    }
+  }
+  epi.finalize(acc);
+}
+
+
+// TMA-staged PACKED tiles (kind 3, format in pack.cpp): same producer/consumer ring as k_spmv_tma, but the matrix part of a
+// tile is ONE bulk copy of its blob -- a per-tile dictionary of (col - row, value) pairs plus one byte per non-zero (or, for
+// tiles with more than 256 distinct pairs, raw values + columns).  Consumers rebuild col = row + delta and add the products in
+// storage order, so the result is bit-identical to the CSR kernels.  The matrix stream of a stencil Hessian shrinks from 12
+// to ~1 byte per non-zero; what remains of K_A / K_A' is the traffic of the fused epilogue vectors.
+static constexpr int PK_UNROLL = 8;
+static constexpr int PK_CT = 128;   // consumer threads of the packed kernel: two rows of a 256-row tile each
+// shared-memory loads by 32-bit address, in program order (volatile): the consumer code below issues every load of a row
+// (code bytes -> dictionary deltas -> x gathers -> dictionary values) before the first multiply-add, so that a warp has
+// 5-8 gathers in flight instead of one
+__device__ __forceinline__ uint32_t lds_u8(uint32_t a)
+{
+  uint32_t v;
+  asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ uint32_t lds_u16(uint32_t a)
+{
+  uint32_t v;
+  asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ int lds_s32(uint32_t a)
+{
+  int v;
+  asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ double lds_f64(uint32_t a)
+{
+  double v;
+  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ uint4 lds_v4(uint32_t a)
+{
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+  return v;
+}
+
+// one coded row of compile-time length L (uniform tiles of stencil matrices): no predicates, all loads up front
+template <int L>
+__device__ __forceinline__ double pk_row_fixed(uint32_t code_a, uint32_t dv_a, uint32_t dd_a, const double *__restrict__ x, int r)
+{
+  uint32_t c[L];
+  int      d[L];
+  double   xv[L], vv[L];
+#pragma unroll
+  for (int j = 0; j < L; j++) c[j] = lds_u8(code_a + j);
+#pragma unroll
+  for (int j = 0; j < L; j++) d[j] = lds_s32(dd_a + 4u * c[j]);
+#pragma unroll
+  for (int j = 0; j < L; j++) xv[j] = __ldg(x + (r + d[j]));
+#pragma unroll
+  for (int j = 0; j < L; j++) vv[j] = lds_f64(dv_a + 8u * c[j]);
+  double sum = 0.0;
+#pragma unroll
+  for (int j = 0; j < L; j++) sum += vv[j] * xv[j];
+  return sum;
+}
+
+// two coded rows of compile-time length at once (each consumer thread owns rows t and t + PK_CT of a tile): 2 L gathers in flight
+template <int L, bool PAD>
+__device__ __forceinline__ void pk_row2_fixed(uint32_t code_a0, uint32_t code_a1, uint32_t dv_a, uint32_t dd_a, const double *__restrict__ x, int r0, int r1,
+                                              uint32_t pad, double &s0, double &s1)
+{
+  uint32_t c0[L], c1[L];
+  int      d0[L], d1[L];
+  double   x0[L], x1[L];
+#pragma unroll
+  for (int j = 0; j < L; j++) c0[j] = lds_u8(code_a0 + j);
+#pragma unroll
+  for (int j = 0; j < L; j++) c1[j] = lds_u8(code_a1 + j);
+#pragma unroll
+  for (int j = 0; j < L; j++) d0[j] = lds_s32(dd_a + 4u * c0[j]);
+#pragma unroll
+  for (int j = 0; j < L; j++) d1[j] = lds_s32(dd_a + 4u * c1[j]);
+#pragma unroll
+  for (int j = 0; j < L; j++) x0[j] = __ldg(x + (r0 + d0[j]));   // a skip code gathers x[r] (delta 0) and drops it
+#pragma unroll
+  for (int j = 0; j < L; j++) x1[j] = __ldg(x + (r1 + d1[j]));
+  // scheduling fence (the consumer warps are converged here): every gather above is issued before the first multiply-add below
+  __syncwarp();
+  s0 = 0.0;
+#pragma unroll
+  for (int j = 0; j < L; j++) {
+    const double v = lds_f64(dv_a + 8u * c0[j]);
+    if (!PAD || c0[j] != pad) s0 += v * x0[j];
+  }
+  s1 = 0.0;
+#pragma unroll
+  for (int j = 0; j < L; j++) {
+    const double v = lds_f64(dv_a + 8u * c1[j]);
+    if (!PAD || c1[j] != pad) s1 += v * x1[j];
+  }
+}
+
+template <bool PAD>
+__device__ __forceinline__ bool pk_row2_dispatch(uint32_t ulen, uint32_t ca0, uint32_t ca1, uint32_t dv_a, uint32_t dd_a, const double *__restrict__ x, int r0,
+                                                 int r1, uint32_t pad, double &s0, double &s1)
+{
+  switch (ulen) {
+  case 1: pk_row2_fixed<1, PAD>(ca0, ca1, dv_a, dd_a, x, r0, r1, pad, s0, s1); return true;
+  case 2: pk_row2_fixed<2, PAD>(ca0, ca1, dv_a, dd_a, x, r0, r1, pad, s0, s1); return true;
+  case 3: pk_row2_fixed<3, PAD>(ca0, ca1, dv_a, dd_a, x, r0, r1, pad, s0, s1); return true;
+  case 4: pk_row2_fixed<4, PAD>(ca0, ca1, dv_a, dd_a, x, r0, r1, pad, s0, s1); return true;
+  case 5: pk_row2_fixed<5, PAD>(ca0, ca1, dv_a, dd_a, x, r0, r1, pad, s0, s1); return true;
+  case 6: pk_row2_fixed<6, PAD>(ca0, ca1, dv_a, dd_a, x, r0, r1, pad, s0, s1); return true;
+  case 7: pk_row2_fixed<7, PAD>(ca0, ca1, dv_a, dd_a, x, r0, r1, pad, s0, s1); return true;
+  case 8: pk_row2_fixed<8, PAD>(ca0, ca1, dv_a, dd_a, x, r0, r1, pad, s0, s1); return true;
+  default: return false;
+  }
+}
+
+// coded row of run-time length: chunks of PK_UNROLL with the same load-first order
+__device__ __forceinline__ double pk_row_var(uint32_t code_a, int len, uint32_t dv_a, uint32_t dd_a, const double *__restrict__ x, int r, uint32_t pad)
+{
+  double sum = 0.0;
+  for (int k = 0; k < len; k += PK_UNROLL) {
+    uint32_t c[PK_UNROLL];
+    int      d[PK_UNROLL];
+    double   xv[PK_UNROLL], vv[PK_UNROLL];
+#pragma unroll
+    for (int j = 0; j < PK_UNROLL; j++) c[j] = (k + j < len) ? lds_u8(code_a + k + j) : 0u;
+#pragma unroll
+    for (int j = 0; j < PK_UNROLL; j++) d[j] = lds_s32(dd_a + 4u * c[j]);
+#pragma unroll
+    for (int j = 0; j < PK_UNROLL; j++) xv[j] = (k + j < len) ? __ldg(x + (r + d[j])) : 0.0;
+#pragma unroll
+    for (int j = 0; j < PK_UNROLL; j++) vv[j] = lds_f64(dv_a + 8u * c[j]);
+#pragma unroll
+    for (int j = 0; j < PK_UNROLL; j++)
+      if (k + j < len && c[j] != pad) sum += vv[j] * xv[j];
+  }
+  return sum;
+}
+
+__device__ __forceinline__ double pk_row_raw(uint32_t a_a, uint32_t ja_a, int len, const double *__restrict__ x)
+{
+  double sum = 0.0;
+  for (int k = 0; k < len; k += PK_UNROLL) {
+    int    col[PK_UNROLL];
+    double xv[PK_UNROLL], vv[PK_UNROLL];
+#pragma unroll
+    for (int j = 0; j < PK_UNROLL; j++) col[j] = (k + j < len) ? lds_s32(ja_a + 4u * (k + j)) : 0;
+#pragma unroll
+    for (int j = 0; j < PK_UNROLL; j++) xv[j] = (k + j < len) ? __ldg(x + col[j]) : 0.0;
+#pragma unroll
+    for (int j = 0; j < PK_UNROLL; j++) vv[j] = (k + j < len) ? lds_f64(a_a + 8u * (k + j)) : 0.0;
+#pragma unroll
+    for (int j = 0; j < PK_UNROLL; j++)
+      if (k + j < len) sum += vv[j] * xv[j];
+  }
+  return sum;
+}
+
+template <class Epi>
+__global__ void __launch_bounds__(PK_CT + 32) k_spmv_pk(CsrDev A, const double *__restrict__ x, Epi epi, int blob_cap, int nstages, int vec_tma)
+{
+  if (!epi.active()) return;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  __shared__ uint64_t full_bar[TMA_MAX_STAGES], empty_bar[TMA_MAX_STAGES];
+  const int nv = epi.nvec();
+  const int stage_bytes = blob_cap + nv * TR * 8;
+  const int ntiles = (A.n + TR - 1) / TR;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  typename Epi::Acc acc;
+  epi.init(acc);
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < nstages; s++) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], PK_CT / 32);
+    }
+    mbar_fence_init();
+  }
+  __syncthreads();
+
+  if (warp == PK_CT / 32) {
+    // ------------------------------ producer warp ------------------------------
+    unsigned o0n = 0, o1n = 0;
+    if (blockIdx.x < ntiles) {
+      o0n = __ldg(A.pk_off + blockIdx.x);
+      o1n = __ldg(A.pk_off + blockIdx.x + 1);
+    }
+    int      s = 0, filled = 0;
+    uint32_t ph = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      const unsigned o0 = o0n, o1 = o1n;
+      const int      nt = tile + gridDim.x;
+      if (nt < ntiles) {   // directory entry of the next tile: in flight while this one is issued
+        o0n = __ldg(A.pk_off + nt);
+        o1n = __ldg(A.pk_off + nt + 1);
+      }
+      if (filled >= nstages) mbar_wait(&empty_bar[s], ph ^ 1u);
+      else filled++;
+      unsigned char *st = smem_raw + (size_t)s * stage_bytes;
+      const int      r0 = tile * TR, r1 = min(r0 + TR, A.n);
+      const uint32_t blob_bytes = (o1 - o0) * 16u;
+      if (r1 - r0 == TR && vec_tma) {
+        if (lane == 0) {
+          mbar_arrive_expect_tx(&full_bar[s], blob_bytes + (uint32_t)nv * TR * 8u);
+          bulk_g2s(st, A.pk + (size_t)o0 * 16, blob_bytes, &full_bar[s]);
+          for (int v = 0; v < nv; v++) bulk_g2s(st + blob_cap + (size_t)v * TR * 8, epi.vsrc(v) + r0, (uint32_t)TR * 8u, &full_bar[s]);
+        }
+      } else {
+        // last (partial) tile, or caller vectors that are not 16-byte aligned: the warp stages the vector slices itself
+        for (int v = 0; v < nv; v++) {
+          double       *vs = (double *)(st + blob_cap) + (size_t)v * TR;
+          const double *src = epi.vsrc(v) + r0;
+          for (int t = lane; t < r1 - r0; t += 32) vs[t] = src[t];
+        }
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive_expect_tx(&full_bar[s], blob_bytes);
+          bulk_g2s(st, A.pk + (size_t)o0 * 16, blob_bytes, &full_bar[s]);
+        }
+      }
+      if (++s == nstages) {
+        s = 0;
+        ph ^= 1u;
+      }
+    }
+  } else {
+    // ------------------------------ consumer warps: two rows (t, t + PK_CT) per thread ------------------------------
+    const uint32_t smem_a = smem_u32(smem_raw);
+    int            s = 0;
+    uint32_t       ph = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      mbar_wait(&full_bar[s], ph);
+      const uint32_t st_a = smem_a + (uint32_t)s * (uint32_t)stage_bytes;
+      const uint32_t vs_a = st_a + (uint32_t)blob_cap + 8u * threadIdx.x;
+      const uint4    hw = lds_v4(st_a);   // PkHeader
+      const uint32_t kind = hw.x & 0xFFFFu, nd = hw.x >> 16, nnz = hw.y, ulen = hw.z & 0xFFFFu, nrows = hw.z >> 16;
+      const uint32_t pad = hw.w - 1u;   // skip code of padded tiles, 0xFFFFFFFF when the tile has none
+      const int      r0 = tile * TR + threadIdx.x, r1 = r0 + PK_CT;
+      const uint32_t dv_a = st_a + (uint32_t)sizeof(PkHeader);
+      const uint32_t dd_a = dv_a + ((nd + 1u) & ~1u) * 8u;
+      const uint32_t q_a = dd_a + ((nd + 3u) & ~3u) * 4u;
+      bool           done = false;
+      if (kind == 1 && ulen != 0xFFFFu && nrows == TR) {
+        // full tile of equal-length coded rows (the bulk of a stencil matrix): both rows together, loads up front
+        const uint32_t ca0 = q_a + threadIdx.x * ulen, ca1 = ca0 + PK_CT * ulen;
+        double         s0 = 0.0, s1 = 0.0;
+        done = pad != 0xFFFFFFFFu ? pk_row2_dispatch<true>(ulen, ca0, ca1, dv_a, dd_a, x, r0, r1, pad, s0, s1)
+                                  : pk_row2_dispatch<false>(ulen, ca0, ca1, dv_a, dd_a, x, r0, r1, pad, s0, s1);
+        if (done) {
+          epi.row_s(r0, vs_a, s0, acc);
+          epi.row_s(r1, vs_a + PK_CT * 8u, s1, acc);
+        }
+      }
+      if (!done) {
+#pragma unroll 1
+        for (int h = 0; h < 2; h++) {
+          const uint32_t t = threadIdx.x + h * PK_CT;
+          const int      r = tile * TR + (int)t;
+          if (r >= A.n) break;
+          double sum;
+          if (kind == 1) {
+            if (ulen != 0xFFFFu) {
+              sum = pk_row_var(q_a + t * ulen, (int)ulen, dv_a, dd_a, x, r, pad);
+            } else {
+              const uint32_t ks = lds_u16(q_a + 2u * t), ke = lds_u16(q_a + 2u * t + 2u);
+              sum = pk_row_var(q_a + ((nrows + 1u + 7u) & ~7u) * 2u + ks, (int)(ke - ks), dv_a, dd_a, x, r, pad);
+            }
+          } else {
+            const uint32_t a_a = st_a + (uint32_t)sizeof(PkHeader);
+            const uint32_t ja_a = a_a + ((nnz + 1u) & ~1u) * 8u;
+            const uint32_t ro_a = ja_a + ((nnz + 3u) & ~3u) * 4u;
+            const uint32_t ks = lds_u16(ro_a + 2u * t), ke = lds_u16(ro_a + 2u * t + 2u);
+            sum = pk_row_raw(a_a + 8u * ks, ja_a + 4u * ks, (int)(ke - ks), x);
+          }
+          epi.row_s(r, st_a + (uint32_t)blob_cap + 8u * t, sum, acc);
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty_bar[s]);
+      if (++s == nstages) {
+        s = 0;
+        ph ^= 1u;
+      }
     }
   }
   epi.finalize(acc);
@@ -654,6 +979,48 @@ static void launch_tma(const CsrDev &A, const double *x, const Epi &epi)
   }
 }
 
+
+template <class Epi>
+static int launch_pk(const CsrDev &A, const double *x, const Epi &epi)
+{
+  if constexpr (!EpiHasStaged<Epi>::value) {
+    set_error("internal: epilogue without staged vectors on a packed matrix");
+    return 76;
+  } else {
+    const int nv = epi.nvec_host();
+    int       vec_tma = 1;
+    for (int v = 0; v < nv && vec_tma; v++) vec_tma = aligned16(epi.vsrc_host(v));
+    const int blob_cap = (A.pk_max + 127) & ~127;
+    const size_t stage = (size_t)blob_cap + (size_t)nv * TR * 8;
+    int          nstages = A.stages > 0 ? A.stages : 3;
+    if (nstages > TMA_MAX_STAGES) nstages = TMA_MAX_STAGES;
+    while (nstages > 1 && stage * nstages > 200 * 1024) nstages--;
+    const size_t smem = stage * nstages;
+    if (smem > 220 * 1024) {
+      set_error("packed SpMV tile does not fit in shared memory (%zu bytes)", smem);
+      return 76;
+    }
+    static size_t attr_smem = 0;
+    if (smem > attr_smem) {
+      cudaFuncSetAttribute(k_spmv_pk<Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      attr_smem = smem;
+    }
+    static int    occ = 0;
+    static size_t occ_smem = (size_t)-1;
+    if (!occ || occ_smem != smem) {
+      int nb = 0;
+      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_spmv_pk<Epi>, PK_CT + 32, smem) != cudaSuccess || nb < 1) nb = 1;
+      occ      = nb;
+      occ_smem = smem;
+    }
+    int ntiles = (A.n + TR - 1) / TR, grid = g_ctx.sm_count * occ;
+    if (grid > ntiles) grid = ntiles;
+    if (grid > max_red_blocks()) grid = max_red_blocks();
+    k_spmv_pk<Epi><<<grid, PK_CT + 32, smem, g_ctx.stream>>>(A, x, epi, blob_cap, nstages, vec_tma);
+    return 0;
+  }
+}
+
 template <class Epi>
 static int launch_spmv(const CsrDev &A, const double *x, const Epi &epi, int family, double bytes)
 {
@@ -661,6 +1028,8 @@ static int launch_spmv(const CsrDev &A, const double *x, const Epi &epi, int fam
   if (A.n == 0) {
     // still run one CTA so that reductions publish their (identity) record
     k_spmv_vector<Epi, 32><<<1, NT, 0, g_ctx.stream>>>(A, x, epi);
+  } else if (A.kind == 3) {
+    PB_CHK(launch_pk(A, x, epi));
   } else if (A.kind == 2) {
     launch_tma(A, x, epi);
   } else if (A.kind == 0) {
@@ -688,6 +1057,12 @@ static int launch_spmv(const CsrDev &A, const double *x, const Epi &epi, int fam
   prof_post(family);
   LAUNCH_CHECK();
   return 0;
+}
+
+double csr_stream_bytes(const CsrDev &A)
+{
+  if (A.kind == 3) return (double)A.pk_bytes;
+  return 12.0 * (double)A.nnz + 4.0 * (A.n + 1);
 }
 
 // decide the kernel flavour from the row pointer (host copy)
@@ -740,7 +1115,7 @@ struct EpiPlain {
   __host__ __device__ const double *vsrc(int) const { return nullptr; }
   int nvec_host() const { return nvec(); }
   const double *vsrc_host(int i) const { return vsrc(i); }
-  __device__ void row_s(int r, int, double ax, const double *, Acc &a) const { row(r, ax, a); }
+  __device__ void row_s(int r, uint32_t, double ax, Acc &a) const { row(r, ax, a); }
 };
 
 struct EpiGated {   // plain SpMV that only runs in the right phase of the device-driven iteration
@@ -760,7 +1135,7 @@ struct EpiGated {   // plain SpMV that only runs in the right phase of the devic
   __host__ __device__ const double *vsrc(int) const { return nullptr; }
   int nvec_host() const { return nvec(); }
   const double *vsrc_host(int i) const { return vsrc(i); }
-  __device__ void row_s(int r, int, double ax, const double *, Acc &a) const { row(r, ax, a); }
+  __device__ void row_s(int r, uint32_t, double ax, Acc &a) const { row(r, ax, a); }
 };
 
 struct AccRed {
@@ -768,7 +1143,9 @@ struct AccRed {
 };
 
 // K_A epilogue: Ap_r = (A p)_r ; p.Ap ; g.p ; B p ; max feasible step (QPCFeas)
-struct EpiA {
+// LBONLY: lower bound present, no upper bound, no equality rows (the obstacle problems): the staged path sheds every run-time flag
+template <bool LBONLY>
+struct EpiAT {
   const double        *p, *g, *x;
   double              *Ap;
   BoxDev               bx;
@@ -790,8 +1167,10 @@ struct EpiA {
     const double pr = p[r];
     a.v[RA_PAP] += pr * ax;
     a.v[RA_GP] += g[r] * pr;
-    for (int j = 0; j < m; j++) a.v[RA_BP + j] += B[(size_t)j * n + r] * pr;
-    a.v[RA_FEAS] = box_feas(x[r], pr, load_box(bx, r), a.v[RA_FEAS]);
+#pragma unroll
+    for (int j = 0; j < PB_MAXEQ; j++)
+      if (j < m) a.v[RA_BP + j] += B[(size_t)j * n + r] * pr;
+    a.v[RA_FEAS] = box_feas_lazy(x[r], pr, load_box(bx, r), a.v[RA_FEAS]);
   }
   __device__ void row(int r, double ax, Acc &a) const
   {
@@ -820,26 +1199,41 @@ struct EpiA {
     }
     return B + (size_t)(i - k) * n;
   }
-  __device__ void row_s(int r, int t, double ax, const double *vs, Acc &a) const
+  // va: shared-memory address of this row's slot in the first staged vector; vector k sits k * TR * 8 bytes further
+  __device__ void row_s(int r, uint32_t va, double ax, Acc &a) const
   {
     Ap[r] = ax;
     if (skip && skip[r]) return;
-    const double pr = vs[t];
+    const double pr = lds_f64(va);
     a.v[RA_PAP] += pr * ax;
-    a.v[RA_GP] += vs[TR + t] * pr;
-    BoxVal b;
-    int    k = 3;
-    b.has_lb = bx.lb != nullptr;
-    b.has_ub = bx.ub != nullptr;
-    b.lb     = b.has_lb ? vs[(k++) * TR + t] : 0.0;
-    b.ub     = b.has_ub ? vs[(k++) * TR + t] : 0.0;
-    for (int j = 0; j < m; j++) a.v[RA_BP + j] += vs[(k + j) * TR + t] * pr;
-    a.v[RA_FEAS] = box_feas(vs[2 * TR + t], pr, b, a.v[RA_FEAS]);
+    a.v[RA_GP] += lds_f64(va + TR * 8) * pr;
+    const double xr = lds_f64(va + 2 * TR * 8);
+    if constexpr (LBONLY) {
+      BoxVal b;
+      b.has_lb = true;
+      b.has_ub = false;
+      b.lb     = lds_f64(va + 3 * TR * 8);
+      b.ub     = 0.0;
+      a.v[RA_FEAS] = box_feas_lazy(xr, pr, b, a.v[RA_FEAS]);
+    } else {
+      BoxVal   b;
+      uint32_t k = 3;
+      b.has_lb = bx.lb != nullptr;
+      b.has_ub = bx.ub != nullptr;
+      b.lb     = b.has_lb ? lds_f64(va + (k++) * TR * 8) : 0.0;
+      b.ub     = b.has_ub ? lds_f64(va + (k++) * TR * 8) : 0.0;
+#pragma unroll
+      for (int j = 0; j < PB_MAXEQ; j++)
+        if (j < m) a.v[RA_BP + j] += lds_f64(va + (k + j) * TR * 8) * pr;
+      a.v[RA_FEAS] = box_feas_lazy(xr, pr, b, a.v[RA_FEAS]);
+    }
   }
 };
+typedef EpiAT<false> EpiA;
 
 // K_A' epilogue: g_r = (A x)_r + rho (B^T Bu)_r - b_r ; split ; p = gf ; |gP|^2 |gc|^2 |gf|^2
-struct EpiA2 {
+template <bool LBONLY>
+struct EpiA2T {
   const double        *x, *b;
   double              *g, *p;
   BoxDev               bx;
@@ -901,27 +1295,36 @@ struct EpiA2 {
     }
     return B + (size_t)(i - k) * n;
   }
-  __device__ void row_s(int r, int t, double ax, const double *vs, Acc &a) const
+  __device__ void row_s(int r, uint32_t va, double ax, Acc &a) const
   {
     if (skip && skip[r]) {
       g[r] = ax;
       return;
     }
     BoxVal bv;
-    int    k = 2;
-    bv.has_lb = bx.lb != nullptr;
-    bv.has_ub = bx.ub != nullptr;
-    bv.lb     = bv.has_lb ? vs[(k++) * TR + t] : 0.0;
-    bv.ub     = bv.has_ub ? vs[(k++) * TR + t] : 0.0;
     double gr = ax;
-    if (m > 0) {
-      double tt = 0.0;
-      for (int j = 0; j < m; j++) tt += vs[(k + j) * TR + t] * S->Bu[j];
-      gr += S->rho * tt;
+    if constexpr (LBONLY) {
+      bv.has_lb = true;
+      bv.has_ub = false;
+      bv.lb     = lds_f64(va + 2 * TR * 8);
+      bv.ub     = 0.0;
+    } else {
+      uint32_t k = 2;
+      bv.has_lb = bx.lb != nullptr;
+      bv.has_ub = bx.ub != nullptr;
+      bv.lb     = bv.has_lb ? lds_f64(va + (k++) * TR * 8) : 0.0;
+      bv.ub     = bv.has_ub ? lds_f64(va + (k++) * TR * 8) : 0.0;
+      if (m > 0) {
+        double tt = 0.0;
+#pragma unroll
+        for (int j = 0; j < PB_MAXEQ; j++)
+          if (j < m) tt += lds_f64(va + (k + j) * TR * 8) * S->Bu[j];
+        gr += S->rho * tt;
+      }
     }
-    gr -= vs[TR + t];
+    gr -= lds_f64(va + TR * 8);
     double gf, gc;
-    box_split(vs[t], gr, bv, bx.astol, gf, gc);
+    box_split(lds_f64(va), gr, bv, bx.astol, gf, gc);
     g[r] = gr;
     p[r] = gf;
     const double gP = gf + gc;
@@ -930,6 +1333,7 @@ struct EpiA2 {
     a.v[RB_GF2] += gf * gf;
   }
 };
+typedef EpiA2T<false> EpiA2;
 
 // ghost pass (multi-GPU): add the off-diagonal block product to the parked partial result, then run the
 // deferred epilogue of K_A (SECOND = false) or K_A' (SECOND = true) for the boundary rows
@@ -973,32 +1377,40 @@ struct EpiGhost {
 int k_spmv(const CsrDev &A, const double *x, double *y, int accumulate)
 {
   EpiPlain e{y, accumulate};
-  return launch_spmv(A, x, e, KF_SPMV_PLAIN, 12.0 * (double)A.nnz + 4.0 * (A.n + 1) + 16.0 * A.n);
+  return launch_spmv(A, x, e, KF_SPMV_PLAIN, csr_stream_bytes(A) + 16.0 * A.n);
 }
 
 int k_spmv_gated(const CsrDev &A, const double *x, double *y, const MpgpCtl *S, int phase)
 {
   EpiGated e{y, S, phase};
-  return launch_spmv(A, x, e, KF_SPMV_PLAIN, 12.0 * (double)A.nnz + 4.0 * (A.n + 1) + 16.0 * A.n);
+  return launch_spmv(A, x, e, KF_SPMV_PLAIN, csr_stream_bytes(A) + 16.0 * A.n);
 }
 
 static double bytes_A(const CsrDev &A, const MpgpVecs &v)
 {   // CSR + p(gather) + g + x + lb[+ub] + B rows, write Ap
-  return 12.0 * (double)A.nnz + 4.0 * (A.n + 1) + 8.0 * v.n * (4 + (v.bx.lb ? 1 : 0) + (v.bx.ub ? 1 : 0) + v.m);
+  return csr_stream_bytes(A) + 8.0 * v.n * (4 + (v.bx.lb ? 1 : 0) + (v.bx.ub ? 1 : 0) + v.m);
 }
 static double bytes_A2(const CsrDev &A, const MpgpVecs &v)
 {   // CSR + x(gather) + b + lb[+ub] + B rows, write g, p
-  return 12.0 * (double)A.nnz + 4.0 * (A.n + 1) + 8.0 * v.n * (4 + (v.bx.lb ? 1 : 0) + (v.bx.ub ? 1 : 0) + v.m);
+  return csr_stream_bytes(A) + 8.0 * v.n * (4 + (v.bx.lb ? 1 : 0) + (v.bx.ub ? 1 : 0) + v.m);
 }
 
 int k_fused_A(const CsrDev &A, const double *xin, const MpgpVecs &v, const MpgpCtl *S, RedBuf rb, const unsigned char *skip)
 {
+  if (v.bx.lb && !v.bx.ub && v.m == 0) {
+    EpiAT<true> e{v.p, v.g, v.x, v.Ap, v.bx, v.B, v.m, v.n, S, rb, skip};
+    return launch_spmv(A, xin, e, KF_SPMV_A, bytes_A(A, v));
+  }
   EpiA e{v.p, v.g, v.x, v.Ap, v.bx, v.B, v.m, v.n, S, rb, skip};
   return launch_spmv(A, xin, e, KF_SPMV_A, bytes_A(A, v));
 }
 
 int k_fused_A2(const CsrDev &A, const double *xin, const MpgpVecs &v, const MpgpCtl *S, RedBuf rb, const unsigned char *skip)
 {
+  if (v.bx.lb && !v.bx.ub && v.m == 0) {
+    EpiA2T<true> e{v.x, v.b, v.g, v.p, v.bx, v.B, v.m, v.n, S, rb, skip};
+    return launch_spmv(A, xin, e, KF_SPMV_A2, bytes_A2(A, v));
+  }
   EpiA2 e{v.x, v.b, v.g, v.p, v.bx, v.B, v.m, v.n, S, rb, skip};
   return launch_spmv(A, xin, e, KF_SPMV_A2, bytes_A2(A, v));
 }
@@ -1644,7 +2056,7 @@ int k_dense_rows_mult(int n, int m, const double *B, const double *x, RedBuf rb)
 }
 int k_qpc_feas(int n, const double *x, const double *d, BoxDev bx, RedBuf rb)
 {
-  return launch_red<(1 << RA_FEAS)>(n, [=] __device__(int i, double(&a)[PB_NRED]) { a[RA_FEAS] = box_feas(x[i], d[i], load_box(bx, i), a[RA_FEAS]); }, rb, KF_QPC, 32.0 * n);
+  return launch_red<(1 << RA_FEAS)>(n, [=] __device__(int i, double(&a)[PB_NRED]) { a[RA_FEAS] = box_feas_lazy(x[i], d[i], load_box(bx, i), a[RA_FEAS]); }, rb, KF_QPC, 32.0 * n);
 }
 // QPCViewKKT_Box numbers (qpcbox.c:333-427): out[0]=sum min(x-lb,0)^2 | max(x-ub,0)^2, out[1]=sum min(lam,0)^2,
 // out[2]=lam'(lb-x) | lam'(x-ub) with the infinite-bound convention of the reference

@@ -1,0 +1,211 @@
+// Packed tile format of a CSR matrix ("dictionary-coded CSR tiles"), built once on the host at upload time.
+//
+// The MPGP iteration is HBM-bound and after fusion the matrix stream is the largest operand of K_A / K_A'
+// (12 bytes per non-zero in CSR).  PDE Hessians repeat a small set of (column offset, value) pairs over and
+// over -- 5 pairs for the whole 5-point Laplacian, a few dozen for a two-material finite-volume operator.  Each
+// 256-row tile therefore carries its own dictionary of distinct (col - row, value) pairs and one byte per
+// non-zero that indexes it; the kernel rebuilds col = row + delta and multiplies by the dictionary value, in
+// storage order, so the row sums are bit-identical to the CSR kernels'.  A tile with more than 256 distinct pairs
+// is stored raw (values + absolute columns) in the same blob, so one kernel handles any matrix.
+//
+// Tile blob (16-byte aligned, fetched with ONE bulk copy):
+//   PkHeader (16 B)
+//   coded: double val[nd2]            nd2 = ndict rounded up to 2
+//          int    delta[nd4]          nd4 = ndict rounded up to 4
+//          u16    rowoff[ro8]         only when the rows differ in length (ulen == 0xFFFF); ro8 = nrows+1 up to 8
+//          u8     code[nnz16]         nnz rounded up to 16
+//   Short ragged rows (longest <= 8, e.g. stencil rows next to a grid boundary) are padded to a common length with a
+//   "skip" code (= ndict, stored in the header as pad = code + 1; its dictionary slot is (0, 0.0) and is never multiplied),
+//   so that the kernel's unrolled equal-length path handles them too.
+//   raw:   double a[nnz2] ; int ja[nnz4] ; u16 rowoff[ro8]
+#include "device.h"
+#include <omp.h>
+#include <algorithm>
+#include <cstring>
+#include <vector>
+
+namespace pb {
+
+static inline size_t up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+size_t pk_coded_bytes(int ndict, int nrows, int nnz, bool uniform)
+{
+  size_t b = sizeof(PkHeader) + up(ndict, 2) * 8 + up(ndict, 4) * 4;
+  if (!uniform) b += up((size_t)nrows + 1, 8) * 2;
+  b += up(nnz, 16);
+  return up(b, 16);
+}
+size_t pk_raw_bytes(int nrows, int nnz)
+{
+  return up(sizeof(PkHeader) + up(nnz, 2) * 8 + up(nnz, 4) * 4 + up((size_t)nrows + 1, 8) * 2, 16);
+}
+
+namespace {
+struct TileDict {
+  // open addressing over (delta, value bits); 1024 slots for at most 256 entries
+  static constexpr int SLOTS = 1024;
+  int                  slot_code[SLOTS];
+  int                  delta[256];
+  uint64_t             bits[256];
+  int                  n;
+  void reset()
+  {
+    n = 0;
+    for (int s = 0; s < SLOTS; s++) slot_code[s] = -1;
+  }
+  // returns the code, or -1 when the dictionary is full
+  int lookup(int d, uint64_t b)
+  {
+    uint64_t h = (b ^ (b >> 29)) * 0x9E3779B97F4A7C15ull + (uint64_t)(uint32_t)d * 0xC2B2AE3D27D4EB4Full;
+    int      s = (int)((h >> 40) & (SLOTS - 1));
+    for (;;) {
+      const int c = slot_code[s];
+      if (c < 0) {
+        if (n == 256) return -1;
+        slot_code[s] = n;
+        delta[n]     = d;
+        bits[n]      = b;
+        return n++;
+      }
+      if (delta[c] == d && bits[c] == b) return c;
+      s = (s + 1) & (SLOTS - 1);
+    }
+  }
+};
+}   // namespace
+
+// h_off: ntiles+1 offsets in units of 16 bytes.  Returns 0 on success; `packed` false when packing is not applicable
+// (a tile whose non-zero count or row lengths do not fit the 16-bit row offsets).
+int pk_build(int n, const int *ia, const int *ja, const double *a, std::vector<unsigned char> &blob, std::vector<unsigned> &h_off, int &max_tile_bytes,
+             int64_t &ncoded, bool &packed)
+{
+  const int ntiles = (n + TR - 1) / TR;
+  packed           = false;
+  h_off.assign((size_t)ntiles + 1, 0);
+  std::vector<unsigned> tbytes(ntiles, 0);
+  std::vector<unsigned char> tkind(ntiles, 0);
+  std::vector<uint16_t>      tnd(ntiles, 0);
+  std::vector<unsigned char> tpad(ntiles, 0);   // common (padded) row length of ragged short-row tiles, 0 = no padding
+  bool    bad = false;
+  int64_t coded = 0;
+  // pass 1: classify and size every tile
+#pragma omp parallel reduction(|| : bad) reduction(+ : coded)
+  {
+    TileDict D;
+#pragma omp for schedule(dynamic, 64)
+    for (int t = 0; t < ntiles; t++) {
+      const int r0 = t * TR, r1 = std::min(r0 + TR, n);
+      const int k0 = ia[r0], k1 = ia[r1], nnz = k1 - k0;
+      if (nnz > 65535) {
+        bad = true;
+        continue;
+      }
+      D.reset();
+      bool ok = true, uniform = true;
+      const int len0 = ia[r0 + 1] - ia[r0];
+      for (int r = r0; r < r1 && ok; r++) {
+        if (ia[r + 1] - ia[r] != len0) uniform = false;
+        for (int k = ia[r]; k < ia[r + 1]; k++) {
+          uint64_t b;
+          memcpy(&b, &a[k], 8);
+          if (D.lookup(ja[k] - r, b) < 0) {
+            ok = false;
+            break;
+          }
+        }
+      }
+      if (ok) {
+        tkind[t] = 1;
+        tnd[t]   = (uint16_t)D.n;
+        int maxlen = 0;
+        for (int r = r0; r < r1; r++) maxlen = std::max(maxlen, ia[r + 1] - ia[r]);
+        const int padded = (r1 - r0) * maxlen;
+        if (!uniform && maxlen <= 8 && D.n <= 255 && padded <= nnz + nnz / 4 + 16) {
+          tpad[t]   = (unsigned char)maxlen;
+          tbytes[t] = (unsigned)pk_coded_bytes(D.n + 1, r1 - r0, padded, true);
+        } else {
+          tbytes[t] = (unsigned)pk_coded_bytes(D.n, r1 - r0, nnz, uniform && len0 < 0xFFFF);
+        }
+        coded++;
+      } else {
+        tkind[t]  = 0;
+        tbytes[t] = (unsigned)pk_raw_bytes(r1 - r0, nnz);
+      }
+    }
+  }
+  if (bad) return 0;
+  size_t tot = 0;
+  max_tile_bytes = 0;
+  for (int t = 0; t < ntiles; t++) {
+    h_off[t] = (unsigned)(tot / 16);
+    tot += tbytes[t];
+    if ((int)tbytes[t] > max_tile_bytes) max_tile_bytes = (int)tbytes[t];
+  }
+  if (tot / 16 > 0xFFFFFFFFull) return 0;
+  h_off[ntiles] = (unsigned)(tot / 16);
+  blob.assign(tot + 16, 0);
+  // pass 2: fill
+#pragma omp parallel
+  {
+    TileDict D;
+#pragma omp for schedule(dynamic, 64)
+    for (int t = 0; t < ntiles; t++) {
+      const int      r0 = t * TR, r1 = std::min(r0 + TR, n), nrows = r1 - r0;
+      const int      k0 = ia[r0], k1 = ia[r1], nnz = k1 - k0;
+      unsigned char *p = blob.data() + (size_t)h_off[t] * 16;
+      PkHeader       H;
+      memset(&H, 0, sizeof H);
+      H.kind  = tkind[t];
+      H.nnz   = (uint32_t)nnz;
+      H.nrows = (uint16_t)nrows;
+      bool      uniform = true;
+      const int len0 = ia[r0 + 1] - ia[r0];
+      for (int r = r0; r < r1; r++)
+        if (ia[r + 1] - ia[r] != len0) uniform = false;
+      if (tkind[t] == 1) {
+        // the dictionary is rebuilt in first-appearance order (as in pass 1) while the codes are written in place
+        const int plen = tpad[t];                     // > 0: rows padded to this length with the skip code
+        const int nd = tnd[t] + (plen ? 1 : 0);       // the skip code owns a (0, 0.0) slot at the end of the dictionary
+        H.ndict      = (uint16_t)nd;
+        H.ulen       = plen ? (uint16_t)plen : ((uniform && len0 < 0xFFFF) ? (uint16_t)len0 : (uint16_t)0xFFFF);
+        H.pad        = plen ? (uint32_t)tnd[t] + 1u : 0u;
+        const size_t o_val = sizeof(PkHeader), o_del = o_val + up(nd, 2) * 8, o_ro = o_del + up(nd, 4) * 4;
+        const size_t o_code = o_ro + (H.ulen == 0xFFFF ? up((size_t)nrows + 1, 8) * 2 : 0);
+        unsigned char *codes = p + o_code;
+        D.reset();
+        for (int r = r0; r < r1; r++) {
+          unsigned char *rc = plen ? codes + (size_t)(r - r0) * plen : codes + (ia[r] - k0);
+          const int      len = ia[r + 1] - ia[r];
+          for (int k = 0; k < len; k++) {
+            uint64_t b;
+            memcpy(&b, &a[ia[r] + k], 8);
+            rc[k] = (unsigned char)D.lookup(ja[ia[r] + k] - r, b);
+          }
+          for (int k = len; k < plen; k++) rc[k] = (unsigned char)tnd[t];
+        }
+        memcpy(p + o_val, D.bits, (size_t)tnd[t] * 8);
+        memcpy(p + o_del, D.delta, (size_t)tnd[t] * 4);
+        if (H.ulen == 0xFFFF) {
+          uint16_t *ro = (uint16_t *)(p + o_ro);
+          for (int r = r0; r <= r1; r++) ro[r - r0] = (uint16_t)(ia[r] - k0);
+        }
+      } else {
+        H.ndict = 0;
+        H.ulen  = 0xFFFF;
+        size_t o = sizeof(PkHeader);
+        if (nnz) memcpy(p + o, a + k0, (size_t)nnz * 8);
+        o += up(nnz, 2) * 8;
+        if (nnz) memcpy(p + o, ja + k0, (size_t)nnz * 4);
+        o += up(nnz, 4) * 4;
+        uint16_t *ro = (uint16_t *)(p + o);
+        for (int r = r0; r <= r1; r++) ro[r - r0] = (uint16_t)(ia[r] - k0);
+      }
+      memcpy(p, &H, sizeof H);
+    }
+  }
+  ncoded = coded;
+  packed = true;
+  return 0;
+}
+
+}   // namespace pb

@@ -883,6 +883,8 @@ _p_Mat::~_p_Mat()
     cudaFree((void *)Ad.ia);
     cudaFree((void *)Ad.ja);
     cudaFree((void *)Ad.a);
+    cudaFree((void *)Ad.pk);
+    cudaFree((void *)Ad.pk_off);
   }
   if (kind == MK_AIJ) {
     cudaFree((void *)Ao.ia);
@@ -914,30 +916,18 @@ _p_Mat::~_p_Mat()
   if (pf && --pf->refct == 0) delete pf;
 }
 
+namespace pb {
+int pk_build(int n, const int *ia, const int *ja, const double *a, std::vector<unsigned char> &blob, std::vector<unsigned> &h_off, int &max_tile_bytes,
+             int64_t &ncoded, bool &packed);
+}
+
 static int upload_csr(pb::CsrDev &C, int nrows, int ncols, const int *ia, const int *ja, const double *a, const int *rows)
 {
   const int64_t nnz = ia[nrows];
   C.n     = nrows;
   C.ncols = ncols;
   C.nnz   = nnz;
-  int *dia, *dja;
-  double *da;
-  // 8 elements of padding: the TMA kernel copies 16-byte aligned, 16-byte granular tile ranges
-  PB_CUDA(cudaMalloc(&dia, sizeof(int) * (size_t)(nrows + 1 + 8)));
-  PB_CUDA(cudaMalloc(&dja, sizeof(int) * (size_t)(nnz + 8)));
-  PB_CUDA(cudaMalloc(&da, sizeof(double) * (size_t)(nnz + 8)));
-  PB_CUDA(cudaMemsetAsync(dia + nrows + 1, 0, sizeof(int) * 8, ctx().stream));
-  PB_CUDA(cudaMemsetAsync(dja + nnz, 0, sizeof(int) * 8, ctx().stream));
-  PB_CUDA(cudaMemsetAsync(da + nnz, 0, sizeof(double) * 8, ctx().stream));
-  C.nnz_alloc = nnz + 8;
-  C.ia_alloc  = nrows + 1 + 8;
   cudaStream_t s = ctx().stream;
-  PB_CUDA(cudaMemcpyAsync(dia, ia, sizeof(int) * (size_t)(nrows + 1), cudaMemcpyHostToDevice, s));
-  PB_CUDA(cudaMemcpyAsync(dja, ja, sizeof(int) * (size_t)nnz, cudaMemcpyHostToDevice, s));
-  PB_CUDA(cudaMemcpyAsync(da, a, sizeof(double) * (size_t)nnz, cudaMemcpyHostToDevice, s));
-  C.ia = dia;
-  C.ja = dja;
-  C.a  = da;
   if (rows) {
     int *dr;
     PB_CUDA(cudaMalloc(&dr, sizeof(int) * (size_t)std::max(nrows, 1)));
@@ -945,6 +935,51 @@ static int upload_csr(pb::CsrDev &C, int nrows, int ncols, const int *ia, const 
     C.rows = dr;
   }
   PB_CHK(spmv_config(C, ia));
+  // Tile-streamable matrices are re-coded into packed tiles (pack.cpp) and only that form goes to the device;
+  // PERMON_B200_SPMV=tma|stream|vector keeps plain CSR for A/B measurements.  Tiny matrices (equality rows) stay CSR.
+  if (C.kind == 2 && !rows && nrows >= 64 && !getenv("PERMON_B200_SPMV")) {
+    std::vector<unsigned char> blob;
+    std::vector<unsigned>      off;
+    int                        max_tile = 0;
+    int64_t                    ncoded = 0;
+    bool                       packed = false;
+    PB_CHK(pb::pk_build(nrows, ia, ja, a, blob, off, max_tile, ncoded, packed));
+    if (packed) {
+      unsigned char *dblob;
+      unsigned      *doff;
+      PB_CUDA(cudaMalloc(&dblob, blob.size()));
+      PB_CUDA(cudaMalloc(&doff, sizeof(unsigned) * off.size()));
+      PB_CUDA(cudaMemcpyAsync(dblob, blob.data(), blob.size(), cudaMemcpyHostToDevice, s));
+      PB_CUDA(cudaMemcpyAsync(doff, off.data(), sizeof(unsigned) * off.size(), cudaMemcpyHostToDevice, s));
+      PB_CUDA(cudaStreamSynchronize(s));   // blob / off are locals
+      C.pk       = dblob;
+      C.pk_off   = doff;
+      C.pk_max   = max_tile;
+      C.pk_bytes = (int64_t)off.back() * 16 + (int64_t)sizeof(unsigned) * (int64_t)off.size();
+      C.pk_coded = ncoded;
+      C.kind     = 3;
+      const char *st = getenv("PERMON_B200_STAGES");
+      C.stages = st ? atoi(st) : 3;
+      return 0;
+    }
+  }
+  int *dia, *dja;
+  double *da;
+  // 8 elements of padding: the TMA kernel copies 16-byte aligned, 16-byte granular tile ranges
+  PB_CUDA(cudaMalloc(&dia, sizeof(int) * (size_t)(nrows + 1 + 8)));
+  PB_CUDA(cudaMalloc(&dja, sizeof(int) * (size_t)(nnz + 8)));
+  PB_CUDA(cudaMalloc(&da, sizeof(double) * (size_t)(nnz + 8)));
+  PB_CUDA(cudaMemsetAsync(dia + nrows + 1, 0, sizeof(int) * 8, s));
+  PB_CUDA(cudaMemsetAsync(dja + nnz, 0, sizeof(int) * 8, s));
+  PB_CUDA(cudaMemsetAsync(da + nnz, 0, sizeof(double) * 8, s));
+  C.nnz_alloc = nnz + 8;
+  C.ia_alloc  = nrows + 1 + 8;
+  PB_CUDA(cudaMemcpyAsync(dia, ia, sizeof(int) * (size_t)(nrows + 1), cudaMemcpyHostToDevice, s));
+  PB_CUDA(cudaMemcpyAsync(dja, ja, sizeof(int) * (size_t)nnz, cudaMemcpyHostToDevice, s));
+  PB_CUDA(cudaMemcpyAsync(da, a, sizeof(double) * (size_t)nnz, cudaMemcpyHostToDevice, s));
+  C.ia = dia;
+  C.ja = dja;
+  C.a  = da;
   return 0;
 }
 
@@ -1302,6 +1337,47 @@ PetscErrorCode MatB200GetHaloInfo(Mat A, PetscInt *nghost, const PetscInt **garr
   if (send_off) *send_off = H ? H->send_off.data() : &zero;
   if (send_idx) *send_idx = H ? H->send_idx.data() : nullptr;
   if (nboundary_rows) *nboundary_rows = H ? H->nboundary : 0;
+  return 0;
+}
+
+PetscErrorCode MatB200GetStorageInfo(Mat A, PetscInt *kind, PetscReal *stream_bytes, PetscInt *coded_tiles, PetscInt *tiles)
+{
+  if (!A || A->kind != MK_AIJ) return err(PETSC_ERR_ARG_WRONG, "MatB200GetStorageInfo: AIJ matrix expected");
+  PB_CHK(pb::mat_ensure_device(A));
+  if (kind) *kind = A->Ad.kind;
+  if (stream_bytes) *stream_bytes = pb::csr_stream_bytes(A->Ad) + (A->halo ? pb::csr_stream_bytes(A->Ao) : 0.0);
+  if (coded_tiles) *coded_tiles = (PetscInt)A->Ad.pk_coded;
+  if (tiles) *tiles = (A->Ad.n + pb::TR - 1) / pb::TR;
+  return 0;
+}
+
+PetscErrorCode PermonB200PackTiles(PetscInt n, const PetscInt ia[], const PetscInt ja[], const PetscScalar a[], unsigned char **blob, unsigned **tile_off,
+                                   PetscInt *ntiles, PetscInt *coded_tiles)
+{
+  if (!ia || !blob || !tile_off) return err(PETSC_ERR_ARG_NULL, "null argument");
+  std::vector<unsigned char> b;
+  std::vector<unsigned>      off;
+  int                        max_tile = 0;
+  int64_t                    ncoded = 0;
+  bool                       packed = false;
+  PB_CHK(pb::pk_build(n, ia, ja, a, b, off, max_tile, ncoded, packed));
+  *blob     = nullptr;
+  *tile_off = nullptr;
+  if (ntiles) *ntiles = (n + pb::TR - 1) / pb::TR;
+  if (coded_tiles) *coded_tiles = (PetscInt)ncoded;
+  if (!packed) return 0;
+  *blob     = (unsigned char *)malloc(b.size());
+  *tile_off = (unsigned *)malloc(sizeof(unsigned) * off.size());
+  if (!*blob || !*tile_off) return err(PETSC_ERR_MEM, "out of memory");
+  memcpy(*blob, b.data(), b.size());
+  memcpy(*tile_off, off.data(), sizeof(unsigned) * off.size());
+  return 0;
+}
+
+PetscErrorCode PermonB200PackFree(unsigned char *blob, unsigned *tile_off)
+{
+  free(blob);
+  free(tile_off);
   return 0;
 }
 

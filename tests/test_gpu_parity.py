@@ -151,6 +151,68 @@ def test_spmv_against_oracle(P, kind):
     P.VecDestroy(vx), P.VecDestroy(vy), P.MatDestroy(A)
 
 
+@pytest.mark.parametrize("kind", ["stencil5", "stencil7", "varcoef", "random_values", "mixed", "ragged", "random_columns"])
+def test_packed_tiles_bit_identical_to_csr(P, kind, monkeypatch):
+    """The dictionary-coded tile format (pack.cpp) is a lossless re-coding: same products, same order, same bits as the CSR kernel."""
+    import scipy.sparse as sp
+    rng = np.random.default_rng(11)
+    if kind == "stencil5":
+        pr = PR.obstacle2d(300)                      # 90000 rows: last tile partial
+        ia, ja, a = pr.ia, pr.ja, pr.a
+    elif kind == "stencil7":
+        pr = PR.obstacle3d(40)
+        ia, ja, a = pr.ia, pr.ja, pr.a
+    elif kind == "varcoef":
+        pr = PR.varcoef3d(32)
+        ia, ja, a = pr.ia, pr.ja, pr.a
+    elif kind == "random_values":                    # every value distinct: all tiles raw
+        pr = PR.obstacle2d(200)
+        ia, ja, a = pr.ia, pr.ja, pr.a * (1.0 + rng.random(len(pr.a)))
+    elif kind == "mixed":                            # a band of perturbed rows: raw tiles between coded ones
+        pr = PR.obstacle2d(256)
+        a = pr.a.copy()
+        lo, hi = pr.ia[20000], pr.ia[30000]
+        a[lo:hi] *= 1.0 + rng.random(hi - lo)
+        ia, ja = pr.ia, pr.ja
+    elif kind == "ragged":                           # stencil with entries knocked out: rows of different length (some empty), coded
+        pr = PR.obstacle2d(150)
+        S = sp.csr_matrix((pr.a, pr.ja, pr.ia), shape=(pr.n, pr.n)).tocoo()
+        keep = rng.random(S.nnz) < 0.6
+        S = sp.csr_matrix((S.data[keep], (S.row[keep], S.col[keep])), shape=(pr.n, pr.n))
+        S.sort_indices()
+        ia, ja, a = S.indptr, S.indices, S.data
+    else:                                            # random columns: every tile has > 256 distinct offsets -> raw tiles with ragged rows
+        S = sp.random(70000, 70000, density=0.00005, random_state=5, format="csr")
+        S.data[:] = rng.integers(1, 4, size=len(S.data)).astype(float)
+        S.sort_indices()
+        ia, ja, a = S.indptr, S.indices, S.data
+    n = len(ia) - 1
+    x = rng.standard_normal(n)
+    ys, infos = [], []
+    for force in (None, "tma"):
+        if force:
+            monkeypatch.setenv("PERMON_B200_SPMV", force)
+        else:
+            monkeypatch.delenv("PERMON_B200_SPMV", raising=False)
+        A = P.MatCreateAIJ(ia, ja, a)
+        infos.append(P.MatStorageInfo(A))
+        vx, vy = P.VecFromArray(x.copy()), P.VecCreate(n)
+        P.MatMult(A, vx, vy)
+        ys.append(P.VecGetArray(vy).copy())
+        P.VecDestroy(vx), P.VecDestroy(vy), P.MatDestroy(A)
+    assert infos[0]["kind"] == 3 and infos[1]["kind"] == 2
+    if kind in ("stencil5", "stencil7", "varcoef", "ragged"):
+        assert infos[0]["coded_tiles"] == infos[0]["tiles"]
+        assert infos[0]["stream_bytes"] < 0.25 * infos[1]["stream_bytes"]
+    elif kind == "random_values":
+        assert infos[0]["coded_tiles"] <= 1          # the 64-row tail tile has only 255 entries
+    elif kind == "random_columns":
+        assert infos[0]["coded_tiles"] <= 2
+    else:
+        assert 0 < infos[0]["coded_tiles"] < infos[0]["tiles"]
+    assert np.array_equal(ys[0], ys[1])
+
+
 def test_power_method(P):
     pr = PR.obstacle2d(128)
     A = P.MatCreateAIJ(pr.ia, pr.ja, pr.a)
