@@ -140,6 +140,12 @@ struct PushRanges {
   unsigned           *counter = nullptr;
   int                 gap_lo = 0, gap_hi = 0;   // largest run of rows outside every range
 };
+// rows whose K_A / K_A' epilogue is deferred to the ghost pass (multi-GPU): byte flags, consulted only outside [lo, hi) --
+// the widest run of rows without ghost columns, i.e. the interior of a slab
+struct SkipRows {
+  const unsigned char *flags = nullptr;
+  int                  lo = 0, hi = 0;
+};
 struct HaloWait {
   const unsigned long long *flags = nullptr;   // local: one flag slot (PB_FLAG_STRIDE apart) per neighbour
   int                       n = 0;
@@ -183,9 +189,9 @@ struct MpgpVecs {
   double *t = nullptr;           // inner-dimension work vector for product operators
 };
 // K_A  : Ap = A xin (xin = p, or t for product operators) + [p.Ap, g.p, B p, alpha_f]
-int k_fused_A(const CsrDev &A, const double *xin, const MpgpVecs &v, const MpgpCtl *S, RedBuf rb, const unsigned char *skip_epilogue);
+int k_fused_A(const CsrDev &A, const double *xin, const MpgpVecs &v, const MpgpCtl *S, RedBuf rb, SkipRows skip_epilogue);
 // K_A' : g = A xin - b (+rho B^T Bu), split, p = gf, [|gP|^2, |gc|^2, |gf|^2]; runs when step=='e' or init
-int k_fused_A2(const CsrDev &A, const double *xin, const MpgpVecs &v, const MpgpCtl *S, RedBuf rb, const unsigned char *skip_epilogue);
+int k_fused_A2(const CsrDev &A, const double *xin, const MpgpVecs &v, const MpgpCtl *S, RedBuf rb, SkipRows skip_epilogue);
 // off-diagonal (ghost) contribution + deferred epilogue for boundary rows (multi-GPU)
 int k_fused_A_ghost(const CsrDev &Ao, const double *ghost, const MpgpVecs &v, const MpgpCtl *S, RedBuf rb, int second, HaloWait hw);
 // peer-memory halo push (which: 0 = p before K_A, 1 = x before K_A' [gated on step 'e' / init])

@@ -1153,7 +1153,8 @@ struct EpiAT {
   int                  m, n;
   const MpgpCtl       *S;
   RedBuf               rb;
-  const unsigned char *skip;    // rows whose epilogue is deferred to the ghost pass (multi-GPU)
+  SkipRows             skip;    // rows whose epilogue is deferred to the ghost pass (multi-GPU)
+  __device__ bool skipped(int r) const { return skip.flags && (r < skip.lo || r >= skip.hi) && skip.flags[r]; }
   typedef AccRed       Acc;
   __device__ bool active() const { return S->reason == 0; }
   __device__ void init(Acc &a) const
@@ -1175,7 +1176,7 @@ struct EpiAT {
   __device__ void row(int r, double ax, Acc &a) const
   {
     Ap[r] = ax;
-    if (skip && skip[r]) return;
+    if (skipped(r)) return;
     epilogue(r, ax, a);
   }
   __device__ void finalize(Acc &a) const { grid_reduce8<(1 << RA_FEAS)>(a.v, rb, nullptr); }
@@ -1203,7 +1204,7 @@ struct EpiAT {
   __device__ void row_s(int r, uint32_t va, double ax, Acc &a) const
   {
     Ap[r] = ax;
-    if (skip && skip[r]) return;
+    if (skipped(r)) return;
     const double pr = lds_f64(va);
     a.v[RA_PAP] += pr * ax;
     a.v[RA_GP] += lds_f64(va + TR * 8) * pr;
@@ -1241,7 +1242,8 @@ struct EpiA2T {
   int                  m, n;
   const MpgpCtl       *S;
   RedBuf               rb;
-  const unsigned char *skip;
+  SkipRows             skip;
+  __device__ bool skipped(int r) const { return skip.flags && (r < skip.lo || r >= skip.hi) && skip.flags[r]; }
   typedef AccRed       Acc;
   __device__ bool active() const { return S->reason == 0 && (S->step == 'e' || S->init); }
   __device__ void init(Acc &a) const
@@ -1269,7 +1271,7 @@ struct EpiA2T {
   }
   __device__ void row(int r, double ax, Acc &a) const
   {
-    if (skip && skip[r]) {
+    if (skipped(r)) {
       g[r] = ax;   // partial product parked in g until the ghost pass
       return;
     }
@@ -1297,7 +1299,7 @@ struct EpiA2T {
   }
   __device__ void row_s(int r, uint32_t va, double ax, Acc &a) const
   {
-    if (skip && skip[r]) {
+    if (skipped(r)) {
       g[r] = ax;
       return;
     }
@@ -1395,7 +1397,7 @@ static double bytes_A2(const CsrDev &A, const MpgpVecs &v)
   return csr_stream_bytes(A) + 8.0 * v.n * (4 + (v.bx.lb ? 1 : 0) + (v.bx.ub ? 1 : 0) + v.m);
 }
 
-int k_fused_A(const CsrDev &A, const double *xin, const MpgpVecs &v, const MpgpCtl *S, RedBuf rb, const unsigned char *skip)
+int k_fused_A(const CsrDev &A, const double *xin, const MpgpVecs &v, const MpgpCtl *S, RedBuf rb, SkipRows skip)
 {
   if (v.bx.lb && !v.bx.ub && v.m == 0) {
     EpiAT<true> e{v.p, v.g, v.x, v.Ap, v.bx, v.B, v.m, v.n, S, rb, skip};
@@ -1405,7 +1407,7 @@ int k_fused_A(const CsrDev &A, const double *xin, const MpgpVecs &v, const MpgpC
   return launch_spmv(A, xin, e, KF_SPMV_A, bytes_A(A, v));
 }
 
-int k_fused_A2(const CsrDev &A, const double *xin, const MpgpVecs &v, const MpgpCtl *S, RedBuf rb, const unsigned char *skip)
+int k_fused_A2(const CsrDev &A, const double *xin, const MpgpVecs &v, const MpgpCtl *S, RedBuf rb, SkipRows skip)
 {
   if (v.bx.lb && !v.bx.ub && v.m == 0) {
     EpiA2T<true> e{v.x, v.b, v.g, v.p, v.bx, v.B, v.m, v.n, S, rb, skip};
@@ -1419,8 +1421,8 @@ int k_fused_A_ghost(const CsrDev &Ao, const double *ghost, const MpgpVecs &v, co
 {
   // rb.out: final record; the diagonal pass left its record in rb.out as well -> read it as `prev`
   RedBuf rd = rb;
-  EpiA  ea{v.p, v.g, v.x, v.Ap, v.bx, v.B, v.m, v.n, S, rd, nullptr};
-  EpiA2 e2{v.x, v.b, v.g, v.p, v.bx, v.B, v.m, v.n, S, rd, nullptr};
+  EpiA  ea{v.p, v.g, v.x, v.Ap, v.bx, v.B, v.m, v.n, S, rd, SkipRows()};
+  EpiA2 e2{v.x, v.b, v.g, v.p, v.bx, v.B, v.m, v.n, S, rd, SkipRows()};
   double bytes = 12.0 * (double)Ao.nnz + 8.0 * Ao.n * 8;
   if (second) {
     EpiGhost<true> e{ea, e2, rb.out, hw};

@@ -70,6 +70,7 @@ struct HaloPlan {
   int                  *d_send_idx = nullptr;
   double               *d_send = nullptr, *d_ghost = nullptr;
   unsigned char        *d_skip = nullptr;   // [n] 1 for rows with ghost columns
+  int                   skip_lo = 0, skip_hi = 0;   // widest run of rows without ghost columns
   PetscInt              nboundary = 0;
   cudaEvent_t           ev_packed = nullptr, ev_arrived = nullptr, ev_consumed = nullptr;
   // peer-memory halo: neighbours store their boundary values straight into my ghost window

@@ -648,7 +648,12 @@ int MpgpImpl::solve_fused(QPS qps)
   Mat        M1 = prod ? base->M1 : base, M2 = prod ? base->M2 : nullptr;
   const bool multi = (qps->comm->size > 1);
   HaloPlan  *H = multi ? M1->halo : nullptr;
-  const unsigned char *skip = H ? H->d_skip : nullptr;
+  SkipRows skip;
+  if (H) {
+    skip.flags = H->d_skip;
+    skip.lo    = H->skip_lo;
+    skip.hi    = H->skip_hi;
+  }
 
   v.n = qp->x->n;
   PB_CHK(vec_dev_rw(qp->x, &v.x));

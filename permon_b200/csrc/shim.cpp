@@ -1128,6 +1128,16 @@ PetscErrorCode MatCreateMPIAIJWithArrays(MPI_Comm comm, PetscInt m, PetscInt n, 
     }
   }
   H->nboundary = (PetscInt)orow.size();
+  {   // widest run of interior rows: kernels skip the per-row flag lookup inside it
+    int best_lo = 0, best_hi = 0, cur = 0;
+    for (int r : orow) {
+      if (r - cur > best_hi - best_lo) best_lo = cur, best_hi = r;
+      cur = r + 1;
+    }
+    if ((int)m - cur > best_hi - best_lo) best_lo = cur, best_hi = (int)m;
+    H->skip_lo = best_lo;
+    H->skip_hi = best_hi;
+  }
   // neighbours that own my ghosts
   H->recv_off.push_back(0);
   for (size_t g = 0; g < gh.size();) {
