@@ -126,6 +126,12 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.rows.append((time.time(), line.strip()))
 
+    def wait_first(self, timeout=8.0):
+        """nvidia-smi needs a few hundred ms to start (longer on 8-GPU boxes): block until it delivers"""
+        t = time.time()
+        while self.proc and not self.rows and time.time() - t < timeout:
+            time.sleep(0.01)
+
     def window_open(self):
         self.t0 = time.time()
 
@@ -160,7 +166,7 @@ class ClockSampler:
         inwin = [r for r in self.rows if self.t0 is not None and self.t1 is not None and self.t0 <= r[0] <= self.t1 + 0.03]
         window = "timed"
         if not inwin:
-            inwin, window = self.rows, "warmup+timed (timed window shorter than the sampling period)"
+            inwin, window = self.rows, "set-up + warm-up + timed (timed window shorter than the sampling period)"
         sm, mx, reasons, pw = parse(inwin)
         if not sm:
             return dict(sm_mhz=None, sm_max_mhz=None, reasons=["no samples"])
@@ -306,14 +312,15 @@ def main():
         P.MatDestroy(h["A"])
 
     keep = []
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     # ---------------- device-resident leg -----------------------------------------------------------------
     h = make_solver(True, keep)
     P.QPSSetTolerances(h["qps"], rtol=1e-30, atol=1e-300, maxits=W - 1)     # never converge inside the window
     P.QPSSetUp(h["qps"])                                                      # upload done, power method done
     maxeig = P.QPSMPGPGetOperatorMaxEigenvalue(h["qps"])
     storage = P.MatStorageInfo(h["A"])
-    sampler = ClockSampler(local_rank)
-    sampler.start()
+    sampler.wait_first()
     P.QPSSolve(h["qps"])                                                      # W warm-up iterations
     assert P.QPSGetIterationNumber(h["qps"]) == W, (P.QPSGetIterationNumber(h["qps"]), W)
     x_after_warmup = h["dev"]["x"].clone()
@@ -347,19 +354,53 @@ def main():
         P.call("PermonB200ProfileDump", (os.environ["PERMON_B200_TIMELINE"] + f".rank{rank}.csv").encode())
     barrier()
     peak, peak_src = peaks()
-    ka = prof.get("K_A spmv+dots+feas", dict(launches=0, total_ms=0.0, bytes_per_launch=0.0))
-    ka_ms = ka["total_ms"] / max(ka["launches"], 1)
-    achieved = ka["bytes_per_launch"] / (ka_ms * 1e-3) / 1e9 if ka_ms > 0 else 0.0
+    nb = 1 + (1 if both else 0)                      # bound vectors
+    M = storage["stream_bytes"]
+    n_cg, n_ex = counts["ncg"] + counts["nprop"], counts["nexp"]
+    # algorithmic bytes per launch of each fused kernel in the layout it streams, averaged over the
+    # window's step mix where the kernel does different work per step kind
+    kbytes = {
+        "K_A spmv+dots+feas": M + 8 * n_loc * (4 + nb),                                                   # p g x bounds -> Ap
+        "K_B update+split": 8 * n_loc * ((n_cg * (7 + nb) + n_ex * (5 + nb)) / max(n_cg + n_ex, 1)),      # c/p: 5+nb r, 3 w; e: 4+nb r, 1 w
+        "K_A' spmv+grad+split": M + 8 * n_loc * (4 + nb),                                                 # x b bounds -> g p
+        "K_C direction": 8 * n_loc * 3,                                                                    # gf p -> p
+    }
+    klaunch = {"K_A spmv+dots+feas": None, "K_B update+split": None, "K_A' spmv+grad+split": n_ex, "K_C direction": n_cg}
+    per_kernel = {}
+    for fam, byts in kbytes.items():
+        pf = prof.get(fam)
+        if not pf or not pf["launches"]:
+            continue
+        real = klaunch[fam] if klaunch[fam] is not None else pf["launches"]   # launches that did work (the rest exit at once)
+        if fam == "K_A spmv+dots+feas" and size > 1:
+            real = pf["launches"] / 2                                           # diagonal pass + ghost pass per SpMV
+        if not real:
+            continue
+        avg = pf["total_ms"] / real
+        gbs = byts / (avg * 1e-3) / 1e9
+        per_kernel[fam] = dict(total_ms=round(pf["total_ms"], 3), working_launches=int(real), avg_ms=round(avg, 5), bytes_per_launch=int(byts),
+                               achieved_gbs=round(gbs, 1), frac_of_measured_peak=round(gbs / peak, 4))
     fam_ms = {k: round(v["total_ms"], 3) for k, v in prof.items() if v["launches"]}
     total_prof_ms = sum(v["total_ms"] for v in prof.values())
-    V_A = 4 + (1 if both else 0)
-    ka_csr_bytes = 12 * nnz_loc + 4 * (n_loc + 1) + 8 * n_loc * (V_A + 1)
-    roofline = dict(bound="hbm", kernel="K_A fused SpMV (Ap = A p, p.Ap, g.p, alpha_f)", achieved=round(achieved, 1), peak=peak, unit="GB/s",
-                    frac=round(achieved / peak, 4), traffic=None, peak_source=peak_src, launches=ka["launches"], avg_launch_ms=round(ka_ms, 5),
-                    algorithmic_bytes_per_launch=ka["bytes_per_launch"],
-                    bytes_note="bytes of the layout the kernel streams (packed matrix tiles + p, g, x, bounds, Ap); the CSR formula of SURVEY 8d would be csr_formula_bytes_per_launch",
-                    csr_formula_bytes_per_launch=ka_csr_bytes, csr_equivalent_gbs=round(ka_csr_bytes / (ka_ms * 1e-3) / 1e9, 1) if ka_ms > 0 else None,
-                    kernel_share_of_step=round(ka["total_ms"] / total_prof_ms, 4) if total_prof_ms else None, family_ms=fam_ms)
+    dom = max(per_kernel, key=lambda k: per_kernel[k]["total_ms"]) if per_kernel else None
+    dk = per_kernel.get(dom, dict(achieved_gbs=0.0, avg_ms=0.0, bytes_per_launch=0, working_launches=0, total_ms=0.0))
+    csr_M = 12 * nnz_loc + 4 * (n_loc + 1)
+    # DRAM traffic of the dominant kernel: taken from the committed `ncu --set full` capture of the same workload (never measured
+    # inside a bench run); null when no capture exists for this workload / rank count
+    traffic, traffic_src = None, None
+    try:
+        tj = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r1b_ncu_traffic.json")))
+        if size == 1 and spec["label"].startswith(tj["workload"] + " ") and dom in tj["dram_bytes_per_launch"]:
+            traffic, traffic_src = tj["dram_bytes_per_launch"][dom], tj["source"]
+    except Exception:
+        pass
+    roofline = dict(bound="hbm", kernel=dom, achieved=dk["achieved_gbs"], peak=peak, unit="GB/s", frac=round(dk["achieved_gbs"] / peak, 4), traffic=traffic,
+                    traffic_source=traffic_src,
+                    peak_source=peak_src, launches=dk["working_launches"], avg_launch_ms=dk["avg_ms"], algorithmic_bytes_per_launch=dk["bytes_per_launch"],
+                    kernel_share_of_step=round(dk["total_ms"] / total_prof_ms, 4) if total_prof_ms else None,
+                    bytes_note="bytes of the layout the kernels stream (packed matrix tiles + fp64 vectors); with the CSR formula of SURVEY 8d K_A / K_A' "
+                               "would count csr_matrix_bytes instead of matrix_bytes",
+                    matrix_bytes=int(M), csr_matrix_bytes=int(csr_M), per_kernel=per_kernel, family_ms=fam_ms)
     step_bytes, b_cg, b_exp = algorithmic_bytes(n_loc, nnz_loc, counts, both_bounds=both, matrix_bytes=storage["stream_bytes"])
     step_bytes_csr, b_cg_csr, b_exp_csr = algorithmic_bytes(n_loc, nnz_loc, counts, both_bounds=both)
     whole_iter_gbs = step_bytes / (ms * 1e-3) / 1e9

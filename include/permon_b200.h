@@ -82,6 +82,7 @@ typedef enum {
   KSP_DIVERGED_DTOL             = -4,
   KSP_DIVERGED_BREAKDOWN        = -5,
   KSP_DIVERGED_NANORINF         = -9,
+  KSP_DIVERGED_INDEFINITE_MAT   = -10,
   KSP_CONVERGED_ITERATING       = 0
 } KSPConvergedReason;
 
@@ -312,6 +313,8 @@ typedef struct _p_QPS *QPS;
 #define QPSType   char *
 #define QPSMPGP   "mpgp"   /* permonqps.h:13 */
 #define QPSSMALXE "smalxe" /* permonqps.h:16 */
+#define QPSKSP    "ksp"    /* permonqps.h:12: unconstrained QPs, conjugate gradients */
+#define QPSPCPG   "pcpg"   /* permonqps.h:15: equality-constrained QPs, projected conjugate gradients */
 
 typedef enum { QPS_ARG_MULTIPLE = 0, QPS_ARG_DIRECT = 1 } QPSScalarArgType; /* permonqps.h:19-22 */
 
@@ -357,6 +360,9 @@ PERMON_EXTERN PetscErrorCode QPSViewConvergence(QPS qps, PetscViewer viewer);   
 typedef enum { QPS_MPGP_EXPANSION_STD, QPS_MPGP_EXPANSION_PROJCG, QPS_MPGP_EXPANSION_GF, QPS_MPGP_EXPANSION_G, QPS_MPGP_EXPANSION_GFGR, QPS_MPGP_EXPANSION_GGR } QPSMPGPExpansionType;
 typedef enum { QPS_MPGP_EXPANSION_LENGTH_FIXED, QPS_MPGP_EXPANSION_LENGTH_OPT, QPS_MPGP_EXPANSION_LENGTH_OPTAPPROX, QPS_MPGP_EXPANSION_LENGTH_BB } QPSMPGPExpansionLengthType;
 PERMON_EXTERN PetscErrorCode QPSMPGPGetCurrentStepType(QPS qps, char *stepType);
+/* QPSKSP: the Krylov method behind the "ksp" type; without PETSc's KSP the accessors reduce to the type name ("cg") */
+PERMON_EXTERN PetscErrorCode QPSKSPSetType(QPS qps, const char *type);                 /* permonqps.h:91, qpsksp.c:83 */
+PERMON_EXTERN PetscErrorCode QPSKSPGetType(QPS qps, const char **type);                /* permonqps.h:92, qpsksp.c:100 */
 PERMON_EXTERN PetscErrorCode QPSMPGPSetAlpha(QPS qps, PetscReal alpha, QPSScalarArgType argtype);
 PERMON_EXTERN PetscErrorCode QPSMPGPGetAlpha(QPS qps, PetscReal *alpha, QPSScalarArgType *argtype);
 PERMON_EXTERN PetscErrorCode QPSMPGPSetGamma(QPS qps, PetscReal gamma);

@@ -235,6 +235,43 @@ def smalxe_solve(op: Operator, b, box: BoxC, B, c=None, x0=None, opts: SmalxeOpt
     return x, out
 
 
+class LinOpts(C.Structure):
+    _fields_ = [("rtol", C.c_double), ("atol", C.c_double), ("divtol", C.c_double), ("max_it", C.c_int), ("nthreads", C.c_int)]
+
+
+class LinResult(C.Structure):
+    _fields_ = [("its", C.c_int), ("reason", C.c_int), ("rnorm", C.c_double), ("norm_rhs", C.c_double), ("seconds", C.c_double)]
+
+
+def lin_opts(**kw) -> LinOpts:
+    o = LinOpts()
+    lib().orc_default_lin_opts(C.byref(o))
+    for k, v in kw.items():
+        setattr(o, k, v)
+    return o
+
+
+def cg_solve(op: Operator, b, x0=None, opts: LinOpts | None = None):
+    """QPSKSP = KSPCG without preconditioner (restated; parity unpinned, see permon_oracle.c)"""
+    b = f64(b)
+    x = np.zeros(op.n) if x0 is None else f64(x0).copy()
+    res = LinResult()
+    lib().orc_cg_solve(C.byref(op.c), _d(b), _d(x), C.byref(opts or lin_opts()), C.byref(res))
+    return x, {f[0]: getattr(res, f[0]) for f in LinResult._fields_}
+
+
+def pcpg_solve(op: Operator, b, G, c=None, x0=None, opts: LinOpts | None = None):
+    """QPSPCPG (pcpg.c:49-131) for min 1/2 x'Ax - b'x s.t. G x = c"""
+    b = f64(b)
+    Gm = f64(G).reshape(-1, op.n)
+    x = np.zeros(op.n) if x0 is None else f64(x0).copy()
+    res = LinResult()
+    cc = None if c is None else f64(c)
+    lib().orc_pcpg_solve(C.byref(op.c), _d(b), C.c_int(Gm.shape[0]), _d(Gm), _d(cc) if cc is not None else None, _d(x), C.byref(opts or lin_opts()),
+                         C.byref(res))
+    return x, {f[0]: getattr(res, f[0]) for f in LinResult._fields_}
+
+
 def max_eigenvalue(op: Operator, tol=DECIDE, maxits=-1):
     lam = C.c_double()
     its = lib().orc_max_eigenvalue(C.byref(op.c), C.c_double(tol), C.c_int(maxits), C.byref(lam))

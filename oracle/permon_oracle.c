@@ -1123,3 +1123,151 @@ int orc_smalxe_solve(orc_op *op, const double *b_user, const orc_box *bx_user, i
   free(Btmu); free(b_inner); free(BtBu); free(bw);
   return 0;
 }
+
+/* ------------------------------------------------------------------------------------------ */
+/* QPSKSP and QPSPCPG                                                      */
+/* ------------------------------------------------------------------------------------------ */
+void orc_default_lin_opts(orc_lin_opts *o)
+{
+  o->rtol = 1e-5; o->atol = 1e-50; o->divtol = 1e4; o->max_it = 10000; /* qps.c:73-76 */
+  o->nthreads = 1;
+}
+
+/* QPSConvergedDefault (qps.c:675-714) on plain scalars */
+static int lin_converged(int i, double rnorm, const orc_lin_opts *o, double norm_rhs)
+{
+  const double ttol = ORC_MAX(o->rtol * norm_rhs, o->atol);
+  if (i > o->max_it) return ORC_DIVERGED_ITS;
+  if (isnan(rnorm) || isinf(rnorm)) return ORC_DIVERGED_NANORINF;
+  if (rnorm <= ttol) return rnorm < o->atol ? ORC_CONVERGED_ATOL : ORC_CONVERGED_RTOL;
+  if (rnorm >= o->divtol * norm_rhs) return ORC_DIVERGED_DTOL;
+  return ORC_CONVERGED_ITERATING;
+}
+
+/* QPSSolve_KSP (qpsksp.c:137-153) hands the problem to PETSc's KSPCG configured in QPSCreate_KSP (qpsksp.c:232-253):
+ * KSPCG, PCNONE, KSP_NORM_UNPRECONDITIONED, non-zero initial guess, convergence through QPSKSPConverged_KSP -> the QPS test
+ * (qpsksp.c:5-14).  PETSc is not in the reference tree: what follows restates the published KSPSolve_CG recurrence
+ * (petsc src/ksp/ksp/impls/cg/cg.c, single-reduction off, real symmetric) -- parity UNPINNED, the reference has no test or
+ * golden output that runs QPSKSP.                                                                                       */
+int orc_cg_solve(const orc_op *op, const double *b, double *x, const orc_lin_opts *opts, orc_lin_result *res)
+{
+  const int n = op->n;
+  double   *R = (double *)malloc(sizeof(double) * (size_t)n), *P = (double *)malloc(sizeof(double) * (size_t)n),
+         *W = (double *)malloc(sizeof(double) * (size_t)n);
+  double beta, betaold = 1.0, dpi, a, dp, bb;
+  int    i = 0, reason;
+  orc_set_threads(opts->nthreads <= 0 ? 0 : opts->nthreads);
+  const double norm_rhs = orc_norm2(n, b);
+  const double t0 = now_seconds();
+  orc_op_apply(op, x, R);      /* r = b - A x  (initial guess non-zero) */
+  v_aypx(n, R, -1.0, b);
+  dp     = orc_norm2(n, R);    /* z = r (PCNONE); unpreconditioned norm */
+  reason = lin_converged(0, dp, opts, norm_rhs);
+  beta   = orc_dot(n, R, R);   /* beta = z'r */
+  if (!reason) {
+    do {
+      if (beta == 0.0) { reason = ORC_CONVERGED_ATOL; break; }
+      if (!i) {
+        v_copy(n, R, P);       /* p = z */
+      } else {
+        bb = beta / betaold;
+        v_aypx(n, P, bb, R);   /* p = z + b p */
+      }
+      orc_op_apply(op, P, W);  /* w = A p */
+      dpi     = orc_dot(n, P, W);
+      betaold = beta;
+      if (!(dpi > 0.0)) { reason = ORC_DIVERGED_INDEFINITE_MAT; break; }
+      a = beta / dpi;
+      v_axpy(n, x, a, P);      /* x += a p */
+      v_axpy(n, R, -a, W);     /* r -= a w */
+      dp     = orc_norm2(n, R);
+      reason = lin_converged(i + 1, dp, opts, norm_rhs);
+      i++;
+      if (reason) break;
+      beta = orc_dot(n, R, R);
+    } while (i < opts->max_it);
+    if (!reason) reason = ORC_DIVERGED_ITS;
+  }
+  res->its = i; res->reason = reason; res->rnorm = dp; res->norm_rhs = norm_rhs; res->seconds = now_seconds() - t0;
+  free(R); free(P); free(W);
+  return 0;
+}
+
+/* P v = v - G^T (G G^T)^{-1} G v : QPPFApplyP = QPPFApplyQ + VecAYPX (qppf.c:454-502,560-575) */
+static void pf_apply_P(int n, int m, const double *G, int orth, const double *v, double *Pv, double *gl, double *y)
+{
+  for (int j = 0; j < m; j++) gl[j] = orc_dot(n, G + (size_t)j * n, v);
+  if (!orth) ggt_solve(n, m, G, gl, y);
+  else memcpy(y, gl, sizeof(double) * (size_t)m);
+  for (int k = 0; k < n; k++) {
+    double s = 0.0;
+    for (int j = 0; j < m; j++) s += G[(size_t)j * n + k] * y[j];
+    Pv[k] = v[k] + -1.0 * s;
+  }
+}
+
+/* QPSSolve_PCPG: src/qps/impls/pcpg/pcpg.c:49-131 with PCNONE (y = w); QPSSetup_PCPG (:31-41) homogenises G x = c first
+ * (QPTHomogenizeEq, qptransform.c:437-527: xtilde = G^T (G G^T)^{-1} c, b_bar = b - A xtilde, the child starts from a copy
+ * of the parent's x, and the post-solve adds xtilde back).                                                              */
+int orc_pcpg_solve(const orc_op *op, const double *b_user, int m, const double *G, const double *c, double *x_user, const orc_lin_opts *opts,
+                   orc_lin_result *res)
+{
+  const int    n = op->n;
+  const size_t nb = sizeof(double) * (size_t)n;
+  double      *p = (double *)malloc(nb), *r = (double *)malloc(nb), *w = (double *)malloc(nb), *Ap = (double *)malloc(nb);
+  double      *gl = (double *)malloc(sizeof(double) * (size_t)(m > 0 ? m : 1)), *yy = (double *)malloc(sizeof(double) * (size_t)(m > 0 ? m : 1));
+  double      *xtilde = NULL, *bh = NULL, *x = x_user;
+  const double *b = b_user;
+  double       alpha, alpha1, beta, beta1 = 0.0, beta2, rnorm = 0.0;
+  int          it = 0, reason = ORC_CONVERGED_ITERATING;
+  orc_set_threads(opts->nthreads <= 0 ? 0 : opts->nthreads);
+  const int orth = rows_orthonormal(n, m, G);
+  if (c) {
+    xtilde = (double *)malloc(nb);
+    bh     = (double *)malloc(nb);
+    if (!orth) ggt_solve(n, m, G, c, yy);
+    else memcpy(yy, c, sizeof(double) * (size_t)m);
+    for (int k = 0; k < n; k++) {
+      double s = 0.0;
+      for (int j = 0; j < m; j++) s += G[(size_t)j * n + k] * yy[j];
+      xtilde[k] = s;
+    }
+    orc_op_apply(op, xtilde, bh);
+    v_aypx(n, bh, -1.0, b_user);
+    b = bh;
+    x = (double *)malloc(nb);
+    memcpy(x, x_user, nb);
+  }
+  const double norm_rhs = orc_norm2(n, b);
+  const double t0 = now_seconds();
+  orc_op_apply(op, x, r);   /* :95-96  r = b - A lm */
+  v_aypx(n, r, -1.0, b);
+  do {
+    pf_apply_P(n, m, G, orth, r, w, gl, yy);             /* :100 */
+    rnorm  = orc_norm2(n, w);                            /* :103 */
+    reason = lin_converged(it, rnorm, opts, norm_rhs);   /* :104 */
+    if (reason) break;
+    beta2 = beta1;                                       /* :113  (y = w) */
+    beta1 = orc_dot(n, w, w);
+    if (!it) {
+      beta = 0;
+      v_copy(n, w, p);                                   /* :117 */
+    } else {
+      beta = beta1 / beta2;
+      v_aypx(n, p, beta, w);                             /* :120 */
+    }
+    orc_op_apply(op, p, Ap);                             /* :122 */
+    alpha1 = orc_dot(n, p, Ap);
+    alpha  = beta1 / alpha1;
+    v_axpy(n, x, alpha, p);                              /* :125 */
+    v_axpy(n, r, -alpha, Ap);
+    it++;
+  } while (it < opts->max_it);                           /* :129 */
+  if (c) { /* QPTHomogenizeEqPostSolve: x = x_child + xtilde */
+    for (int k = 0; k < n; k++) x_user[k] = x[k] + xtilde[k];
+    free(x); free(xtilde); free(bh);
+  }
+  res->its = it; res->reason = reason; res->rnorm = rnorm; res->norm_rhs = norm_rhs; res->seconds = now_seconds() - t0;
+  free(p); free(r); free(w); free(Ap); free(gl); free(yy);
+  return 0;
+}

@@ -50,7 +50,8 @@ enum {
   ORC_DIVERGED_ITS              = -3,
   ORC_DIVERGED_DTOL             = -4,
   ORC_DIVERGED_BREAKDOWN        = -5,
-  ORC_DIVERGED_NANORINF         = -9
+  ORC_DIVERGED_NANORINF         = -9,
+  ORC_DIVERGED_INDEFINITE_MAT   = -10
 };
 
 /* include/permonqps.h:100-114 */
@@ -143,6 +144,24 @@ typedef struct {
   double rnorm, normBu, M1, rho, maxeig, maxeig_inner, alpha_inner, eta;
   double seconds;
 } orc_smalxe_result;
+
+/* linear solvers of the "next" rows: QPSKSP (= PETSc KSPCG, PCNONE, unpreconditioned norm, non-zero
+ * initial guess: src/qps/impls/ksp/qpsksp.c:232-253) and QPSPCPG (src/qps/impls/pcpg/pcpg.c:49-131) */
+typedef struct {
+  double rtol, atol, divtol;
+  int    max_it;
+  int    nthreads;
+} orc_lin_opts;
+typedef struct {
+  int    its, reason;
+  double rnorm, norm_rhs;
+  double seconds;
+} orc_lin_result;
+void orc_default_lin_opts(orc_lin_opts *o);
+int  orc_cg_solve(const orc_op *op, const double *b, double *x, const orc_lin_opts *opts, orc_lin_result *res);
+/* min 1/2 x'Ax - b'x  s.t.  G x = c  (G dense row-major m x n, c may be NULL = 0) */
+int  orc_pcpg_solve(const orc_op *op, const double *b, int m, const double *G, const double *c, double *x, const orc_lin_opts *opts,
+                    orc_lin_result *res);
 
 void orc_default_mpgp_opts(orc_mpgp_opts *o);
 void orc_default_smalxe_opts(orc_smalxe_opts *o);

@@ -510,6 +510,12 @@ def QPSSetType(qps, t):
     call("QPSSetType", qps, t.encode())
 
 
+def QPSGetType(qps) -> str:
+    t = C.c_char_p()
+    call("QPSGetType", qps, C.byref(t))
+    return t.value.decode()
+
+
 def QPSSetQP(qps, qp):
     call("QPSSetQP", qps, qp)
 

@@ -25,6 +25,8 @@ using namespace pb;
 static std::map<std::string, PetscErrorCode (*)(QPS)> g_qps_registry;
 static PetscErrorCode                                QPSCreate_MPGP(QPS qps);
 static PetscErrorCode                                QPSCreate_SMALXE(QPS qps);
+PetscErrorCode                                       QPSCreate_KSP(QPS qps);    // qps_lin.cpp
+PetscErrorCode                                       QPSCreate_PCPG(QPS qps);
 extern "C" PetscErrorCode                            QPSConverged_Inner_SMALXE(QPS qps_inner, KSPConvergedReason *reason);
 int                                                  smalxe_fill_ctl(QPS inner, MpgpCtl *S, bool *host_needed);
 int                                                  smalxe_read_ctl(QPS inner, const MpgpCtl *S);
@@ -41,6 +43,7 @@ static const char *reason_name(int r)
   case KSP_DIVERGED_DTOL: return "DIVERGED_DTOL";
   case KSP_DIVERGED_BREAKDOWN: return "DIVERGED_BREAKDOWN";
   case KSP_DIVERGED_NANORINF: return "DIVERGED_NANORINF";
+  case KSP_DIVERGED_INDEFINITE_MAT: return "DIVERGED_INDEFINITE_MAT";
   case KSP_CONVERGED_ITERATING: return "CONVERGED_ITERATING";
   }
   return "UNKNOWN";
@@ -78,6 +81,8 @@ static void qps_register_all()
   if (!g_qps_registry.empty()) return;
   QPSRegister(QPSMPGP, QPSCreate_MPGP);
   QPSRegister(QPSSMALXE, QPSCreate_SMALXE);
+  QPSRegister(QPSKSP, QPSCreate_KSP);
+  QPSRegister(QPSPCPG, QPSCreate_PCPG);
 }
 
 PetscErrorCode QPSConvergedDefaultCreate(void **ctx)
@@ -151,7 +156,7 @@ PetscErrorCode QPSSetType(QPS qps, const QPSType type)
 {   // qps.c:379-406
   if (qps->impl && qps->type == type) return 0;
   auto it = g_qps_registry.find(type);
-  if (it == g_qps_registry.end()) return err(PETSC_ERR_ARG_UNKNOWN_TYPE, "Unable to find requested QPS type %s (the B200 build provides \"mpgp\" and \"smalxe\")", type);
+  if (it == g_qps_registry.end()) return err(PETSC_ERR_ARG_UNKNOWN_TYPE, "Unable to find requested QPS type %s (the B200 build provides \"mpgp\", \"smalxe\", \"ksp\" and \"pcpg\")", type);
   if (qps->impl) {
     qps->impl->reset(qps);
     delete qps->impl;
@@ -175,7 +180,7 @@ PetscErrorCode QPSSetDefaultType(QPS qps)
   PB_CHK(QPChainGetLast(qps->topQP, &qp));
   if (qp->BE) PB_CHK(QPSSetType(qps, (char *)QPSSMALXE));
   else if (qp->qpc) PB_CHK(QPSSetType(qps, (char *)QPSMPGP));
-  else return err(PETSC_ERR_SUP, "unconstrained QPs (QPSKSP) are outside the B200 hot path");
+  else PB_CHK(QPSSetType(qps, (char *)QPSKSP));
   qps->user_type = false;
   return 0;
 }
