@@ -177,6 +177,8 @@ def algorithmic_bytes(n, nnz, counts, both_bounds=False, matrix_bytes=None):
     """B_cg = M + 8 n V ; B_exp = 2 M + 8 n V_e ; proportioning ~ B_cg, with M the matrix stream of one SpMV:
     12 nnz + 4(n+1) for CSR (the survey's formula), or the bytes of the packed tile format the library actually keeps in HBM."""
     V, Ve = (18, 19) if both_bounds else (16, 16)
+    if matrix_bytes is not None:
+        V -= 0.75          # layout actually streamed: K_B writes a byte mask instead of gf (-7/8 pass), K_C reads g + the mask (+1/8)
     M = 12 * nnz + 4 * (n + 1) if matrix_bytes is None else matrix_bytes
     b_cg = M + 8 * n * V
     b_exp = 2 * M + 8 * n * Ve
@@ -203,6 +205,39 @@ def run_oracle(pr, warmup, steps, budget_s, maxeig=None):
                 sample=f"{its} MPGP iterations (after {r0['its']} warm-up iterations) of the full-size workload, {threads} OpenMP threads standing in for MPI ranks")
 
 
+def short_device_leg(P, torch, dev, stream, pr, W, K):
+    """device-resident MPGP window on one GPU, no profiling / e2e: used for the N = 1 point of the C3 strong-scaling series"""
+    A = P.MatCreateAIJ(pr.ia, pr.ja, pr.a, ncols_local=pr.n)
+    d = {k: torch.from_numpy(np.ascontiguousarray(getattr(pr, k))).to(dev) for k in ("b", "lb")}
+    d["x"] = torch.zeros(pr.n, dtype=torch.float64, device=dev)
+    vb, vlb, vx = (P.VecFromDevicePointer(d[k].data_ptr(), pr.n) for k in ("b", "lb", "x"))
+    qp = P.QPCreate()
+    P.QPSetOperator(qp, A); P.QPSetRhs(qp, vb); P.QPSetInitialVector(qp, vx); P.QPSetBox(qp, None, vlb, None)
+    qps = P.QPSCreate()
+    P.QPSSetType(qps, "mpgp"); P.QPSSetQP(qps, qp); P.QPSSetAutoPostSolve(qps, False)
+    P.QPSSetTolerances(qps, rtol=1e-30, atol=1e-300, maxits=W - 1)
+    P.QPSSetUp(qps)
+    P.QPSSolve(qps)
+    c0 = P.QPSMPGPGetStepCounts(qps)
+    P.QPSSetTolerances(qps, maxits=K - 1)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record(stream)
+    P.QPSSolve(qps)
+    e1.record(stream)
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    assert P.QPSGetIterationNumber(qps) == K
+    c1 = P.QPSMPGPGetStepCounts(qps)
+    P.QPSDestroy(qps); P.QPDestroy(qp)
+    for v in (vb, vlb, vx):
+        P.VecDestroy(v)
+    P.MatDestroy(A)
+    del d
+    torch.cuda.empty_cache()
+    return dict(value=round(K / (ms * 1e-3), 2), unit=UNIT, ms_per_step=round(ms / K, 5), steps=K, warmup=W, step_mix={k: c1[k] - c0[k] for k in c1})
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -212,6 +247,7 @@ def main():
     ap.add_argument("--workload", default="auto")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-scaling-base", action="store_true")
     ap.add_argument("--cpu-budget", type=float, default=20.0)
     args = ap.parse_args()
     K, W = max(1, args.steps), max(3, args.warmup)
@@ -361,9 +397,9 @@ def main():
     # window's step mix where the kernel does different work per step kind
     kbytes = {
         "K_A spmv+dots+feas": M + 8 * n_loc * (4 + nb),                                                   # p g x bounds -> Ap
-        "K_B update+split": 8 * n_loc * ((n_cg * (7 + nb) + n_ex * (5 + nb)) / max(n_cg + n_ex, 1)),      # c/p: 5+nb r, 3 w; e: 4+nb r, 1 w
+        "K_B update+split": 8 * n_loc * ((n_cg * (6.125 + nb) + n_ex * (5 + nb)) / max(n_cg + n_ex, 1)),  # c/p: 4+nb r, x g + byte mask w; e: 4+nb r, 1 w
         "K_A' spmv+grad+split": M + 8 * n_loc * (4 + nb),                                                 # x b bounds -> g p
-        "K_C direction": 8 * n_loc * 3,                                                                    # gf p -> p
+        "K_C direction": 8 * n_loc * 3.125,                                                                # g, byte mask, p -> p
     }
     klaunch = {"K_A spmv+dots+feas": None, "K_B update+split": None, "K_A' spmv+grad+split": n_ex, "K_C direction": n_cg}
     per_kernel = {}
@@ -439,6 +475,24 @@ def main():
         cpu = dict(value=round(res["value"], 3), unit=UNIT, cores=res["threads"], kind="port", sample=res["sample"],
                    note="restatement of the reference CPU path (un-fused PETSc call sequence), not PETSc itself; the reference cannot be built here")
 
+    # ---------------- N = 1 point of the strong-scaling series --------------------------------------------------
+    # BASELINE.json quotes the metric on C2 for one GPU and on C3 for 1/2/4/8 GPUs: the N = 1 headline is C2, the N > 1 lines are
+    # C3, so the one-GPU C3 number that the scaling efficiency has to be computed against is measured here as well
+    scaling_base = None
+    if size == 1 and args.workload == "auto" and not args.no_scaling_base:
+        spec3 = workload_spec("c3", 1)
+        t3 = time.time()
+        pr3 = generate(spec3, 0, 1)
+        sb = short_device_leg(P, torch, dev, stream, pr3, 20, min(K, 300))
+        sb.update(workload=spec3["label"], seconds_total=round(time.time() - t3, 1),
+                  note="N = 1 point of the C3 strong-scaling series that `bench.py --gpus N` (N > 1) reports: efficiency(N) = value(N) / (N * scaling_base.value)")
+        scaling_base = sb
+        del pr3
+    scaling_note = None
+    if size > 1:
+        scaling_note = ("strong scaling of C3 (fixed 134M-dof problem); its one-GPU point is the `scaling_base` object of the N = 1 line, "
+                        "whose headline `value` is C2 as BASELINE.json asks")
+
     if rank == 0:
         line = dict(metric=METRIC, value=round(value, 2), unit=UNIT, n_gpus=size, steps=K, warmup=W, ms_per_step=round(ms / K, 5), higher_is_better=True,
                     scaling="strong", vs_baseline=None, dtype="f64", data="synthetic",
@@ -451,6 +505,10 @@ def main():
                                 frac_of_measured_hbm_whole_iteration=round(whole_iter_gbs / peak, 4), frac_of_8tbs_whole_iteration=round(whole_iter_gbs / 8000.0, 4),
                                 generate_s=round(t_gen, 1)),
                     clocks=clocks, e2e=e2e, gpu_launches=int(launches), roofline=roofline, cpu_baseline=cpu)
+        if scaling_base:
+            line["scaling_base"] = scaling_base
+        if scaling_note:
+            line["scaling_note"] = scaling_note
         print(json.dumps(line), flush=True)
     if size > 1:
         dist.destroy_process_group()

@@ -310,6 +310,9 @@ __device__ __forceinline__ void box_split(double x, double g, const BoxVal &b, d
   }
 }
 // QPCGradReduced (qpc.c:601 prefill + qpcbox.c:86-92)
+// 1 when the split replaced g by +0.0 (bit comparison: a NaN gradient stays "not replaced", -0.0 counts as replaced)
+__device__ __forceinline__ unsigned char gf_differs(double gf, double g) { return __double_as_longlong(gf) != __double_as_longlong(g); }
+
 __device__ __forceinline__ double box_reduced(double x, double gf, const BoxVal &b, double alpha)
 {
   double gr = gf;
@@ -1609,7 +1612,7 @@ __global__ void __launch_bounds__(NT, EQ ? 3 : 4) k_update_B(MpgpVecs v, CtrlFol
     const int      n2 = n >> 1;
     const double2 *x2 = reinterpret_cast<const double2 *>(v.x), *p2 = reinterpret_cast<const double2 *>(v.p), *g2 = reinterpret_cast<const double2 *>(v.g),
                   *A2 = reinterpret_cast<const double2 *>(v.Ap), *l2 = reinterpret_cast<const double2 *>(v.bx.lb), *u2 = reinterpret_cast<const double2 *>(v.bx.ub);
-    double2 *xo = reinterpret_cast<double2 *>(v.x), *go = reinterpret_cast<double2 *>(v.g), *fo = reinterpret_cast<double2 *>(v.gf), *po = reinterpret_cast<double2 *>(v.p);
+    double2 *xo = reinterpret_cast<double2 *>(v.x), *go = reinterpret_cast<double2 *>(v.g), *po = reinterpret_cast<double2 *>(v.p);
     int glo = INT_MAX, ghi = INT_MAX;
     if (PUSH && pushx) {
       glo = hp->gap_lo;
@@ -1649,8 +1652,14 @@ __global__ void __launch_bounds__(NT, EQ ? 3 : 4) k_update_B(MpgpVecs v, CtrlFol
         update_cp_elem<EQ>(step, acg, astol, xr.y, pr.y, g0.y, a1, b1, br1, m, xn.y, gn.y, gf.y, acc);
         xo[i] = xn;
         go[i] = gn;
-        if (step == 'c') fo[i] = gf;   // mpgp.c:555: gf kept for the direction update
-        else po[i] = gf;               // mpgp.c:638: p = gf
+        if (step == 'c') {             // mpgp.c:555: gf is needed once more, by the direction update: K_C rebuilds it from g
+          uchar2 am;                   // and this byte mask (gf = active ? 0 : g), 1/8 of the bytes of writing gf itself
+          am.x = gf_differs(gf.x, gn.x);
+          am.y = gf_differs(gf.y, gn.y);
+          reinterpret_cast<uchar2 *>(v.gf)[i] = am;
+        } else {
+          po[i] = gf;                  // mpgp.c:638: p = gf
+        }
       }
     }
   } else {
@@ -1673,7 +1682,7 @@ __global__ void __launch_bounds__(NT, EQ ? 3 : 4) k_update_B(MpgpVecs v, CtrlFol
         update_cp_elem<EQ>(step, acg, astol, xr, pr, g0, apr, b, brow, m, xn, gn, gf, acc);
         v.x[r] = xn;
         v.g[r] = gn;
-        if (step == 'c') v.gf[r] = gf;
+        if (step == 'c') reinterpret_cast<unsigned char *>(v.gf)[r] = gf_differs(gf, gn);
         else v.p[r] = gf;
       }
     }
@@ -1696,8 +1705,8 @@ int k_fused_B(const MpgpVecs &v, const CtrlFold &cf, RedBuf rb, const PushRanges
   int        need = ((vec2 ? v.n / 2 : v.n) + NT - 1) / NT;
   if (need < 1) need = 1;
   if (grid > need) grid = need;
-  // x p g Ap lb[ub] read, x g gf written (CG step)
-  prof_pre(KF_UPDATE_B, 8.0 * v.n * (7 + (v.bx.lb ? 1 : 0) + (v.bx.ub ? 1 : 0) + v.m));
+  // x p g Ap lb[ub] read, x g + the gf byte mask written (CG step)
+  prof_pre(KF_UPDATE_B, 8.0 * v.n * (6.125 + (v.bx.lb ? 1 : 0) + (v.bx.ub ? 1 : 0) + v.m));
   if (v.m > 0) {
     if (vec2) launch_B<true, true>(grid, v, cf, rb, hp, push_seq);
     else launch_B<true, false>(grid, v, cf, rb, hp, push_seq);
@@ -1737,7 +1746,8 @@ __global__ void __launch_bounds__(NT, 8) k_direction_C(MpgpVecs v, CtrlFold cf, 
   const int    stride = gridDim.x * NT;
   if (pmode == 1) {
     if (vec2) {
-      const double2 *f2 = reinterpret_cast<const double2 *>(v.gf);
+      const double2 *g2 = reinterpret_cast<const double2 *>(v.g);
+      const uchar2  *a2 = reinterpret_cast<const uchar2 *>(v.gf);   // K_B's byte mask lives in the gf array
       double2       *p2 = reinterpret_cast<double2 *>(v.p);
       const int      n2 = v.n >> 1;
       int            glo = INT_MAX, ghi = INT_MAX;
@@ -1746,10 +1756,11 @@ __global__ void __launch_bounds__(NT, 8) k_direction_C(MpgpVecs v, CtrlFold cf, 
         ghi = hp->gap_hi;
       }
       for (int i = blockIdx.x * NT + threadIdx.x; i < n2; i += stride) {
-        const double2 f = f2[i], q = p2[i];
+        const double2 gg = g2[i], q = p2[i];
+        const uchar2  am = a2[i];
         double2       pn;
-        pn.x  = f.x - bcg * q.x;
-        pn.y  = f.y - bcg * q.y;
+        pn.x  = (am.x ? 0.0 : gg.x) - bcg * q.x;
+        pn.y  = (am.y ? 0.0 : gg.y) - bcg * q.y;
         p2[i] = pn;
         if (PUSH && (2 * i < glo || 2 * i + 1 >= ghi)) {
           push_boundary(hp, 2 * i, pn.x);
@@ -1758,7 +1769,7 @@ __global__ void __launch_bounds__(NT, 8) k_direction_C(MpgpVecs v, CtrlFold cf, 
       }
     } else {
       for (int r = blockIdx.x * NT + threadIdx.x; r < v.n; r += stride) {
-        const double pn = v.gf[r] - bcg * v.p[r];
+        const double pn = (reinterpret_cast<const unsigned char *>(v.gf)[r] ? 0.0 : v.g[r]) - bcg * v.p[r];
         v.p[r]          = pn;
         if (PUSH) push_boundary(hp, r, pn);
       }
@@ -1787,8 +1798,8 @@ int k_fused_C(const MpgpVecs &v, const CtrlFold &cf, const PushRanges *hp, unsig
   int need = (v.n + NT - 1) / NT;
   if (need < 1) need = 1;
   if (grid > need) grid = need;
-  const int vec2 = (v.n % 2 == 0) && aligned16(v.gf) && aligned16(v.p) && !getenv("PERMON_B200_NOVEC");
-  prof_pre(KF_DIR_C, 8.0 * v.n * 3);
+  const int vec2 = (v.n % 2 == 0) && aligned16(v.gf) && aligned16(v.g) && aligned16(v.p) && !getenv("PERMON_B200_NOVEC");
+  prof_pre(KF_DIR_C, 8.0 * v.n * 3.125);
   if (hp) k_direction_C<true><<<grid, NT, 0, g_ctx.stream>>>(v, cf, hp, push_seq, vec2);
   else k_direction_C<false><<<grid, NT, 0, g_ctx.stream>>>(v, cf, nullptr, 0, vec2);
   prof_post(KF_DIR_C);

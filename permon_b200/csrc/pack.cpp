@@ -76,22 +76,38 @@ struct TileDict {
 
 // h_off: ntiles+1 offsets in units of 16 bytes.  Returns 0 on success; `packed` false when packing is not applicable
 // (a tile whose non-zero count or row lengths do not fit the 16-bit row offsets).
+//
+// Pass 1 (parallel over tiles) classifies every tile, builds its dictionary and writes the code bytes into a scratch array; the
+// k-th entry of a row is first compared with the k-th entry of the previous row (a hit for almost every entry of a stencil
+// matrix), the hash table is only consulted on a miss.  Pass 2 lays the blobs out: dictionary, row offsets and code bytes are
+// copied, nothing is hashed again.
 int pk_build(int n, const int *ia, const int *ja, const double *a, std::vector<unsigned char> &blob, std::vector<unsigned> &h_off, int &max_tile_bytes,
              int64_t &ncoded, bool &packed)
 {
   const int ntiles = (n + TR - 1) / TR;
   packed           = false;
   h_off.assign((size_t)ntiles + 1, 0);
-  std::vector<unsigned> tbytes(ntiles, 0);
+  std::vector<unsigned>      tbytes(ntiles, 0);
   std::vector<unsigned char> tkind(ntiles, 0);
   std::vector<uint16_t>      tnd(ntiles, 0);
-  std::vector<unsigned char> tpad(ntiles, 0);   // common (padded) row length of ragged short-row tiles, 0 = no padding
+  std::vector<unsigned char> tpad(ntiles, 0);    // common (padded) row length of ragged short-row tiles, 0 = no padding
+  std::vector<unsigned char> tuni(ntiles, 0);    // all rows of the tile have the same length
+  std::vector<int>           tthr(ntiles, 0);    // which thread's arena holds the tile's dictionary ...
+  std::vector<size_t>        tdoff(ntiles, 0);   // ... and where
+  const int64_t  nnz_all = n > 0 ? ia[n] : 0;
+  unsigned char *codes_tmp = (unsigned char *)malloc((size_t)std::max<int64_t>(nnz_all, 1));
+  if (!codes_tmp) return 55;
+  const int nthr = omp_get_max_threads();
+  std::vector<std::vector<int>>      arena_d(nthr);
+  std::vector<std::vector<uint64_t>> arena_b(nthr);
   bool    bad = false;
   int64_t coded = 0;
-  // pass 1: classify and size every tile
 #pragma omp parallel reduction(|| : bad) reduction(+ : coded)
   {
-    TileDict D;
+    TileDict               D;
+    const int              me = omp_get_thread_num();
+    std::vector<int>      &ad = arena_d[me];
+    std::vector<uint64_t> &ab = arena_b[me];
 #pragma omp for schedule(dynamic, 64)
     for (int t = 0; t < ntiles; t++) {
       const int r0 = t * TR, r1 = std::min(r0 + TR, n);
@@ -101,30 +117,47 @@ int pk_build(int n, const int *ia, const int *ja, const double *a, std::vector<u
         continue;
       }
       D.reset();
-      bool ok = true, uniform = true;
+      bool      ok = true, uniform = true;
       const int len0 = ia[r0 + 1] - ia[r0];
+      int       maxlen = 0, prev_len = 0;
+      const unsigned char *prev = nullptr;
       for (int r = r0; r < r1 && ok; r++) {
-        if (ia[r + 1] - ia[r] != len0) uniform = false;
-        for (int k = ia[r]; k < ia[r + 1]; k++) {
+        const int      len = ia[r + 1] - ia[r];
+        unsigned char *rc = codes_tmp + ia[r];
+        if (len != len0) uniform = false;
+        if (len > maxlen) maxlen = len;
+        for (int k = 0; k < len; k++) {
           uint64_t b;
-          memcpy(&b, &a[k], 8);
-          if (D.lookup(ja[k] - r, b) < 0) {
+          memcpy(&b, &a[ia[r] + k], 8);
+          const int d = ja[ia[r] + k] - r;
+          if (k < prev_len && D.delta[prev[k]] == d && D.bits[prev[k]] == b) {
+            rc[k] = prev[k];
+            continue;
+          }
+          const int c = D.lookup(d, b);
+          if (c < 0) {
             ok = false;
             break;
           }
+          rc[k] = (unsigned char)c;
         }
+        prev     = rc;
+        prev_len = len;
       }
       if (ok) {
         tkind[t] = 1;
         tnd[t]   = (uint16_t)D.n;
-        int maxlen = 0;
-        for (int r = r0; r < r1; r++) maxlen = std::max(maxlen, ia[r + 1] - ia[r]);
+        tuni[t]  = uniform && len0 < 0xFFFF;
+        tthr[t]  = me;
+        tdoff[t] = ad.size();
+        ad.insert(ad.end(), D.delta, D.delta + D.n);
+        ab.insert(ab.end(), D.bits, D.bits + D.n);
         const int padded = (r1 - r0) * maxlen;
         if (!uniform && maxlen <= 8 && D.n <= 255 && padded <= nnz + nnz / 4 + 16) {
           tpad[t]   = (unsigned char)maxlen;
           tbytes[t] = (unsigned)pk_coded_bytes(D.n + 1, r1 - r0, padded, true);
         } else {
-          tbytes[t] = (unsigned)pk_coded_bytes(D.n, r1 - r0, nnz, uniform && len0 < 0xFFFF);
+          tbytes[t] = (unsigned)pk_coded_bytes(D.n, r1 - r0, nnz, tuni[t]);
         }
         coded++;
       } else {
@@ -133,7 +166,10 @@ int pk_build(int n, const int *ia, const int *ja, const double *a, std::vector<u
       }
     }
   }
-  if (bad) return 0;
+  if (bad) {
+    free(codes_tmp);
+    return 0;
+  }
   size_t tot = 0;
   max_tile_bytes = 0;
   for (int t = 0; t < ntiles; t++) {
@@ -141,68 +177,62 @@ int pk_build(int n, const int *ia, const int *ja, const double *a, std::vector<u
     tot += tbytes[t];
     if ((int)tbytes[t] > max_tile_bytes) max_tile_bytes = (int)tbytes[t];
   }
-  if (tot / 16 > 0xFFFFFFFFull) return 0;
+  if (tot / 16 > 0xFFFFFFFFull) {
+    free(codes_tmp);
+    return 0;
+  }
   h_off[ntiles] = (unsigned)(tot / 16);
-  blob.assign(tot + 16, 0);
-  // pass 2: fill
-#pragma omp parallel
-  {
-    TileDict D;
-#pragma omp for schedule(dynamic, 64)
-    for (int t = 0; t < ntiles; t++) {
-      const int      r0 = t * TR, r1 = std::min(r0 + TR, n), nrows = r1 - r0;
-      const int      k0 = ia[r0], k1 = ia[r1], nnz = k1 - k0;
-      unsigned char *p = blob.data() + (size_t)h_off[t] * 16;
-      PkHeader       H;
-      memset(&H, 0, sizeof H);
-      H.kind  = tkind[t];
-      H.nnz   = (uint32_t)nnz;
-      H.nrows = (uint16_t)nrows;
-      bool      uniform = true;
-      const int len0 = ia[r0 + 1] - ia[r0];
-      for (int r = r0; r < r1; r++)
-        if (ia[r + 1] - ia[r] != len0) uniform = false;
-      if (tkind[t] == 1) {
-        // the dictionary is rebuilt in first-appearance order (as in pass 1) while the codes are written in place
-        const int plen = tpad[t];                     // > 0: rows padded to this length with the skip code
-        const int nd = tnd[t] + (plen ? 1 : 0);       // the skip code owns a (0, 0.0) slot at the end of the dictionary
-        H.ndict      = (uint16_t)nd;
-        H.ulen       = plen ? (uint16_t)plen : ((uniform && len0 < 0xFFFF) ? (uint16_t)len0 : (uint16_t)0xFFFF);
-        H.pad        = plen ? (uint32_t)tnd[t] + 1u : 0u;
-        const size_t o_val = sizeof(PkHeader), o_del = o_val + up(nd, 2) * 8, o_ro = o_del + up(nd, 4) * 4;
-        const size_t o_code = o_ro + (H.ulen == 0xFFFF ? up((size_t)nrows + 1, 8) * 2 : 0);
-        unsigned char *codes = p + o_code;
-        D.reset();
+  blob.resize(tot + 16);
+#pragma omp parallel for schedule(dynamic, 64)
+  for (int t = 0; t < ntiles; t++) {
+    const int      r0 = t * TR, r1 = std::min(r0 + TR, n), nrows = r1 - r0;
+    const int      k0 = ia[r0], k1 = ia[r1], nnz = k1 - k0;
+    unsigned char *p = blob.data() + (size_t)h_off[t] * 16;
+    memset(p, 0, tbytes[t]);   // padding bytes are defined
+    PkHeader H;
+    memset(&H, 0, sizeof H);
+    H.kind  = tkind[t];
+    H.nnz   = (uint32_t)nnz;
+    H.nrows = (uint16_t)nrows;
+    if (tkind[t] == 1) {
+      const int plen = tpad[t];                     // > 0: rows padded to this length with the skip code
+      const int nd0 = tnd[t], nd = nd0 + (plen ? 1 : 0);   // the skip code owns a (0, 0.0) slot at the end of the dictionary
+      H.ndict = (uint16_t)nd;
+      H.ulen  = plen ? (uint16_t)plen : (tuni[t] ? (uint16_t)(ia[r0 + 1] - ia[r0]) : (uint16_t)0xFFFF);
+      H.pad   = plen ? (uint32_t)nd0 + 1u : 0u;
+      const size_t o_val = sizeof(PkHeader), o_del = o_val + up(nd, 2) * 8, o_ro = o_del + up(nd, 4) * 4;
+      const size_t o_code = o_ro + (H.ulen == 0xFFFF ? up((size_t)nrows + 1, 8) * 2 : 0);
+      unsigned char *codes = p + o_code;
+      memcpy(p + o_val, arena_b[tthr[t]].data() + tdoff[t], (size_t)nd0 * 8);
+      memcpy(p + o_del, arena_d[tthr[t]].data() + tdoff[t], (size_t)nd0 * 4);
+      if (plen) {
         for (int r = r0; r < r1; r++) {
-          unsigned char *rc = plen ? codes + (size_t)(r - r0) * plen : codes + (ia[r] - k0);
+          unsigned char *rc = codes + (size_t)(r - r0) * plen;
           const int      len = ia[r + 1] - ia[r];
-          for (int k = 0; k < len; k++) {
-            uint64_t b;
-            memcpy(&b, &a[ia[r] + k], 8);
-            rc[k] = (unsigned char)D.lookup(ja[ia[r] + k] - r, b);
-          }
-          for (int k = len; k < plen; k++) rc[k] = (unsigned char)tnd[t];
+          memcpy(rc, codes_tmp + ia[r], (size_t)len);
+          for (int k = len; k < plen; k++) rc[k] = (unsigned char)nd0;
         }
-        memcpy(p + o_val, D.bits, (size_t)tnd[t] * 8);
-        memcpy(p + o_del, D.delta, (size_t)tnd[t] * 4);
-        if (H.ulen == 0xFFFF) {
-          uint16_t *ro = (uint16_t *)(p + o_ro);
-          for (int r = r0; r <= r1; r++) ro[r - r0] = (uint16_t)(ia[r] - k0);
-        }
-      } else {
-        H.ndict = 0;
-        H.ulen  = 0xFFFF;
-        size_t o = sizeof(PkHeader);
-        if (nnz) memcpy(p + o, a + k0, (size_t)nnz * 8);
-        o += up(nnz, 2) * 8;
-        if (nnz) memcpy(p + o, ja + k0, (size_t)nnz * 4);
-        o += up(nnz, 4) * 4;
-        uint16_t *ro = (uint16_t *)(p + o);
+      } else if (nnz) {
+        memcpy(codes, codes_tmp + k0, (size_t)nnz);
+      }
+      if (H.ulen == 0xFFFF) {
+        uint16_t *ro = (uint16_t *)(p + o_ro);
         for (int r = r0; r <= r1; r++) ro[r - r0] = (uint16_t)(ia[r] - k0);
       }
-      memcpy(p, &H, sizeof H);
+    } else {
+      H.ndict = 0;
+      H.ulen  = 0xFFFF;
+      size_t o = sizeof(PkHeader);
+      if (nnz) memcpy(p + o, a + k0, (size_t)nnz * 8);
+      o += up(nnz, 2) * 8;
+      if (nnz) memcpy(p + o, ja + k0, (size_t)nnz * 4);
+      o += up(nnz, 4) * 4;
+      uint16_t *ro = (uint16_t *)(p + o);
+      for (int r = r0; r <= r1; r++) ro[r - r0] = (uint16_t)(ia[r] - k0);
     }
+    memcpy(p, &H, sizeof H);
   }
+  free(codes_tmp);
   ncoded = coded;
   packed = true;
   return 0;
