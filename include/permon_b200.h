@@ -48,6 +48,7 @@ typedef enum { PETSC_FALSE = 0, PETSC_TRUE = 1 } PetscBool;
 
 #define PETSC_SUCCESS 0
 #define PETSC_ERR_MEM 55
+#define PETSC_ERR_NOT_CONVERGED 82
 #define PETSC_ERR_SUP 56
 #define PETSC_ERR_ORDER 58
 #define PETSC_ERR_ARG_SIZ 60
@@ -258,6 +259,7 @@ PERMON_EXTERN PetscErrorCode QPPFApplyHalfQ(QPPF cp, Vec x, Vec y);             
 PERMON_EXTERN PetscErrorCode QPPFApplyHalfQTranspose(QPPF cp, Vec x, Vec y);         /* permonqppf.h:23, qppf.c:535 */
 PERMON_EXTERN PetscErrorCode QPPFApplyCP(QPPF cp, Vec x, Vec y);                     /* permonqppf.h:24, qppf.c:610 */
 PERMON_EXTERN PetscErrorCode QPPFApplyGtG(QPPF cp, Vec v, Vec GtGv);                 /* permonqppf.h:25, qppf.c:580 */
+PERMON_EXTERN PetscErrorCode QPPFCreateP(QPPF cp, Mat *P);                           /* permonqppf.h:32, qppf.c:685 */
 
 /* ===================================================================================================
  * QP -- problem container: include/permonqp.h:21-123, src/qp/interface/qp.c
@@ -300,6 +302,12 @@ PERMON_EXTERN PetscErrorCode QPChainViewKKT(QP qp, PetscViewer v);              
 PERMON_EXTERN PetscErrorCode QPRemoveChild(QP qp);                                   /* permonqp.h:34 */
 PERMON_EXTERN PetscErrorCode QPTEnforceEqByPenalty(QP qp, PetscReal rho_user, PetscBool rho_direct); /* permonqp.h:96, qptransform.c:329 */
 PERMON_EXTERN PetscErrorCode QPTHomogenizeEq(QP qp);                                 /* permonqp.h:97, qptransform.c:437 */
+PERMON_EXTERN PetscErrorCode QPTEnforceEqByProjector(QP qp);                        /* permonqp.h:98, qptransform.c:215 */
+/* MatOrthType / MatOrthForm: include/permonmat.h:160-171.  The B200 path orthonormalises the (at most 4) dense equality rows with
+   MAT_ORTH_GS or MAT_ORTH_CHOLESKY and always stores T*BE explicitly. */
+typedef enum { MAT_ORTH_NONE = 0, MAT_ORTH_GS, MAT_ORTH_GS_LINGEN, MAT_ORTH_CHOLESKY, MAT_ORTH_IMPLICIT, MAT_ORTH_INEXACT } MatOrthType;
+typedef enum { MAT_ORTH_FORM_IMPLICIT = 0, MAT_ORTH_FORM_EXPLICIT = 1 } MatOrthForm;
+PERMON_EXTERN PetscErrorCode QPTOrthonormalizeEq(QP qp, MatOrthType type, MatOrthForm form); /* permonqp.h:101, qptransform.c:566 */
 /* MatPenalized: permonqp.h:119-123, src/qp/utils/matpenalized.c */
 PERMON_EXTERN PetscErrorCode MatCreatePenalized(QP qp, PetscReal rho, Mat *A_inner);
 PERMON_EXTERN PetscErrorCode MatPenalizedSetPenalty(Mat Arho, PetscReal rho);

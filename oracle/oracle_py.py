@@ -29,7 +29,8 @@ _ip = C.POINTER(C.c_int)
 class Op(C.Structure):
     _fields_ = [("kind", C.c_int), ("n", C.c_int), ("ia", _ip), ("ja", _ip), ("a", _dp), ("d", C.c_int),
                 ("ia2", _ip), ("ja2", _ip), ("a2", _dp), ("twork", _dp), ("m", C.c_int), ("B", _dp),
-                ("rho", C.c_double), ("bwork", _dp)]
+                ("rho", C.c_double), ("bwork", _dp),
+                ("pmode", C.c_int), ("pm", C.c_int), ("PG", _dp), ("porth", C.c_int), ("pw1", _dp), ("pw2", _dp)]
 
 
 class Box(C.Structure):
@@ -134,6 +135,16 @@ class Operator:
             self.c.d = self.d
             self.c.ia2, self.c.ja2, self.c.a2, self.c.twork = _i(self.ia2), _i(self.ja2), _d(self.a2), _d(self.tw)
         self.c.m = 0
+
+    def set_projector(self, G, mode=2):
+        """A -> P A P (mode 2) or P A (mode 1), P = I - G'(G G')^-1 G  (QPTEnforceEqByProjector)"""
+        self.PG = f64(G).reshape(-1, self.n)
+        self.pw = np.zeros((2, self.n))
+        self.c.pmode = int(mode)
+        self.c.pm = self.PG.shape[0]
+        self.c.PG = _d(self.PG)
+        self.c.porth = int(lib().orc_rows_orthonormal(C.c_int(self.n), C.c_int(self.c.pm), _d(self.PG)))
+        self.c.pw1, self.c.pw2 = _d(self.pw[0]), _d(self.pw[1])
 
     def set_penalty(self, B, rho):
         self.B = f64(B).reshape(-1, self.n)
@@ -270,6 +281,40 @@ def pcpg_solve(op: Operator, b, G, c=None, x0=None, opts: LinOpts | None = None)
     lib().orc_pcpg_solve(C.byref(op.c), _d(b), C.c_int(Gm.shape[0]), _d(Gm), _d(cc) if cc is not None else None, _d(x), C.byref(opts or lin_opts()),
                          C.byref(res))
     return x, {f[0]: getattr(res, f[0]) for f in LinResult._fields_}
+
+
+def orth_rows(B, c=None, kind="gs"):
+    """QPTOrthonormalizeEq's MatOrthRows, explicit form: -> (T B, T c, T)"""
+    Bm = f64(B)
+    m, n = Bm.shape
+    TB, T = np.empty((m, n)), np.empty((m, m))
+    cc = None if c is None else f64(c)
+    Tc = None if c is None else np.empty(m)
+    rc = lib().orc_orth_rows(C.c_int(n), C.c_int(m), _d(Bm), _d(cc) if cc is not None else None, C.c_int({"gs": 1, "cholesky": 3}[kind]), _d(TB),
+                             _d(Tc) if Tc is not None else None, _d(T))
+    if rc:
+        raise RuntimeError(f"orc_orth_rows failed ({rc})")
+    return TB, Tc, T
+
+
+def apply_P(G, v):
+    Gm = f64(G)
+    m, n = Gm.shape
+    out = np.empty(n)
+    lib().orc_apply_P(C.c_int(n), C.c_int(m), _d(Gm), _d(f64(v)), _d(out))
+    return out
+
+
+def homogenize(op: Operator, b, box, G, c):
+    """QPTHomogenizeEq: -> (xtilde, b_h, lb_h, ub_h)"""
+    Gm = f64(G)
+    m, n = Gm.shape
+    xt, bh = np.empty(n), np.empty(n)
+    lbh = None if box is None or box.lb is None else np.empty(len(box.lb))
+    ubh = None if box is None or box.ub is None else np.empty(len(box.ub))
+    lib().orc_homogenize(C.byref(op.c), _d(f64(b)), C.byref(box.c) if box is not None else None, C.c_int(m), _d(Gm), _d(f64(c)), _d(xt), _d(bh),
+                         _d(lbh) if lbh is not None else None, _d(ubh) if ubh is not None else None)
+    return xt, bh, lbh, ubh
 
 
 def max_eigenvalue(op: Operator, tol=DECIDE, maxits=-1):

@@ -182,17 +182,43 @@ static void gtg_apply(int n, int m, const double *B, const double *x, double *y,
   }
 }
 
+static int  ggt_solve(int n, int m, const double *B, const double *r, double *y);
+static void pf_apply_P(int n, int m, const double *G, int orth, const double *v, double *Pv, double *gl, double *y);
+
+/* the Hessian without the penalty term: A, or the MatProd P*A*P / P*A of QPTEnforceEqByProjector (applied right to left,
+ * matprod.c:42-48, each P through QPPFApplyP)                                                                            */
+static void op_apply_hessian(const orc_op *op, const double *x, double *y)
+{
+  if (!op->pmode) {
+    op_apply_plain(op, x, y);
+    return;
+  }
+  double gl[8], yy[8];
+  const double *in = x;
+  if (op->pmode == 2) {
+    pf_apply_P(op->n, op->pm, op->PG, op->porth, x, op->pw1, gl, yy);
+    in = op->pw1;
+  }
+  op_apply_plain(op, in, op->pw2);
+  pf_apply_P(op->n, op->pm, op->PG, op->porth, op->pw2, y, gl, yy);
+}
+
 /* MatMult for the (possibly penalised) Hessian.
  * MatMult_Penalized (src/qp/utils/matpenalized.c:12-22): y = BtB x; y *= rho; y += A x.         */
 void orc_op_apply(const orc_op *op, const double *x, double *y)
 {
   if (op->m <= 0) {
-    op_apply_plain(op, x, y);
+    op_apply_hessian(op, x, y);
     return;
   }
   gtg_apply(op->n, op->m, op->B, x, y, op->bwork);
   v_scale(op->n, y, op->rho);
-  if (op->kind == 0) {
+  if (op->pmode) {
+    double *w = (double *)malloc(sizeof(double) * (size_t)op->n);
+    op_apply_hessian(op, x, w);
+    v_axpy(op->n, y, 1.0, w);
+    free(w);
+  } else if (op->kind == 0) {
     spmv_add(op->n, op->ia, op->ja, op->a, x, y);
   } else {
     /* composite operator: MatMultAdd = MatMult into a work vector + add */
@@ -1270,4 +1296,106 @@ int orc_pcpg_solve(const orc_op *op, const double *b_user, int m, const double *
   res->its = it; res->reason = reason; res->rnorm = rnorm; res->norm_rhs = norm_rhs; res->seconds = now_seconds() - t0;
   free(p); free(r); free(w); free(Ap); free(gl); free(yy);
   return 0;
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* QPTOrthonormalizeEq / QPTHomogenizeEq / projector pieces                 */
+/* ------------------------------------------------------------------------------------------ */
+int orc_rows_orthonormal(int n, int m, const double *B) { return rows_orthonormal(n, m, B); }
+
+void orc_apply_P(int n, int m, const double *G, const double *v, double *Pv)
+{
+  double gl[8], yy[8];
+  pf_apply_P(n, m, G, rows_orthonormal(n, m, G), v, Pv, gl, yy);
+}
+
+/* MatOrthRows (src/mat/interface/permonmatorth.c:494-520) = MatOrthColumns on the transpose; explicit forms.
+ * type 1: MatOrthColumns_GS_Default (:196-234), iterated classical Gram-Schmidt with re-orthogonalisation while the norm drops
+ *         below alpha = 0.5 of its previous value; S accumulates the same operations on the identity, T = S^T.
+ * type 3: MatOrthColumns_Cholesky_Default (:33-150): G G^T = L L^T, TB = L^{-1} G (forward solve of every column), T = L^{-1}.
+ * T is m x m row-major; Tc = T c (qptransform.c:610-613).                                                                   */
+int orc_orth_rows(int n, int m, const double *B, const double *c, int type, double *TB, double *Tc, double *T)
+{
+  memcpy(TB, B, sizeof(double) * (size_t)m * n);
+  for (int i = 0; i < m; i++)
+    for (int j = 0; j < m; j++) T[i * m + j] = (i == j) ? 1.0 : 0.0;
+  if (type == 1) {
+    double dots[8];
+    for (int i = 0; i < m; i++) {
+      double *q = TB + (size_t)i * n;
+      double  norm = orc_norm2(n, q), norm_last;
+      do {
+        norm_last = norm;
+        for (int j = 0; j < i; j++) dots[j] = -orc_dot(n, q, TB + (size_t)j * n); /* VecMDot, negated :220-221 */
+        for (int j = 0; j < i; j++) v_axpy(n, q, dots[j], TB + (size_t)j * n);    /* VecMAXPY :222 */
+        for (int j = 0; j < i; j++)
+          for (int k = 0; k < m; k++) T[i * m + k] += dots[j] * T[j * m + k];    /* the same on s[i] :223 */
+        norm = orc_norm2(n, q);
+        if (norm < 1e2 * 2.220446049250313e-16) return 1;                          /* :227 */
+      } while (norm <= 0.5 * norm_last);
+      v_scale(n, q, 1.0 / norm);
+      for (int k = 0; k < m; k++) T[i * m + k] *= 1.0 / norm;
+    }
+  } else if (type == 3) {
+    double L[64];
+    for (int i = 0; i < m; i++)
+      for (int j = 0; j <= i; j++) L[i * m + j] = orc_dot(n, B + (size_t)i * n, B + (size_t)j * n);
+    for (int j = 0; j < m; j++) {
+      double d = L[j * m + j];
+      for (int k = 0; k < j; k++) d -= L[j * m + k] * L[j * m + k];
+      if (d <= 0.0) return 1;
+      d = sqrt(d);
+      L[j * m + j] = d;
+      for (int i = j + 1; i < m; i++) {
+        double v = L[i * m + j];
+        for (int k = 0; k < j; k++) v -= L[i * m + k] * L[j * m + k];
+        L[i * m + j] = v / d;
+      }
+    }
+    /* forward solve L Y = G (column by column of G) and L T = I */
+    for (int col = 0; col < n; col++)
+      for (int i = 0; i < m; i++) {
+        double v = B[(size_t)i * n + col];
+        for (int k = 0; k < i; k++) v -= L[i * m + k] * TB[(size_t)k * n + col];
+        TB[(size_t)i * n + col] = v / L[i * m + i];
+      }
+    for (int col = 0; col < m; col++)
+      for (int i = 0; i < m; i++) {
+        double v = (i == col) ? 1.0 : 0.0;
+        for (int k = 0; k < i; k++) v -= L[i * m + k] * T[k * m + col];
+        T[i * m + col] = v / L[i * m + i];
+      }
+  } else {
+    return 2;
+  }
+  if (c && Tc)
+    for (int i = 0; i < m; i++) {
+      double s = 0.0;
+      for (int k = 0; k < m; k++) s += T[i * m + k] * c[k];
+      Tc[i] = s;
+    }
+  return 0;
+}
+
+void orc_homogenize(const orc_op *op, const double *b, const orc_box *bx, int m, const double *G, const double *c, double *xtilde, double *b_h,
+                    double *lb_h, double *ub_h)
+{
+  const int n = op->n;
+  double    y[8];
+  if (!rows_orthonormal(n, m, G)) ggt_solve(n, m, G, c, y); /* QPPFApplyHalfQTranspose qppf.c:535-568 */
+  else memcpy(y, c, sizeof(double) * (size_t)m);
+  for (int k = 0; k < n; k++) {
+    double s = 0.0;
+    for (int j = 0; j < m; j++) s += G[(size_t)j * n + k] * y[j];
+    xtilde[k] = s;
+  }
+  orc_op_apply(op, xtilde, b_h); /* qptransform.c:468-469 */
+  v_aypx(n, b_h, -1.0, b);
+  if (bx) {
+    const int ns = NSUB(bx);
+    if (bx->lb && lb_h)
+      for (int k = 0; k < ns; k++) lb_h[k] = bx->lb[k] - xtilde[IDX(bx, k)]; /* :498-501 */
+    if (bx->ub && ub_h)
+      for (int k = 0; k < ns; k++) ub_h[k] = bx->ub[k] - xtilde[IDX(bx, k)]; /* :503-506 */
+  }
 }

@@ -77,6 +77,13 @@ typedef struct {
   const double *B;     /* m x n */
   double        rho;
   double       *bwork; /* length m */
+  /* projected operator (QPTEnforceEqByProjector, qptransform.c:283-296): y = P A P x (pmode 2) or y = P A x (pmode 1, only
+   * equality constraints present) with P = I - G^T (G G^T)^{-1} G; 0 = no projector.  The plain / product part above is "A". */
+  int           pmode;
+  int           pm;     /* rows of G */
+  const double *PG;     /* pm x n */
+  int           porth;  /* G has orthonormal rows (QPPFApplyQ then skips the coarse solve, qppf.c:454-502) */
+  double       *pw1, *pw2; /* two work vectors of length n */
 } orc_op;
 
 /* Box constraint (QPC_Box, src/qpc/impls/box/qpcboximpl.h:5-10) optionally
@@ -157,6 +164,14 @@ typedef struct {
   double rnorm, norm_rhs;
   double seconds;
 } orc_lin_result;
+/* "next" row rank 2: pieces of QPTOrthonormalizeEq / QPTHomogenizeEq / QPTEnforceEqByProjector.
+ * orth types as MatOrthType (permonmat.h:160-167): 1 = MAT_ORTH_GS, 3 = MAT_ORTH_CHOLESKY (explicit forms).            */
+int  orc_orth_rows(int n, int m, const double *B, const double *c, int type, double *TB, double *Tc, double *T);
+int  orc_rows_orthonormal(int n, int m, const double *B);
+void orc_apply_P(int n, int m, const double *G, const double *v, double *Pv);
+/* QPTHomogenizeEq (qptransform.c:437-527): xtilde = G^T (G G^T)^{-1} c, b_h = b - A xtilde, bounds shifted by xtilde */
+void orc_homogenize(const orc_op *op, const double *b, const orc_box *bx, int m, const double *G, const double *c, double *xtilde, double *b_h,
+                    double *lb_h, double *ub_h);
 void orc_default_lin_opts(orc_lin_opts *o);
 int  orc_cg_solve(const orc_op *op, const double *b, double *x, const orc_lin_opts *opts, orc_lin_result *res);
 /* min 1/2 x'Ax - b'x  s.t.  G x = c  (G dense row-major m x n, c may be NULL = 0) */

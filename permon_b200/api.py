@@ -453,6 +453,27 @@ def QPSetEq(qp, B, c):
     call("QPSetEq", qp, _h(B), _h(c))
 
 
+MAT_ORTH = dict(none=0, gs=1, gslingen=2, cholesky=3, implicit=4, inexact=5)
+
+
+def QPTOrthonormalizeEq(qp, kind="gs", explicit=True):
+    call("QPTOrthonormalizeEq", qp, C.c_int(MAT_ORTH[kind]), C.c_int(1 if explicit else 0))
+
+
+def QPTEnforceEqByProjector(qp):
+    call("QPTEnforceEqByProjector", qp)
+
+
+def QPTHomogenizeEq(qp):
+    call("QPTHomogenizeEq", qp)
+
+
+def QPChainGetLast(qp):
+    c = C.c_void_p()
+    call("QPChainGetLast", qp, C.byref(c))
+    return c
+
+
 def QPSetOptionsPrefix(qp, prefix):
     call("QPSetOptionsPrefix", qp, prefix.encode())
 

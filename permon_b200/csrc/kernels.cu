@@ -1999,6 +1999,31 @@ int k_qpc_project(int n, const double *x, BoxDev bx, double *Px)
 {
   return launch_ew(n, [=] __device__(int i) { Px[i] = box_project(x[i], load_box(bx, i)); }, KF_QPC, 32.0 * n);
 }
+// MatOrthColumns_Cholesky_Default (permonmatorth.c:97-110): every column of G is forward-solved with the Cholesky factor of G G^T
+struct SmallLower {
+  double v[PB_MAXEQ * PB_MAXEQ];
+};
+int k_rows_forward_solve(int n, int m, const double *L, const double *G, double *TB)
+{
+  SmallLower Ls;
+  for (int i = 0; i < m * m; i++) Ls.v[i] = L[i];
+  return launch_ew(
+    n,
+    [=] __device__(int col) {
+      double y[PB_MAXEQ];
+#pragma unroll
+      for (int i = 0; i < PB_MAXEQ; i++) {
+        if (i < m) {
+          double v = G[(size_t)i * n + col];
+          for (int k = 0; k < i; k++) v -= Ls.v[i * m + k] * y[k];
+          y[i]                   = v / Ls.v[i * m + i];
+          TB[(size_t)i * n + col] = y[i];
+        }
+      }
+    },
+    KF_VEC, 16.0 * n * m);
+}
+
 int k_qpc_grads(int n, const double *x, const double *g, BoxDev bx, double *gf, double *gc)
 {
   return launch_ew(n, [=] __device__(int i) {

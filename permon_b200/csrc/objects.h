@@ -93,7 +93,7 @@ struct HaloPlan {
   } *host = nullptr;
 };
 
-enum MatKind { MK_AIJ = 0, MK_ONEROW, MK_PROD, MK_PENALIZED };
+enum MatKind { MK_AIJ = 0, MK_ONEROW, MK_PROD, MK_PENALIZED, MK_PROJ /* P = I - G'(GG')^-1 G of a QPPF */, MK_DENSEROWS /* m x n dense rows on the device */ };
 
 struct _p_Mat : PObj {
   MatKind  kind = MK_AIJ;
@@ -107,7 +107,9 @@ struct _p_Mat : PObj {
   // PROD: y = M1 (M2 x)
   Mat M1 = nullptr, M2 = nullptr;
   Vec twork = nullptr;
-  // PENALIZED: y = A x + rho G^T G x   (matpenalized.c:4-8)
+  // DENSEROWS: row-major m x n device array (orthonormalised equality rows)
+  double *rows_d = nullptr;
+  // PENALIZED: y = A x + rho G^T G x   (matpenalized.c:4-8); PROJ uses pf only
   Mat    A = nullptr;
   QPPF   pf = nullptr;
   double rho = 0.0;
@@ -149,7 +151,8 @@ struct _p_QP : PObj {   // qpimpl.h:6-57
   QP            parent = nullptr, child = nullptr;
   QPPostSolveFn postSolve = nullptr;
   Vec           postSolveCtx = nullptr;   // xtilde of QPTHomogenizeEq
-  int           transform = 0;            // 0 none, 1 penalty, 2 homogenize
+  std::vector<double> postT;              // T (m x m) of QPTOrthonormalizeEq
+  int           transform = 0;            // 0 none, 1 penalty, 2 homogenize, 3 projector, 4 orthonormalize
   std::string   transform_name = "";
   int           id = 0;
   bool          setupcalled = false, solved = false;
@@ -250,6 +253,7 @@ int  vec_norm2(Vec x, double *val);
 int  vec_mdot2(Vec x, Vec y0, Vec y1, double *v0, double *v1);
 int  mat_mult(Mat A, Vec x, Vec y);
 int  mat_mult_dev(Mat A, const double *x, double *y);        // raw device pointers (local lengths)
+int  qppf_apply_P_dev(QPPF cp, const double *x, double *y);   // y = x - G^T (G G^T)^{-1} G x on raw device pointers
 int  mat_ensure_device(Mat A);                               // upload a lazily kept host split (multi-rank AIJ)
 int  mat_halo_begin(Mat A, const double *x);                 // pack + post send/recv on the comm stream
 int  mat_halo_end(Mat A);                                    // make the compute stream wait for the ghosts

@@ -374,6 +374,9 @@ PetscErrorCode QPPFSetUp(QPPF cp)
     PB_CHK(vec_dev_read(G->row, &d));
     cp->Bd       = const_cast<double *>(d);
     cp->Bd_owned = false;
+  } else if (G->kind == MK_DENSEROWS) {
+    cp->Bd       = G->rows_d;
+    cp->Bd_owned = false;
   } else if (G->kind == MK_AIJ) {
     if (G->comm->size > 1) return err(PETSC_ERR_SUP, "row-partitioned AIJ equality matrices are not supported; use MatCreateOneRow");
     const int        m = G->m, n = G->n;
@@ -531,6 +534,38 @@ PetscErrorCode QPPFApplyP(QPPF cp, Vec v, Vec Pv)
   PB_CHK(QPPFApplyQ(cp, v, Pv));
   return VecAYPX(Pv, -1.0, v);
 }
+namespace pb {
+int qppf_apply_P_dev(QPPF cp, const double *x, double *y)
+{   // QPPFMatMult_P -> QPPFApplyP (qppf.c:560-575): y = x - G^T (G G^T)^{-1} G x
+  PB_CHK(QPPFSetUp(cp));
+  double   t[PB_MAXEQ], s[PB_MAXEQ];
+  Reducer &R = reducer(cp->comm);
+  PB_CHK(k_dense_rows_mult(cp->n, cp->m, cp->Bd, x, R.rb));
+  PB_CHK(R.gather());
+  PB_CHK(R.fetch());
+  for (int j = 0; j < cp->m; j++) t[j] = R.sum(j);
+  if (!cp->orth) PB_CHK(qppf_solve(cp, t, s));
+  else memcpy(s, t, sizeof s);
+  PB_CUDA(cudaMemcpyAsync(R.d_all, s, sizeof(double) * cp->m, cudaMemcpyHostToDevice, ctx().stream));
+  PB_CHK(k_dense_rows_multT_add(cp->n, cp->m, cp->Bd, R.d_all, 1.0, y, 0));   // y = Q x
+  return k_aypx(cp->n, y, -1.0, x);                                            // VecAYPX(Pv, -1, v)
+}
+}   // namespace pb
+
+PetscErrorCode QPPFCreateP(QPPF cp, Mat *newP)
+{   // qppf.c:685-700: P = I - G' inv(G G') G in implicit form
+  if (!cp->G) return err(PETSC_ERR_ORDER, "QPPFSetG must be called first");
+  _p_Mat *P = new _p_Mat;
+  P->comm   = cp->comm;
+  P->kind   = MK_PROJ;
+  P->pf     = cp;
+  cp->refct++;
+  P->m = P->n = cp->G->n;
+  P->M = P->N = cp->G->N;
+  *newP       = P;
+  return 0;
+}
+
 PetscErrorCode QPPFApplyHalfQ(QPPF cp, Vec x, Vec y)
 {   // qppf.c:507-530: y = (G G^T)^{-1} G x
   PB_CHK(QPPFSetUp(cp));
@@ -1054,6 +1089,183 @@ static PetscErrorCode post_penalty(QP, QP) { return 0; }   // qptransform.c:320-
 static PetscErrorCode post_homogenize(QP child, QP parent)
 {   // qptransform.c:414-422: x_parent = x_child + xtilde
   return VecWAXPY(parent->x, 1.0, child->x, child->postSolveCtx);
+}
+
+static PetscErrorCode post_projector(QP child, QP parent)
+{   // QPTEnforceEqByProjectorPostSolve_Private qptransform.c:57-93
+  PB_CHK(post_default(child, parent));
+  bool skip_lambda_E = true, skip_Bt_lambda = true;
+  if (child->BE) {   // -qpt_project_inherit_eq_multipliers defaults to true
+    skip_lambda_E  = !child->lambda_E || child->lambda_E->invalidated;
+    skip_Bt_lambda = !child->Bt_lambda || child->Bt_lambda->invalidated;
+  }
+  if (skip_lambda_E && skip_Bt_lambda) return 0;
+  Vec r = parent->xwork;
+  PB_CHK(mat_mult(parent->A, parent->x, r));
+  PB_CHK(VecAYPX(r, -1.0, parent->b));   // r = b - A x
+  if (!skip_lambda_E) {                    // lambda_E1 = lambda_E2 + (B B')\B (b - A x)
+    PB_CHK(QPPFApplyHalfQ(parent->pf, r, parent->lambda_E));
+    PB_CHK(VecAXPY(parent->lambda_E, 1.0, child->lambda_E));
+  }
+  if (!skip_Bt_lambda) {                   // (B' lambda)_1 = (B' lambda)_2 + B' (B B')\B (b - A x)
+    PB_CHK(QPPFApplyQ(parent->pf, r, parent->Bt_lambda));
+    PB_CHK(VecAXPY(parent->Bt_lambda, 1.0, child->Bt_lambda));
+  }
+  return 0;
+}
+
+// QPTEnforceEqByProjector qptransform.c:215-316: child = (P A P, P b, box, eq kept) or, with equality constraints only,
+// (P A, P b, unconstrained); P = I - B'(B B')^{-1} B through the QPPF.
+PetscErrorCode QPTEnforceEqByProjector(QP qp)
+{
+  PB_CHK(QPChainGetLast(qp, &qp));
+  if (!qp->BE) {
+    pb::unref(qp->cE);
+    return 0;
+  }
+  if (qp->cE) {   // non-zero right-hand side: homogenise first (:236-240)
+    PB_CHK(QPTHomogenizeEq(qp));
+    PB_CHK(QPChainGetLast(qp, &qp));
+  }
+  QP child;
+  PB_CHK(qp_chain_add(qp, &child, 3, "QPTEnforceEqByProjector", post_projector));
+  child->prefix += "proj_";
+  const bool eqonly = !qp->qpc;
+  QPPF       pf;
+  PB_CHK(QPGetQPPF(qp, &pf));
+  if (eqonly) {
+    PB_CHK(QPSetEq(child, NULL, NULL));
+  } else {
+    PB_CHK(qp_set_qppf(child, pf));
+    PB_CHK(QPSetEq(child, qp->BE, qp->cE));
+  }
+  if (qp->qpc) PB_CHK(QPSetBox(child, qp->qpc->is, qp->qpc->lb, qp->qpc->ub));
+  Mat P, newA, arr[3];
+  PB_CHK(QPPFCreateP(pf, &P));
+  if (eqonly) {   // newA = P*A
+    arr[0] = qp->A;
+    arr[1] = P;
+    PB_CHK(MatCreateProd(qp->comm, 2, arr, &newA));
+  } else {        // newA = P*A*P
+    arr[0] = P;
+    arr[1] = qp->A;
+    arr[2] = P;
+    PB_CHK(MatCreateProd(qp->comm, 3, arr, &newA));
+  }
+  PB_CHK(QPSetOperator(child, newA));
+  PB_CHK(MatDestroy(&newA));
+  Vec newb;
+  PB_CHK(VecDuplicate(qp->b, &newb));
+  PB_CHK(mat_mult(P, qp->b, newb));   // newb = P*b
+  PB_CHK(QPSetRhs(child, newb));
+  PB_CHK(VecDestroy(&newb));
+  PB_CHK(MatDestroy(&P));
+  return 0;
+}
+
+static PetscErrorCode post_orthonormalize(QP, QP) { return 0; }   // QPTPostSolve_QPTOrthonormalizeEq :528-550: both branches are disabled upstream
+
+// QPTOrthonormalizeEq qptransform.c:566-636 with MatOrthRows (permonmatorth.c:494-520) for the small dense G of this path:
+// MAT_ORTH_GS = MatOrthColumns_GS_Default (:196-234), MAT_ORTH_CHOLESKY = MatOrthColumns_Cholesky_Default (:33-150).
+// The orthonormalised rows are always formed explicitly (m <= 4 rows): `form` only selects how the reference stores T*BE.
+PetscErrorCode QPTOrthonormalizeEq(QP qp, MatOrthType type, MatOrthForm form)
+{
+  (void)form;
+  PB_CHK(QPChainGetLast(qp, &qp));
+  if (!qp->BE) return 0;
+  if (type == MAT_ORTH_NONE) return 0;
+  if (type != MAT_ORTH_GS && type != MAT_ORTH_CHOLESKY) return err(PETSC_ERR_SUP, "QPTOrthonormalizeEq: the B200 path provides MAT_ORTH_GS and MAT_ORTH_CHOLESKY");
+  if (qp->comm->size > 1) return err(PETSC_ERR_SUP, "QPTOrthonormalizeEq is single-GPU in this round");
+  QPPF pf;
+  PB_CHK(QPGetQPPF(qp, &pf));
+  PB_CHK(QPPFSetUp(pf));
+  const int m = pf->m, n = pf->n;
+  QP        child;
+  PB_CHK(qp_chain_add(qp, &child, 4, "QPTOrthonormalizeEq", post_orthonormalize));
+  // QP_DUPLICATE_COPY_POINTERS: the child shares A, b, x, the box and the multipliers' layout with its parent
+  PB_CHK(QPSetOperator(child, qp->A));
+  PB_CHK(QPSetRhs(child, qp->b));
+  if (qp->x) PB_CHK(QPSetInitialVector(child, qp->x));
+  if (qp->qpc) PB_CHK(QPSetQPC(child, qp->qpc));
+  // TBE
+  _p_Mat *TB = new _p_Mat;
+  TB->comm   = qp->comm;
+  TB->kind   = MK_DENSEROWS;
+  TB->m = TB->M = m;
+  TB->n      = n;
+  TB->N      = qp->BE->N;
+  PB_CUDA(cudaMalloc(&TB->rows_d, sizeof(double) * (size_t)m * std::max(n, 1)));
+  std::vector<double> T((size_t)m * m, 0.0);
+  for (int i = 0; i < m; i++) T[i * m + i] = 1.0;
+  if (type == MAT_ORTH_CHOLESKY) {
+    PB_CHK(k_rows_forward_solve(n, m, pf->L.data(), pf->Bd, TB->rows_d));
+    // T = L^{-1}: forward solve of the identity, column by column (permonmatorth.c:111-117)
+    const double *L = pf->L.data();
+    for (int col = 0; col < m; col++)
+      for (int i = 0; i < m; i++) {
+        double v = (i == col) ? 1.0 : 0.0;
+        for (int k = 0; k < i; k++) v -= L[i * m + k] * T[k * m + col];
+        T[i * m + col] = v / L[i * m + i];
+      }
+  } else {
+    PB_CHK(k_copy(m * n, pf->Bd, TB->rows_d));
+    Reducer &R = reducer(qp->comm);
+    auto     dot = [&](const double *x, const double *y, double *val) -> int {
+      PB_CHK(k_dot(n, x, y, R.rb));
+      PB_CHK(R.gather());
+      PB_CHK(R.fetch());
+      *val = R.sum(0);
+      return 0;
+    };
+    for (int i = 0; i < m; i++) {
+      double *q = TB->rows_d + (size_t)i * n;
+      double  d, norm, norm_last, dots[PB_MAXEQ];
+      PB_CHK(dot(q, q, &d));
+      norm = sqrt(d);
+      do {
+        norm_last = norm;
+        for (int j = 0; j < i; j++) {
+          PB_CHK(dot(q, TB->rows_d + (size_t)j * n, &dots[j]));
+          dots[j] = -dots[j];
+        }
+        for (int j = 0; j < i; j++) PB_CHK(k_axpy(n, q, dots[j], TB->rows_d + (size_t)j * n));
+        for (int j = 0; j < i; j++)
+          for (int k = 0; k < m; k++) T[i * m + k] += dots[j] * T[j * m + k];
+        PB_CHK(dot(q, q, &d));
+        norm = sqrt(d);
+        if (norm < 1e2 * PETSC_MACHINE_EPSILON) {
+          {
+            Mat tbm = TB;
+            MatDestroy(&tbm);
+          }
+          return err(PETSC_ERR_NOT_CONVERGED, "MatOrthColumns has not converged due to zero norm of the current column %d (i.e. columns 0 - %d are linearly dependent)", i, i);
+        }
+      } while (norm <= 0.5 * norm_last);
+      PB_CHK(k_scale(n, q, 1.0 / norm));
+      for (int k = 0; k < m; k++) T[i * m + k] *= 1.0 / norm;
+    }
+  }
+  Vec TcE = nullptr;
+  if (qp->cE) {   // TcE = T*cE (:610-613)
+    double c[PB_MAXEQ], tc[PB_MAXEQ];
+    PB_CHK(mvec_get(qp->cE, m, c));
+    for (int i = 0; i < m; i++) {
+      double s2 = 0.0;
+      for (int k = 0; k < m; k++) s2 += T[i * m + k] * c[k];
+      tc[i] = s2;
+    }
+    PB_CHK(VecDuplicate(qp->cE, &TcE));
+    PB_CHK(mvec_put(TcE, m, tc));
+  }
+  PB_CHK(qp_set_qppf(child, nullptr));
+  PB_CHK(QPSetEq(child, TB, TcE));   // QPPF re-created in QPSetEq
+  {
+    Mat tbm = TB;
+    PB_CHK(MatDestroy(&tbm));
+  }
+  if (TcE) PB_CHK(VecDestroy(&TcE));
+  child->postT = T;
+  return 0;
 }
 
 PetscErrorCode MatCreatePenalized(QP qp, PetscReal rho, Mat *Arho_new)

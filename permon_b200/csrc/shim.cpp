@@ -886,6 +886,7 @@ _p_Mat::~_p_Mat()
     cudaFree((void *)Ad.pk);
     cudaFree((void *)Ad.pk_off);
   }
+  if (kind == MK_DENSEROWS) cudaFree(rows_d);
   if (kind == MK_AIJ) {
     cudaFree((void *)Ao.ia);
     cudaFree((void *)Ao.ja);
@@ -1409,16 +1410,26 @@ PetscErrorCode MatCreateOneRow(Vec a, Mat *A_new)
 
 // MatCreateProd: src/mat/impls/composite/matprod.c:42-48 -- product mats[nmat-1]*...*mats[0]
 PetscErrorCode MatCreateProd(MPI_Comm comm, PetscInt nmat, const Mat *mats, Mat *mat)
-{
+{   // src/mat/impls/prod/matprod.c: the product mats[nmat-1] * ... * mats[0], applied right to left
+  if (nmat < 1) return err(PETSC_ERR_ARG_OUTOFRANGE, "MatCreateProd: no factors");
   if (nmat == 1) {
     *mat = mats[0];
     pb::ref(mats[0]);
     return 0;
   }
-  if (nmat != 2) return err(PETSC_ERR_SUP, "MatCreateProd: at most two factors");
-  if (comm->size > 1) return err(PETSC_ERR_SUP, "product operators are single-GPU in this round");
+  if (nmat > 2) {   // (mats[nmat-1] * ... * mats[1]) * mats[0] by nesting two-factor products
+    Mat head, pair[2];
+    PB_CHK(MatCreateProd(comm, nmat - 1, mats + 1, &head));
+    pair[0]  = mats[0];
+    pair[1]  = head;
+    int ierr = MatCreateProd(comm, 2, pair, mat);
+    MatDestroy(&head);
+    return ierr;
+  }
   Mat M2 = mats[0], M1 = mats[1];
-  if (M1->kind != MK_AIJ || M2->kind != MK_AIJ) return err(PETSC_ERR_SUP, "MatCreateProd: AIJ factors only");
+  for (Mat F : {M1, M2})
+    if (F->kind != MK_AIJ && F->kind != MK_PROJ && F->kind != MK_PROD && F->kind != MK_PENALIZED) return err(PETSC_ERR_SUP, "MatCreateProd: unsupported factor kind");
+  if (comm->size > 1) return err(PETSC_ERR_SUP, "product operators are single-GPU in this round");
   if (M1->n != M2->m) return err(PETSC_ERR_ARG_SIZ, "MatCreateProd: inner dimensions differ (%d vs %d)", (int)M1->n, (int)M2->m);
   _p_Mat *A = new _p_Mat;
   A->comm = comm;
@@ -1517,11 +1528,14 @@ int mat_mult_dev(Mat A, const double *x, double *y)
     PB_CHK(mat_mult_dev(A->M2, x, t));
     return mat_mult_dev(A->M1, t, y);
   }
+  case MK_PROJ: return qppf_apply_P_dev(A->pf, x, y);   // QPPFMatMult_P
   case MK_PENALIZED: {
-    // MatMult_Penalized (src/qp/utils/matpenalized.c:12-22): y = BtB x; y *= rho; y += A x
+    // MatMult_Penalized (src/qp/utils/matpenalized.c:12-22): y = BtB x; y *= rho; y += A x.  A x goes first here: a projected
+    // Hessian (MK_PROD of MK_PROJ) uses the reducer's device scratch for its own coefficients
     const double *Bd;
     int           m;
     PB_CHK(qppf_dense_rows(A->pf, &Bd, &m));
+    PB_CHK(mat_mult_dev(A->A, x, y));
     Reducer &R = reducer(A->comm);
     PB_CHK(k_dense_rows_mult(A->n, m, Bd, x, R.rb));
     PB_CHK(R.gather());
@@ -1531,7 +1545,6 @@ int mat_mult_dev(Mat A, const double *x, double *y)
     for (int j = 0; j < m; j++) t[j] = R.sum(j);
     double *dt = R.d_all;   // reuse as device scratch for the m coefficients
     PB_CUDA(cudaMemcpyAsync(dt, t, sizeof(double) * m, cudaMemcpyHostToDevice, ctx().stream));
-    PB_CHK(mat_mult_dev(A->A, x, y));
     return k_dense_rows_multT_add(A->n, m, Bd, dt, A->rho, y, 1);
   }
   default: return err(PETSC_ERR_SUP, "MatMult: unsupported matrix kind for device vectors");
