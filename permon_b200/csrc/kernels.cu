@@ -1146,8 +1146,9 @@ struct AccRed {
 };
 
 // K_A epilogue: Ap_r = (A p)_r ; p.Ap ; g.p ; B p ; max feasible step (QPCFeas)
-// LBONLY: lower bound present, no upper bound, no equality rows (the obstacle problems): the staged path sheds every run-time flag
-template <bool LBONLY>
+// MODE 1: lower bound only, no equality rows (the obstacle problems); MODE 2: lower and upper bound arrays, no equality rows
+// (two-sided boxes, C5); MODE 0: anything.  In modes 1 and 2 the staged path sheds every run-time flag.
+template <int MODE>
 struct EpiAT {
   const double        *p, *g, *x;
   double              *Ap;
@@ -1212,12 +1213,12 @@ struct EpiAT {
     a.v[RA_PAP] += pr * ax;
     a.v[RA_GP] += lds_f64(va + TR * 8) * pr;
     const double xr = lds_f64(va + 2 * TR * 8);
-    if constexpr (LBONLY) {
+    if constexpr (MODE != 0) {
       BoxVal b;
       b.has_lb = true;
-      b.has_ub = false;
+      b.has_ub = (MODE == 2);
       b.lb     = lds_f64(va + 3 * TR * 8);
-      b.ub     = 0.0;
+      b.ub     = (MODE == 2) ? lds_f64(va + 4 * TR * 8) : 0.0;
       a.v[RA_FEAS] = box_feas_lazy(xr, pr, b, a.v[RA_FEAS]);
     } else {
       BoxVal   b;
@@ -1233,10 +1234,10 @@ struct EpiAT {
     }
   }
 };
-typedef EpiAT<false> EpiA;
+typedef EpiAT<0> EpiA;
 
 // K_A' epilogue: g_r = (A x)_r + rho (B^T Bu)_r - b_r ; split ; p = gf ; |gP|^2 |gc|^2 |gf|^2
-template <bool LBONLY>
+template <int MODE>
 struct EpiA2T {
   const double        *x, *b;
   double              *g, *p;
@@ -1308,11 +1309,11 @@ struct EpiA2T {
     }
     BoxVal bv;
     double gr = ax;
-    if constexpr (LBONLY) {
+    if constexpr (MODE != 0) {
       bv.has_lb = true;
-      bv.has_ub = false;
+      bv.has_ub = (MODE == 2);
       bv.lb     = lds_f64(va + 2 * TR * 8);
-      bv.ub     = 0.0;
+      bv.ub     = (MODE == 2) ? lds_f64(va + 3 * TR * 8) : 0.0;
     } else {
       uint32_t k = 2;
       bv.has_lb = bx.lb != nullptr;
@@ -1338,7 +1339,7 @@ struct EpiA2T {
     a.v[RB_GF2] += gf * gf;
   }
 };
-typedef EpiA2T<false> EpiA2;
+typedef EpiA2T<0> EpiA2;
 
 // ghost pass (multi-GPU): add the off-diagonal block product to the parked partial result, then run the
 // deferred epilogue of K_A (SECOND = false) or K_A' (SECOND = true) for the boundary rows
@@ -1403,7 +1404,11 @@ static double bytes_A2(const CsrDev &A, const MpgpVecs &v)
 int k_fused_A(const CsrDev &A, const double *xin, const MpgpVecs &v, const MpgpCtl *S, RedBuf rb, SkipRows skip)
 {
   if (v.bx.lb && !v.bx.ub && v.m == 0) {
-    EpiAT<true> e{v.p, v.g, v.x, v.Ap, v.bx, v.B, v.m, v.n, S, rb, skip};
+    EpiAT<1> e{v.p, v.g, v.x, v.Ap, v.bx, v.B, v.m, v.n, S, rb, skip};
+    return launch_spmv(A, xin, e, KF_SPMV_A, bytes_A(A, v));
+  }
+  if (v.bx.lb && v.bx.ub && v.m == 0) {
+    EpiAT<2> e{v.p, v.g, v.x, v.Ap, v.bx, v.B, v.m, v.n, S, rb, skip};
     return launch_spmv(A, xin, e, KF_SPMV_A, bytes_A(A, v));
   }
   EpiA e{v.p, v.g, v.x, v.Ap, v.bx, v.B, v.m, v.n, S, rb, skip};
@@ -1413,7 +1418,11 @@ int k_fused_A(const CsrDev &A, const double *xin, const MpgpVecs &v, const MpgpC
 int k_fused_A2(const CsrDev &A, const double *xin, const MpgpVecs &v, const MpgpCtl *S, RedBuf rb, SkipRows skip)
 {
   if (v.bx.lb && !v.bx.ub && v.m == 0) {
-    EpiA2T<true> e{v.x, v.b, v.g, v.p, v.bx, v.B, v.m, v.n, S, rb, skip};
+    EpiA2T<1> e{v.x, v.b, v.g, v.p, v.bx, v.B, v.m, v.n, S, rb, skip};
+    return launch_spmv(A, xin, e, KF_SPMV_A2, bytes_A2(A, v));
+  }
+  if (v.bx.lb && v.bx.ub && v.m == 0) {
+    EpiA2T<2> e{v.x, v.b, v.g, v.p, v.bx, v.B, v.m, v.n, S, rb, skip};
     return launch_spmv(A, xin, e, KF_SPMV_A2, bytes_A2(A, v));
   }
   EpiA2 e{v.x, v.b, v.g, v.p, v.bx, v.B, v.m, v.n, S, rb, skip};
