@@ -305,6 +305,33 @@ def test_varcoef3d_both_bounds(P):
     assert np.array_equal(la, pr.meta["lower_active"])
 
 
+@pytest.mark.parametrize("kind", ["raw_tiles", "mixed_tiles"])
+def test_fused_solve_on_raw_and_mixed_tiles(P, kind):
+    """Hessians whose values do not repeat: every tile (or a band of tiles) overflows the 256-entry dictionary and is stored raw in
+    the packed format; the fused MPGP iteration must not care.  A = D L D with a random positive diagonal scaling D; the load is
+    large enough for CG, expansion and proportioning steps and a few hundred active dofs."""
+    import scipy.sparse as sp
+    pr = PR.obstacle2d(96, -100.0)
+    n = pr.n
+    rng = np.random.default_rng(17)
+    d = 1.0 + 0.5 * rng.random(n)
+    if kind == "mixed_tiles":
+        d[: n // 3] = 1.0
+        d[2 * n // 3:] = 1.0
+    A = sp.csr_matrix((pr.a, pr.ja, pr.ia), shape=(n, n))
+    A = (sp.diags(d) @ A @ sp.diags(d)).tocsr()
+    A.sort_indices()
+    pr.ia, pr.ja, pr.a = A.indptr.astype(np.int32), A.indices.astype(np.int32), A.data
+    Am = P.MatCreateAIJ(pr.ia, pr.ja, pr.a)
+    info = P.MatStorageInfo(Am)
+    P.MatDestroy(Am)
+    assert info["kind"] == 3
+    assert (info["coded_tiles"] <= 1) if kind == "raw_tiles" else (0 < info["coded_tiles"] < info["tiles"])
+    r = P.solve_problem(pr, "mpgp", "-qps_rtol 1e-8 -qps_mpgp_b200_driver fused")
+    xr, ro = oracle_solve(pr, rtol=1e-8)
+    check_parity(pr, r, xr, ro, band_kw=dict(rtol=1e-8))
+
+
 @pytest.mark.parametrize("N,bscale,maxit", [(1024, -30.0, 150), (512, -100.0, 400)])
 def test_fused_equals_generic_driver_midsize(P, N, bscale, maxit):
     """size-independent property: the fused device-driven iteration and the un-fused host-driven one take the
