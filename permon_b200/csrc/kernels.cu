@@ -435,7 +435,17 @@ __global__ void __launch_bounds__(NT) k_spmv_vector(CsrDev A, const double *__re
     double    s = 0.0;
     if (r < A.n) {
       const int ks = __ldg(A.ia + r), ke = __ldg(A.ia + r + 1);
-      for (int k = ks + lane; k < ke; k += W) s += __ldg(A.a + k) * __ldg(x + __ldg(A.ja + k));
+      int k = ks + lane;
+      for (; k + 3 * W < ke; k += 4 * W) {   // four independent index -> gather chains in flight, products added in the same order
+        const int    j0 = __ldg(A.ja + k), j1 = __ldg(A.ja + k + W), j2 = __ldg(A.ja + k + 2 * W), j3 = __ldg(A.ja + k + 3 * W);
+        const double a0 = __ldg(A.a + k), a1 = __ldg(A.a + k + W), a2 = __ldg(A.a + k + 2 * W), a3 = __ldg(A.a + k + 3 * W);
+        const double x0 = __ldg(x + j0), x1 = __ldg(x + j1), x2 = __ldg(x + j2), x3 = __ldg(x + j3);
+        s += a0 * x0;
+        s += a1 * x1;
+        s += a2 * x2;
+        s += a3 * x3;
+      }
+      for (; k < ke; k += W) s += __ldg(A.a + k) * __ldg(x + __ldg(A.ja + k));
     }
 #pragma unroll
     for (int o = W / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
