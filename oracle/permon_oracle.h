@@ -15,6 +15,13 @@
  * SMALXE has no reference golden reachable without MUMPS/QPTDualize
  * (SURVEY.md 8c), so the SMALXE part is pinned only through its MPGP inner
  * solver and hand-checkable cases.
+ * Parity UNPINNED for the "next" rows added later:
+ * orc_cg_solve (QPSKSP = PETSc's KSPCG recurrence), orc_pcpg_solve (QPSPCPG),
+ * orc_orth_rows / orc_homogenize / the projected operator (QPTOrthonormalizeEq,
+ * QPTEnforceEqByProjector).  The reference has no test or golden output that
+ * reaches them without QPTDualize + MUMPS; they are checked against their
+ * defining identities and scipy (tests/test_oracle_linear.py,
+ * tests/test_oracle_transforms.py).
  *
  * The reference (permon/permon) is plain C on PETSc.  PETSc is an un-vendored
  * third-party dependency (requires >= 3.17, uses 3.23/3.24-era API; no lock
