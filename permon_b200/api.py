@@ -260,6 +260,14 @@ def VecGetArray(v) -> np.ndarray:
     return out
 
 
+def VecSyncToHost(v):
+    """VecGetArrayRead + Restore without a copy: the current contents land in the host buffer the Vec was created over
+    (VecCreate*WithArray semantics: the user's array is the storage)."""
+    p = C.POINTER(C.c_double)()
+    call("VecGetArrayRead", v, C.byref(p))
+    call("VecRestoreArrayRead", v, C.byref(p))
+
+
 def VecSetArray(v, arr):
     n = VecGetLocalSize(v)
     p = C.POINTER(C.c_double)()

@@ -3,6 +3,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "mpgp_ctl.h"
 
@@ -58,6 +59,25 @@ struct PkHeader {
   uint32_t pad;
 };
 static_assert(sizeof(PkHeader) == 16, "tile header is one 16-byte line");
+
+// uninitialised host byte buffer (std::vector would zero-fill ~100 MB on one thread before the parallel fill)
+struct RawBuf {
+  unsigned char *p = nullptr;
+  size_t         n = 0;
+  RawBuf() {}
+  RawBuf(const RawBuf &) = delete;
+  RawBuf &operator=(const RawBuf &) = delete;
+  ~RawBuf() { free(p); }
+  bool alloc(size_t bytes)
+  {
+    free(p);
+    p = (unsigned char *)malloc(bytes ? bytes : 1);
+    n = p ? bytes : 0;
+    return p != nullptr;
+  }
+  unsigned char *data() { return p; }
+  size_t         size() const { return n; }
+};
 
 struct CsrDev {
   int           n      = 0;        // rows

@@ -1088,6 +1088,7 @@ int spmv_config(CsrDev &A, const int *h_ia)
     int t  = h_ia[r1] - h_ia[r0];
     if (t > cap) cap = t;
   }
+#pragma omp parallel for reduction(max : maxrow) schedule(static)
   for (int r = 0; r < n; r++) {
     int l = h_ia[r + 1] - h_ia[r];
     if (l > maxrow) maxrow = l;

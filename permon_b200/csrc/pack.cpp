@@ -81,7 +81,7 @@ struct TileDict {
 // k-th entry of a row is first compared with the k-th entry of the previous row (a hit for almost every entry of a stencil
 // matrix), the hash table is only consulted on a miss.  Pass 2 lays the blobs out: dictionary, row offsets and code bytes are
 // copied, nothing is hashed again.
-int pk_build(int n, const int *ia, const int *ja, const double *a, std::vector<unsigned char> &blob, std::vector<unsigned> &h_off, int &max_tile_bytes,
+int pk_build(int n, const int *ia, const int *ja, const double *a, RawBuf &blob, std::vector<unsigned> &h_off, int &max_tile_bytes,
              int64_t &ncoded, bool &packed)
 {
   const int ntiles = (n + TR - 1) / TR;
@@ -182,7 +182,11 @@ int pk_build(int n, const int *ia, const int *ja, const double *a, std::vector<u
     return 0;
   }
   h_off[ntiles] = (unsigned)(tot / 16);
-  blob.resize(tot + 16);
+  if (!blob.alloc(tot + 16)) {
+    free(codes_tmp);
+    return 55;
+  }
+  memset(blob.data() + tot, 0, 16);
 #pragma omp parallel for schedule(dynamic, 64)
   for (int t = 0; t < ntiles; t++) {
     const int      r0 = t * TR, r1 = std::min(r0 + TR, n), nrows = r1 - r0;

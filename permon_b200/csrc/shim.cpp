@@ -2,6 +2,7 @@
 // options database, viewers, IS, Vec and Mat with host<->device validity tracking, the row-partitioned AIJ
 // matrix with its halo plan, and the generic (un-fused) Mat/Vec operations built on the CUDA kernels.
 // There is no CPU arithmetic here: every numerical operation launches a kernel from kernels.cu.
+#include <time.h>
 #include <cuda_runtime.h>
 #include <math.h>
 #include <nccl.h>
@@ -918,9 +919,17 @@ _p_Mat::~_p_Mat()
 }
 
 namespace pb {
-int pk_build(int n, const int *ia, const int *ja, const double *a, std::vector<unsigned char> &blob, std::vector<unsigned> &h_off, int &max_tile_bytes,
+int pk_build(int n, const int *ia, const int *ja, const double *a, RawBuf &blob, std::vector<unsigned> &h_off, int &max_tile_bytes,
              int64_t &ncoded, bool &packed);
 }
+
+static double wall_now()
+{
+  struct timespec ts;
+  clock_gettime(CLOCK_MONOTONIC, &ts);
+  return ts.tv_sec + 1e-9 * ts.tv_nsec;
+}
+static bool verbose_timing() { return getenv("PERMON_B200_VERBOSE") != nullptr; }
 
 static int upload_csr(pb::CsrDev &C, int nrows, int ncols, const int *ia, const int *ja, const double *a, const int *rows)
 {
@@ -939,12 +948,14 @@ static int upload_csr(pb::CsrDev &C, int nrows, int ncols, const int *ia, const 
   // Tile-streamable matrices are re-coded into packed tiles (pack.cpp) and only that form goes to the device;
   // PERMON_B200_SPMV=tma|stream|vector keeps plain CSR for A/B measurements.  Tiny matrices (equality rows) stay CSR.
   if (C.kind == 2 && !rows && nrows >= 64 && !getenv("PERMON_B200_SPMV")) {
-    std::vector<unsigned char> blob;
-    std::vector<unsigned>      off;
+    pb::RawBuf            blob;
+    std::vector<unsigned> off;
     int                        max_tile = 0;
     int64_t                    ncoded = 0;
     bool                       packed = false;
+    const double t_pk0 = wall_now();
     PB_CHK(pb::pk_build(nrows, ia, ja, a, blob, off, max_tile, ncoded, packed));
+    const double t_pk1 = wall_now();
     if (packed) {
       unsigned char *dblob;
       unsigned      *doff;
@@ -953,6 +964,9 @@ static int upload_csr(pb::CsrDev &C, int nrows, int ncols, const int *ia, const 
       PB_CUDA(cudaMemcpyAsync(dblob, blob.data(), blob.size(), cudaMemcpyHostToDevice, s));
       PB_CUDA(cudaMemcpyAsync(doff, off.data(), sizeof(unsigned) * off.size(), cudaMemcpyHostToDevice, s));
       PB_CUDA(cudaStreamSynchronize(s));   // blob / off are locals
+      if (verbose_timing())
+        fprintf(stderr, "[permon_b200] matrix %d rows, %lld nnz: re-coded into packed tiles in %.1f ms, %.1f MB uploaded in %.1f ms\n", nrows, (long long)nnz,
+                1e3 * (t_pk1 - t_pk0), blob.size() / 1e6, 1e3 * (wall_now() - t_pk1));
       C.pk       = dblob;
       C.pk_off   = doff;
       C.pk_max   = max_tile;
@@ -1366,8 +1380,8 @@ PetscErrorCode PermonB200PackTiles(PetscInt n, const PetscInt ia[], const PetscI
                                    PetscInt *ntiles, PetscInt *coded_tiles)
 {
   if (!ia || !blob || !tile_off) return err(PETSC_ERR_ARG_NULL, "null argument");
-  std::vector<unsigned char> b;
-  std::vector<unsigned>      off;
+  pb::RawBuf            b;
+  std::vector<unsigned> off;
   int                        max_tile = 0;
   int64_t                    ncoded = 0;
   bool                       packed = false;
