@@ -11,10 +11,15 @@
  * golden outputs exactly (iteration / Hessian-mult / step-kind counts of
  * src/tutorials/output/ex1_{1,opt,optapprox,bb,projcg}.out,
  * ex2_1_infinite-{false,true}.out, and the 11-digit per-iteration traces and
- * alpha of jbearing2_{4,5,6}.out); see tests/test_oracle_golden.py.
- * SMALXE has no reference golden reachable without MUMPS/QPTDualize
- * (SURVEY.md 8c), so the SMALXE part is pinned only through its MPGP inner
- * solver and hand-checkable cases.
+ * alpha of jbearing2_{4,5,6}.out); see tests/test_oracle_golden.py.  Also
+ * ex3_1.out (MPGP on the dualised problem of ex3, restated with a dense K^-1
+ * instead of MUMPS: counts and printed KKT digits agree) and, for SMALXE,
+ * ex3_nullspace.out: the dual QP with a zero-row equality constraint runs
+ * QPSSolve_SMALXE + QPSConverged_Inner_SMALXE to "1 outer iteration, inner
+ * CONVERGED_HAPPY_BREAKDOWN after 46 iterations, 74/18/27/1" exactly.  The
+ * SMALXE update rules for a non-empty B (M1 / rho updates) have no reference
+ * output reachable without QPTDualize of FETI problems; they are covered by
+ * hand-checkable cases.
  * Parity UNPINNED for the "next" rows added later:
  * orc_cg_solve (QPSKSP = PETSc's KSPCG recurrence), orc_pcpg_solve (QPSPCPG),
  * orc_orth_rows / orc_homogenize / the projected operator (QPTOrthonormalizeEq,

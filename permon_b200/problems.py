@@ -113,6 +113,31 @@ def tutorial_ex1(n=100):
     return QPProblem("ex1", n, 0, n, ia, ja, a, b, lb, None, np.zeros(n))
 
 
+def tutorial_ex3_dual(n=100):
+    """ex3.c dualised (QPTDualize, qptransform.c:909-1186, the -spd / empty-nullspace branch): the primal problem is ex1 with the
+    bound written as the inequality -I x <= -c; the dual QP is  min 1/2 l'F l - l'd, l >= 0  with F = B K^+ B', d = B K^+ f - c_I,
+    B = -I.  The reference applies K^+ with a sparse direct solver (MUMPS); here K^-1 is formed densely (n = 100), so F is an
+    explicit dense matrix in CSR -- same mathematics, rounding of a different factorisation."""
+    ia, ja, a = _tutorial_1d_matrix(n)
+    K = np.zeros((n, n))
+    for i in range(n):
+        K[i, ja[ia[i]:ia[i + 1]]] = a[ia[i]:ia[i + 1]]
+    h = 1.0 / (n - 1)
+    f = np.full(n, -15 * h * h * 2)
+    f[0] = f[-1] = 0.0
+    c = _fobst(np.arange(n, dtype=np.float64), n)
+    c[0] = c[-1] = 0.0
+    cI = -c                                   # VecScale(c, -1), ex3.c:126
+    Kinv = np.linalg.inv(K)
+    Bm = -np.eye(n)                           # MatScale(B, -1), ex3.c:127
+    F = Bm @ Kinv @ Bm.T
+    d = Bm @ (Kinv @ f) - cI                  # d = B K^+ f - c (:1128-1132)
+    fia = (np.arange(n + 1) * n).astype(np.int32)
+    fja = np.tile(np.arange(n, dtype=np.int32), n)
+    return QPProblem("ex3dual", n, 0, n, fia, fja, np.ascontiguousarray(F).ravel(), d, np.zeros(n), None, np.zeros(n),
+                     meta=dict(Kinv=Kinv, f=f, B=Bm, cI=cI, K=K))
+
+
 def tutorial_ex2(n=100, infinite=False):
     h = 1.0 / (n - 1)
     ia, ja, a = _tutorial_1d_matrix(n)

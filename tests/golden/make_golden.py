@@ -3,7 +3,7 @@
 
 Run in the build container only (reads /root/reference, which does not exist on the GPU box):
     python tests/golden/make_golden.py
-Source files: /root/reference/src/tutorials/output/{ex1_*,ex2_1_*,jbearing2_{4,5,6}}.out, produced by the
+Source files: /root/reference/src/tutorials/output/{ex1_*,ex2_1_*,ex3_*,jbearing2_{4,5,6}}.out, produced by the
 reference's own test harness (test specs: src/tutorials/ex1.c:161-184, ex2.c:163-169, jbearing2.c:586-598).
 Only numbers are extracted (counts, KKT residual magnitudes, per-iteration monitor values) -- no source code.
 """
@@ -56,6 +56,16 @@ def main():
         m = re.search(r"Norm of difference of results from TAO and QP = (\S+) <= (\S+) = tolerance", text)
         d["tao_diff"], d["tao_diff_tol"] = float(m.group(1)), float(m.group(2))
         g[name] = d
+    # ex3 (dualised problem, src/tutorials/ex3.c:166-182): MPGP on the dual QP, and SMALXE around it when an empty null space
+    # matrix makes the dual carry a zero-row equality constraint
+    text = open(os.path.join(REF, "ex3_1.out")).read()
+    g["ex3_1"] = dict(problem="ex3dual", n=100, args={}, **parse_counts(text))
+    text = open(os.path.join(REF, "ex3_nullspace.out")).read()
+    d = parse_counts(text)               # counts of the inner MPGP; the first CONVERGED line is the outer SMALXE
+    inner = re.findall(r"CONVERGED due to (\w+), KSPReason=(-?\d+), required (\d+) iterations", text)
+    d.update(problem="ex3dual", n=100, outer_reason=int(inner[0][1]), outer_its=int(inner[0][2]), inner_reason=int(inner[1][1]),
+             inner_its=int(inner[1][2]), total_inner=int(re.search(r"Total number of inner iterations (\d+)", text).group(1)))
+    g["ex3_nullspace"] = d
     with open(OUT, "w") as f:
         json.dump(g, f, indent=1, sort_keys=True)
     print("wrote", OUT, {k: (v["its"], v["nmv"]) for k, v in g.items() if isinstance(v, dict)})

@@ -245,6 +245,18 @@ def test_tutorials_match_golden_counts(P, golden, name, driver):
     assert np.allclose(r.llb, llb, rtol=1e-12, atol=1e-14)
 
 
+@pytest.mark.parametrize("driver", ["fused", "generic"])
+def test_ex3_dualised_problem_matches_golden_counts(P, golden, driver):
+    """src/tutorials/output/ex3_1.out: MPGP on the dual QP of ex3 (dense Hessian F = B K^+ B', rows of 100 entries -> long-row SpMV)"""
+    g = golden["ex3_1"]
+    pr = PR.tutorial_ex3_dual(g["n"])
+    r = P.solve_problem(pr, "mpgp", f"-qps_mpgp_b200_driver {driver}")
+    c = r.counts
+    assert (r.its, c["nmv"], c["ncg"], c["nexp"], c["nprop"], r.reason) == (g["its"], g["nmv"], g["ncg"], g["nexp"], g["nprop"], g["reason"])
+    xr, ro = oracle_solve(pr)
+    assert np.linalg.norm(r.x - xr) <= 1e-9 * np.linalg.norm(xr)
+
+
 @pytest.mark.parametrize("name", ["ex1_opt", "ex1_optapprox", "ex1_bb", "ex1_projcg"])
 def test_expansion_variants_generic_driver(P, golden, name):
     g = golden[name]
@@ -446,6 +458,33 @@ def test_smalxe_two_rows_generic_aij(P):
     r = P.solve_problem(pr, "smalxe", "-qps_rtol 1e-9")
     xr, ro = oracle_smalxe(pr, rtol=1e-9)
     smalxe_check(pr, r, xr, ro, band_kw=dict(rtol=1e-9))
+
+
+def test_ex3_nullspace_smalxe_matches_golden(P, golden):
+    """src/tutorials/output/ex3_nullspace.out: the dual QP of ex3 with a zero-row equality constraint -> SMALXE (default type) around
+    MPGP; one outer iteration, inner solve ended from inside by the outer criterion (CONVERGED_HAPPY_BREAKDOWN) after 46 iterations"""
+    g = golden["ex3_nullspace"]
+    pr = PR.tutorial_ex3_dual(g["n"])
+    pr.B = np.zeros((0, pr.n))
+    pr.c = None
+    P.options_clear()
+    A = P.MatCreateAIJ(pr.ia, pr.ja, pr.a)
+    vb, vx, vl = P.VecFromArray(pr.b.copy()), P.VecFromArray(np.zeros(pr.n)), P.VecFromArray(np.zeros(pr.n))
+    BE = P.MatCreateAIJ(np.zeros(1, dtype=np.int32), np.zeros(0, dtype=np.int32), np.zeros(0), ncols_local=pr.n)
+    qp = P.QPCreate()
+    P.QPSetOperator(qp, A), P.QPSetRhs(qp, vb), P.QPSetInitialVector(qp, vx), P.QPSetBox(qp, None, vl, None), P.QPSetEq(qp, BE, None)
+    qps = P.QPSCreate()
+    P.QPSSetQP(qps, qp)
+    P.QPSSetFromOptions(qps)
+    P.QPSSolve(qps)
+    assert P.QPSGetType(qps) == "smalxe"
+    inner = P.QPSSMALXEGetInnerQPS(qps)
+    c = P.QPSMPGPGetStepCounts(inner)
+    st = P.QPSSMALXEGetStatistics(qps)
+    assert (P.QPSGetIterationNumber(qps), P.QPSGetConvergedReason(qps)) == (g["outer_its"], g["outer_reason"])
+    assert (st["inner_iter_accu"], P.QPSGetConvergedReason(inner)) == (g["total_inner"], g["inner_reason"])
+    assert (c["nmv"], c["ncg"], c["nexp"], c["nprop"]) == (g["nmv"], g["ncg"], g["nexp"], g["nprop"])
+    P.QPSDestroy(qps), P.QPDestroy(qp)
 
 
 def test_error_paths(P):

@@ -63,6 +63,45 @@ def test_jbearing2_trace(golden, name, exact):
     assert r["rnorm"] <= max(1e-6 * np.linalg.norm(pr.b), 1e-8)
 
 
+def test_ex3_dualised_problem_counts_and_kkt(golden):
+    """src/tutorials/output/ex3_1.out: MPGP on the dual QP built by QPTDualize (dense, non-stencil Hessian F = B K^+ B').  The
+    reference forms K^+ with MUMPS, the fixture problem with a dense inverse: the counts and the printed KKT digits still agree."""
+    g = golden["ex3_1"]
+    pr = P.tutorial_ex3_dual(g["n"])
+    x, r, op, bx = _solve(pr)
+    assert _counts(r) == (g["its"], g["nmv"], g["ncg"], g["nexp"], g["nprop"], g["reason"])
+    llb, lub = O.box_multipliers(op, pr.b, bx, x)
+    k = O.kkt(op, pr.b, bx, x, llb, lub)
+    # the dual QP's four lines; ||min(x-lb,0)|| is round-off of the K^+ application (0 in ex3_1.out, 1e-19 in ex3_nullspace.out)
+    assert k[1] == g["kkt"][0]["r"] == 0.0 and k[2] < 1e-15 and g["kkt"][1]["r"] < 1e-15
+    assert ["%.2e" % v for v in k[3:5]] == ["%.2e" % q["r"] for q in g["kkt"][2:4]]
+    assert ["%.2e" % (v / k[0]) for v in k[3:5]] == ["%.2e" % q["rel"] for q in g["kkt"][2:4]]
+    # primal lines of the same report (QPTDualizePostSolve: u = K^+ (f - B' lambda)): ||max(B_I u - c_I, 0)|| and the complementarity
+    m = pr.meta
+    u = m["Kinv"] @ (m["f"] - m["B"].T @ x)
+    viol = np.linalg.norm(np.maximum(m["B"] @ u - m["cI"], 0.0))
+    assert "%.2e" % viol == "%.2e" % g["kkt"][5]["r"]
+    assert "%.2e" % abs(x @ (m["B"] @ u - m["cI"])) == "%.2e" % g["kkt"][7]["r"]
+
+
+def test_ex3_nullspace_pins_the_smalxe_driver(golden):
+    """src/tutorials/output/ex3_nullspace.out: with an empty null-space matrix the dual QP carries an equality constraint with zero
+    rows, so the default solver is SMALXE around MPGP.  One outer iteration, the inner solve stopped by the outer criterion from
+    inside (CONVERGED_HAPPY_BREAKDOWN) after 46 iterations: this pins QPSSolve_SMALXE / QPSConverged_Inner_SMALXE themselves."""
+    g = golden["ex3_nullspace"]
+    pr = P.tutorial_ex3_dual(g["n"])
+    op = O.Operator(pr.ia, pr.ja, pr.a)
+    bx = O.BoxC(pr.n, pr.lb, None)
+    x, r = O.smalxe_solve(op, pr.b, bx, np.zeros((0, pr.n)), None, pr.x0, O.smalxe_opts())
+    assert (r["outer_its"], r["reason"]) == (g["outer_its"], g["outer_reason"])
+    assert (r["inner_its_accu"], r["inner_reason_last"]) == (g["total_inner"], g["inner_reason"])
+    assert (r["nmv"], r["ncg"], r["nexp"], r["nprop"]) == (g["nmv"], g["ncg"], g["nexp"], g["nprop"])
+    op.c.m = 0
+    llb, lub = O.box_multipliers(op, pr.b, bx, x)
+    k = O.kkt(op, pr.b, bx, x, llb, lub)
+    assert ["%.2e" % v for v in k[3:5]] == ["%.2e" % q["r"] for q in g["kkt"][2:4]]            # ||min(lambda_lb,0)||, |lambda_lb'(lb-x)|
+
+
 def test_threads_do_not_change_counts(golden):
     """The golden ex1_1 output is identical for 1 and 3 MPI ranks; threads stand in for ranks."""
     g = golden["ex1_1"]
