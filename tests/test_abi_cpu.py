@@ -92,6 +92,43 @@ def test_host_side_object_conventions(P):
     assert qps.value is None and qp.value is None and x.value is None   # Destroy nulls the handle (qps.c:340-362)
 
 
+def test_solver_types_and_compatibility_rules(P):
+    """QPSRegister'ed types and their QPSIsQPCompatible rules are host logic: mpgp needs a box and no equality (mpgp.c:695-711), ksp
+    an unconstrained QP (qpsksp.c:205-219), pcpg an equality constraint and no box (pcpg.c:13-22); QPSKSP only offers CG here"""
+    def compat(qps, qp):
+        f = C.c_int()
+        P.call("QPSIsQPCompatible", qps, qp, C.byref(f))
+        return bool(f.value)
+    x, lb = P.VecFromArray(np.zeros(5)), P.VecFromArray(np.zeros(5))
+    qp = P.QPCreate()
+    P.QPSetInitialVector(qp, x)
+    qps = P.QPSCreate()
+    for t in ("ksp", "pcpg", "mpgp", "smalxe"):
+        P.QPSSetType(qps, t)
+        assert P.QPSGetType(qps) == t
+    P.QPSSetType(qps, "ksp")
+    assert compat(qps, qp)
+    t = C.c_char_p()
+    P.call("QPSKSPGetType", qps, C.byref(t))
+    assert t.value == b"cg"
+    P.call("QPSKSPSetType", qps, b"cg")
+    with pytest.raises(P.PermonError) as e:
+        P.call("QPSKSPSetType", qps, b"gmres")
+    assert e.value.code == 56                                    # PETSC_ERR_SUP
+    P.QPSSetType(qps, "pcpg")
+    assert not compat(qps, qp)                                    # no equality constraint
+    P.QPSetBox(qp, None, lb, None)
+    assert not compat(qps, qp)
+    P.QPSSetType(qps, "ksp")
+    assert not compat(qps, qp)                                    # box-constrained
+    P.QPSSetType(qps, "mpgp")
+    assert compat(qps, qp)
+    with pytest.raises(P.PermonError) as e:
+        P.call("QPSKSPGetType", qps, C.byref(t))                  # "This is a QPSKSP specific routine!"
+    assert e.value.code == 56
+    P.QPSDestroy(qps), P.QPDestroy(qp), P.VecDestroy(x), P.VecDestroy(lb)
+
+
 def test_no_cpu_fallback(P):
     if P.device_count() > 0:
         pytest.skip("a CUDA device is present")
