@@ -547,6 +547,12 @@ PetscErrorCode PermonB200CommInitRank(int nranks, int rank, const void *id128)
   g_world.rank = rank;
   g_world.size = nranks;
   if (nranks == 1) return 0;
+  // one process per GPU on one node: the ranks' OpenMP regions (host split of the matrix, packer) share the host cores instead of
+  // every rank starting one thread per core
+  if (!getenv("OMP_NUM_THREADS")) {
+    const int per = omp_get_num_procs() / nranks;
+    omp_set_num_threads(per > 1 ? per : 1);
+  }
   PB_CHK(dev_init());
   ncclUniqueId id;
   memcpy(&id, id128, 128);
