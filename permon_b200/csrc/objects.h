@@ -6,6 +6,7 @@
 
 #include <map>
 #include <string>
+#include <cstdlib>
 #include <vector>
 
 #include "../../include/permon_b200.h"
@@ -86,9 +87,30 @@ struct HaloPlan {
   pb::PushRanges       *d_ranges = nullptr;                   // device copies [2] (p, x) for the fused pushes
   // host copy of the split matrix, kept until the first device use (lets the plan be built and inspected
   // without a GPU; the arithmetic still needs one)
+  // big arrays of the diagonal block: filled in parallel right after the allocation, never zero-filled first
+  template <class T>
+  struct UVec {
+    T     *p = nullptr;
+    size_t n = 0;
+    UVec() {}
+    UVec(const UVec &) = delete;
+    UVec &operator=(const UVec &) = delete;
+    ~UVec() { free(p); }
+    void resize(size_t k)
+    {
+      free(p);
+      p = (T *)malloc((k ? k : 1) * sizeof(T));
+      n = p ? k : 0;
+    }
+    T       *data() { return p; }
+    size_t   size() const { return n; }
+    T       &operator[](size_t i) { return p[i]; }
+  };
   struct HostSplit {
-    std::vector<int>           dia, dja, oia, oja, orow;
-    std::vector<double>        da, oa;
+    std::vector<int>           dia, oia, oja, orow;
+    UVec<int>                  dja;
+    std::vector<double>        oa;
+    UVec<double>               da;
     std::vector<unsigned char> skip;
   } *host = nullptr;
 };

@@ -1082,6 +1082,7 @@ PetscErrorCode MatCreateMPIAIJWithArrays(MPI_Comm comm, PetscInt m, PetscInt n, 
   A->cstart = (PetscInt)cs[rank];
   const PetscInt c0 = A->cstart, c1 = A->cstart + n;
   const int64_t  nnz = i[m];
+  const double   t_s0 = wall_now();
   HaloPlan      *H = new HaloPlan;
   A->halo          = H;
   // ghosts (host threads: the split is O(nnz) and sits inside the e2e path of multi-GPU runs)
@@ -1104,10 +1105,13 @@ PetscErrorCode MatCreateMPIAIJWithArrays(MPI_Comm comm, PetscInt m, PetscInt n, 
   std::sort(gh.begin(), gh.end());
   gh.erase(std::unique(gh.begin(), gh.end()), gh.end());
   H->garray = gh;
+  const double t_s1 = wall_now();
   // split: count, prefix-sum, fill
   H->host = new HaloPlan::HostSplit;
-  std::vector<int>    &dia = H->host->dia, &dja = H->host->dja, &oia = H->host->oia, &oja = H->host->oja, &orow = H->host->orow;
-  std::vector<double> &da = H->host->da, &oa = H->host->oa;
+  std::vector<int>       &dia = H->host->dia, &oia = H->host->oia, &oja = H->host->oja, &orow = H->host->orow;
+  std::vector<double>    &oa = H->host->oa;
+  HaloPlan::UVec<int>    &dja = H->host->dja;
+  HaloPlan::UVec<double> &da = H->host->da;
   std::vector<unsigned char> &skip = H->host->skip;
   dia.assign(m + 1, 0);
   skip.assign(std::max<PetscInt>(m, 1), 0);
@@ -1149,6 +1153,7 @@ PetscErrorCode MatCreateMPIAIJWithArrays(MPI_Comm comm, PetscInt m, PetscInt n, 
     }
   }
   H->nboundary = (PetscInt)orow.size();
+  const double t_s2 = wall_now();
   {   // widest run of interior rows: kernels skip the per-row flag lookup inside it
     int best_lo = 0, best_hi = 0, cur = 0;
     for (int r : orow) {
@@ -1202,6 +1207,9 @@ PetscErrorCode MatCreateMPIAIJWithArrays(MPI_Comm comm, PetscInt m, PetscInt n, 
     H->send_off = soff;
     H->send_idx = sidx;
   }
+  if (verbose_timing())
+    fprintf(stderr, "[permon_b200] rank %d host split of %d rows / %lld nnz: ghosts %.1f ms, diag/off-diag split %.1f ms, plan exchange %.1f ms\n", rank, (int)m,
+            (long long)nnz, 1e3 * (t_s1 - t_s0), 1e3 * (t_s2 - t_s1), 1e3 * (wall_now() - t_s2));
   A->Ad.n = m;   // sizes are known; the arrays reach the device on first use (mat_ensure_device)
   A->Ad.ncols = n;
   A->Ad.nnz = (int64_t)dja.size();
