@@ -205,6 +205,10 @@ PERMON_EXTERN PetscErrorCode MatGetMaxEigenvalue(Mat A, Vec v, PetscReal *lambda
 /* halo-plan introspection (host data; used by the CPU multi-rank tests) */
 PERMON_EXTERN PetscErrorCode MatB200GetHaloInfo(Mat A, PetscInt *nghost, const PetscInt **garray, PetscInt *nneigh, const PetscInt **neigh_rank,
                                                 const PetscInt **recv_off, const PetscInt **send_off, const PetscInt **send_idx, PetscInt *nboundary_rows);
+/* host split of a row-partitioned matrix (diagonal block with local columns, compressed off-diagonal rows with ghost-buffer columns,
+   the local row id of every off-diagonal row); valid until the matrix is first used on the device.  CPU multi-rank tests. */
+PERMON_EXTERN PetscErrorCode MatB200GetHostSplit(Mat A, const PetscInt **dia, const PetscInt **dja, const PetscScalar **da, PetscInt *noffrows,
+                                                 const PetscInt **oia, const PetscInt **oja, const PetscScalar **oa, const PetscInt **orow);
 /* device storage introspection: kind 0/1/2 = CSR (tile-streamed / vector / TMA-staged), 3 = packed dictionary-coded tiles;
    stream_bytes = bytes one SpMV reads for the matrix itself (diagonal + off-diagonal block); coded_tiles / tiles of the packed form.
    Uploads a row-partitioned matrix if it is not on the device yet. */

@@ -383,6 +383,20 @@ def MatGetHaloInfo(A):
                 send_idx=[si[i] for i in range(send_off[-1])], nboundary=nb.value)
 
 
+def MatGetHostSplit(A, m):
+    """(dia, dja, da, oia, oja, oa, orow) of a row-partitioned matrix that has not been used on the device yet (copies)"""
+    pi = lambda: C.POINTER(C.c_int32)()
+    dia, dja, oia, oja, orow = pi(), pi(), pi(), pi(), pi()
+    da, oa = C.POINTER(C.c_double)(), C.POINTER(C.c_double)()
+    no = C.c_int()
+    call("MatB200GetHostSplit", A, C.byref(dia), C.byref(dja), C.byref(da), C.byref(no), C.byref(oia), C.byref(oja), C.byref(oa), C.byref(orow))
+    arr = lambda p, k, t: np.ctypeslib.as_array(p, shape=(k,)).astype(t).copy() if k else np.zeros(0, dtype=t)
+    dia_ = arr(dia, m + 1, np.int64)
+    oia_ = arr(oia, no.value + 1, np.int64)
+    return (dia_, arr(dja, int(dia_[-1]), np.int64), arr(da, int(dia_[-1]), np.float64), oia_, arr(oja, int(oia_[-1]), np.int64),
+            arr(oa, int(oia_[-1]), np.float64), arr(orow, no.value, np.int64))
+
+
 def MatStorageInfo(A):
     """Device storage of an AIJ matrix: kind (3 = packed dictionary-coded tiles), matrix bytes streamed per SpMV, coded / all tiles."""
     kind, coded, tiles = C.c_int(), C.c_int(), C.c_int()

@@ -1379,6 +1379,22 @@ PetscErrorCode MatB200GetHaloInfo(Mat A, PetscInt *nghost, const PetscInt **garr
   return 0;
 }
 
+PetscErrorCode MatB200GetHostSplit(Mat A, const PetscInt **dia, const PetscInt **dja, const PetscScalar **da, PetscInt *noffrows, const PetscInt **oia,
+                                   const PetscInt **oja, const PetscScalar **oa, const PetscInt **orow)
+{
+  if (!A || A->kind != MK_AIJ || !A->halo || !A->halo->host) return err(PETSC_ERR_ARG_WRONGSTATE, "no host split (sequential matrix, or already on the device)");
+  HaloPlan::HostSplit *S = A->halo->host;
+  if (dia) *dia = S->dia.data();
+  if (dja) *dja = S->dja.data();
+  if (da) *da = S->da.data();
+  if (noffrows) *noffrows = (PetscInt)S->orow.size();
+  if (oia) *oia = S->oia.data();
+  if (oja) *oja = S->oja.data();
+  if (oa) *oa = S->oa.data();
+  if (orow) *orow = S->orow.data();
+  return 0;
+}
+
 PetscErrorCode MatB200GetStorageInfo(Mat A, PetscInt *kind, PetscReal *stream_bytes, PetscInt *coded_tiles, PetscInt *tiles)
 {
   if (!A || A->kind != MK_AIJ) return err(PETSC_ERR_ARG_WRONG, "MatB200GetStorageInfo: AIJ matrix expected");

@@ -67,6 +67,21 @@ def _worker(rank, size, port, kind, ret):
     # 3. boundary rows = rows with at least one ghost column
     nb = sum(1 for r in range(pr.n) if np.any((pr.ja[pr.ia[r]:pr.ia[r + 1]] < r0) | (pr.ja[pr.ia[r]:pr.ia[r + 1]] >= r1)))
     assert info["nboundary"] == nb
+    # 3b. the split itself: diagonal block (local columns) + off-diagonal rows (ghost-buffer columns) put together again give back
+    #     every local row exactly, entries in their original order within each block
+    dia, dja, da, oia, oja, oa, orow = P.MatGetHostSplit(A, pr.n)
+    garr = np.asarray(info["garray"], dtype=np.int64)
+    opos = {int(r): k for k, r in enumerate(orow)}
+    assert len(orow) == nb and np.all(np.diff(orow) > 0)
+    for r in range(pr.n):
+        cols, vals = np.asarray(pr.ja[pr.ia[r]:pr.ia[r + 1]], dtype=np.int64), np.asarray(pr.a[pr.ia[r]:pr.ia[r + 1]])
+        loc = (cols >= r0) & (cols < r1)
+        assert np.array_equal(dja[dia[r]:dia[r + 1]] + r0, cols[loc]) and np.array_equal(da[dia[r]:dia[r + 1]], vals[loc])
+        if r in opos:
+            k = opos[r]
+            assert np.array_equal(garr[oja[oia[k]:oia[k + 1]]], cols[~loc]) and np.array_equal(oa[oia[k]:oia[k + 1]], vals[~loc])
+        else:
+            assert loc.all()
     # 4. emulate the halo exchange with gloo following the plan, then the split SpMV must equal the global one
     rng = np.random.default_rng(7)
     xg = rng.standard_normal(n_glob)
