@@ -1085,7 +1085,17 @@ PetscErrorCode MatCreateMPIAIJWithArrays(MPI_Comm comm, PetscInt m, PetscInt n, 
   const double   t_s0 = wall_now();
   HaloPlan      *H = new HaloPlan;
   A->halo          = H;
-  // ghosts (host threads: the split is O(nnz) and sits inside the e2e path of multi-GPU runs)
+  // pass 1 (host threads: the split is O(nnz) and sits inside the e2e path of multi-GPU runs): per row, how many entries fall into the
+  // diagonal block / outside it, and which columns outside it occur (the ghosts)
+  H->host = new HaloPlan::HostSplit;
+  std::vector<int>       &dia = H->host->dia, &oia = H->host->oia, &oja = H->host->oja, &orow = H->host->orow;
+  std::vector<double>    &oa = H->host->oa;
+  HaloPlan::UVec<int>    &dja = H->host->dja;
+  HaloPlan::UVec<double> &da = H->host->da;
+  std::vector<unsigned char> &skip = H->host->skip;
+  dia.assign(m + 1, 0);
+  skip.assign(std::max<PetscInt>(m, 1), 0);
+  std::vector<int>      ocnt(m + 1, 0);
   std::vector<PetscInt> gh;
   {
     std::vector<std::vector<PetscInt>> part;
@@ -1095,8 +1105,20 @@ PetscErrorCode MatCreateMPIAIJWithArrays(MPI_Comm comm, PetscInt m, PetscInt n, 
       part.resize(omp_get_num_threads());
       std::vector<PetscInt> &mine = part[omp_get_thread_num()];
 #pragma omp for schedule(static)
-      for (int64_t k = 0; k < nnz; k++)
-        if (j[k] < c0 || j[k] >= c1) mine.push_back(j[k]);
+      for (PetscInt r = 0; r < m; r++) {
+        int nd = 0, no = 0;
+        for (PetscInt k = i[r]; k < i[r + 1]; k++) {
+          if (j[k] >= c0 && j[k] < c1) {
+            nd++;
+          } else {
+            no++;
+            mine.push_back(j[k]);
+          }
+        }
+        dia[r + 1]  = nd;
+        ocnt[r + 1] = no;
+        skip[r]     = no > 0;
+      }
       std::sort(mine.begin(), mine.end());
       mine.erase(std::unique(mine.begin(), mine.end()), mine.end());
     }
@@ -1106,27 +1128,7 @@ PetscErrorCode MatCreateMPIAIJWithArrays(MPI_Comm comm, PetscInt m, PetscInt n, 
   gh.erase(std::unique(gh.begin(), gh.end()), gh.end());
   H->garray = gh;
   const double t_s1 = wall_now();
-  // split: count, prefix-sum, fill
-  H->host = new HaloPlan::HostSplit;
-  std::vector<int>       &dia = H->host->dia, &oia = H->host->oia, &oja = H->host->oja, &orow = H->host->orow;
-  std::vector<double>    &oa = H->host->oa;
-  HaloPlan::UVec<int>    &dja = H->host->dja;
-  HaloPlan::UVec<double> &da = H->host->da;
-  std::vector<unsigned char> &skip = H->host->skip;
-  dia.assign(m + 1, 0);
-  skip.assign(std::max<PetscInt>(m, 1), 0);
-  std::vector<int> ocnt(m + 1, 0);
-#pragma omp parallel for schedule(static)
-  for (PetscInt r = 0; r < m; r++) {
-    int nd = 0, no = 0;
-    for (PetscInt k = i[r]; k < i[r + 1]; k++) {
-      if (j[k] >= c0 && j[k] < c1) nd++;
-      else no++;
-    }
-    dia[r + 1]  = nd;
-    ocnt[r + 1] = no;
-    skip[r]     = no > 0;
-  }
+  // prefix sums, then pass 2 fills both blocks
   for (PetscInt r = 0; r < m; r++) {
     dia[r + 1] += dia[r];
     ocnt[r + 1] += ocnt[r];
@@ -1208,7 +1210,7 @@ PetscErrorCode MatCreateMPIAIJWithArrays(MPI_Comm comm, PetscInt m, PetscInt n, 
     H->send_idx = sidx;
   }
   if (verbose_timing())
-    fprintf(stderr, "[permon_b200] rank %d host split of %d rows / %lld nnz: ghosts %.1f ms, diag/off-diag split %.1f ms, plan exchange %.1f ms\n", rank, (int)m,
+    fprintf(stderr, "[permon_b200] rank %d host split of %d rows / %lld nnz: count + ghosts %.1f ms, fill %.1f ms, plan exchange %.1f ms\n", rank, (int)m,
             (long long)nnz, 1e3 * (t_s1 - t_s0), 1e3 * (t_s2 - t_s1), 1e3 * (wall_now() - t_s2));
   A->Ad.n = m;   // sizes are known; the arrays reach the device on first use (mat_ensure_device)
   A->Ad.ncols = n;
