@@ -1,22 +1,26 @@
 #!/usr/bin/env python
 """bench.py -- MPGP iterations/second on the named configurations (BASELINE.json), one process per GPU.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2|c2x|c3|c1]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload auto|c3|c2|c2x|c2r|c5|c4|...]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N --steps K --warmup W
 
 A "step" is ONE MPGP iteration (SpMV + fused update + direction update, src/qps/impls/mpgp/mpgp.c:511-641) of a
 QPSSolve that runs through the C ABI of libpermon_b200.so.  W warm-up iterations, then exactly K timed ones:
 
-  value  device-resident leg: CSR + vectors already in HBM, CUDA events on the library's stream, max over ranks
-  e2e    same K iterations through the reference-facing calls with HOST buffers: MatCreate...WithArrays (H2D of the
-         CSR), VecCreate...WithArray, QPSSetUp (power method), QPSSolve, VecGetArrayRead (D2H of x) all inside the
-         timed region (wall clock around the calls, device synchronised on both sides)
-  roofline      K_A (the fused SpMV) timed per launch with CUDA events inside a repeat of the timed region
+  value         device-resident leg: matrix + vectors already in HBM, CUDA events on the library's stream, max over ranks
+  e2e           a fresh solve of K iterations through the reference-facing calls with HOST (pinned) buffers:
+                MatCreate...WithArrays (re-code + H2D), VecCreate...WithArray, QPSSetUp (power method), QPSSolve,
+                VecGetArrayRead (D2H of x), all inside the timed region (wall clock, device synchronised on both sides)
+  roofline      every fused kernel timed per launch with CUDA events in a repeat of the timed region; the object describes
+                the kernel with the largest share of the step, `per_kernel` lists all of them (working launches only)
   cpu_baseline  the CPU oracle (restatement of the reference's un-fused PETSc call sequence, OpenMP threads standing in
-                for MPI ranks) on a bounded sample of the same workload, on this box's host cores
+                for MPI ranks) on a bounded sample of the same workload, on this box's host cores (rank 0)
+  parity        GPU iterate after Kp iterations from x0 against the oracle's iterate after the same Kp iterations of the
+                same full-size problem: relx, objective, step mix, active set (rank 0 gathers x at N > 1)
 
-N = 1 runs C2 (2-D obstacle 4096^2, 16.7 M dofs); N > 1 runs C3 (3-D obstacle 512^3, 134 M dofs) row-partitioned in
-z-slabs, strong scaling (the global problem is fixed).
+The headline workload is the SAME at every N: C3 (3-D obstacle 512^3, 134 M dofs, z-slab row partition, strong scaling).
+The N = 1 line additionally carries C2 (2-D obstacle 4096^2, 16.7 M dofs) as a nested `c2` object with its own
+roofline / e2e / parity / cpu_baseline.
 """
 from __future__ import annotations
 
@@ -35,6 +39,8 @@ sys.path.insert(0, ROOT)
 
 METRIC = "mpgp_iterations_per_second"
 UNIT = "it/s"
+ASTOL = 10 * 2.2204460492503131e-16      # QPC active-set tolerance (qpc.c:28)
+L2_NOTE = "inputs larger than L2 (every kernel streams >= 3 vectors of 8n bytes, n >= 8.4M rows per GPU, vs 126 MB L2)"
 
 
 def peaks():
@@ -45,18 +51,25 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def workload_spec(name, n_gpus):
+WORKLOADS = {
+    "c1": dict(kind="2d", N=256, bscale=-30.0, label="C1 2-D obstacle 256^2 (65 536 dofs), 5-point Laplacian, lower bound"),
+    "c2": dict(kind="2d", N=4096, bscale=-30.0, label="C2 2-D obstacle 4096^2 (16.7M dofs), 5-point Laplacian, lower bound"),
+    "c2x": dict(kind="2d", N=4096, bscale=-100.0, label="C2x expansion-heavy 2-D obstacle 4096^2, b=-100h^2"),
+    "c2r": dict(kind="2d", N=4096, bscale=-30.0, scaled=True,
+                label="C2r 2-D obstacle 4096^2 with the Hessian scaled D*A*D (every value distinct: incompressible, 12 B per non-zero)"),
+    "c3": dict(kind="3d", N=512, label="C3 3-D obstacle 512^3 (134M dofs), 7-point Laplacian, lower bound, z-slab row partition"),
+    "c3s": dict(kind="3d", N=256, label="3-D obstacle 256^3 (16.7M dofs) stand-in"),
+    "c5": dict(kind="var", N=256, label="C5 variable-coefficient 3-D Laplacian 256^3 (16.7M dofs, contrast 1e4), lb and ub arrays, ~50% active at the solution"),
+    "c5s": dict(kind="var", N=128, label="variable-coefficient 3-D Laplacian 128^3 stand-in"),
+    "t2d": dict(kind="2d", N=512, bscale=-30.0, label="tiny 2-D obstacle 512^2 (harness self-test)"),
+    "t3d": dict(kind="3d", N=64, label="tiny 3-D obstacle 64^3 (harness self-test)"),
+}
+
+
+def workload_spec(name):
     if name == "auto":
-        name = "c2" if n_gpus == 1 else "c3"
-    spec = {
-        "c1": dict(kind="2d", N=256, bscale=-30.0, label="C1 2-D obstacle 256^2 (65 536 dofs), 5-point Laplacian, lower bound"),
-        "c2": dict(kind="2d", N=4096, bscale=-30.0, label="C2 2-D obstacle 4096^2 (16.7M dofs), 5-point Laplacian, lower bound"),
-        "c2x": dict(kind="2d", N=4096, bscale=-100.0, label="C2x expansion-heavy 2-D obstacle 4096^2, b=-100h^2"),
-        "c3": dict(kind="3d", N=512, label="C3 3-D obstacle 512^3 (134M dofs), 7-point Laplacian, lower bound, z-slab row partition"),
-        "c3s": dict(kind="3d", N=256, label="3-D obstacle 256^3 (16.7M dofs) stand-in"),
-        "c5": dict(kind="var", N=256, label="C5 variable-coefficient 3-D Laplacian 256^3 (16.7M dofs, contrast 1e4), lb and ub arrays, ~50% active at the solution"),
-        "c5s": dict(kind="var", N=128, label="variable-coefficient 3-D Laplacian 128^3 stand-in"),
-    }[name]
+        name = "c3"
+    spec = dict(WORKLOADS[name])
     spec["name"] = name
     return spec
 
@@ -69,7 +82,7 @@ def generate(spec, rank, size):
         N = spec["N"]
         starts = PR.row_partition(N * N, size, align=N)
         step = max(N, (2_000_000 // N) * N)
-        make = lambda r0, r1: PR.obstacle2d(N, spec["bscale"], rows=(r0, r1))
+        make = lambda r0, r1: PR.obstacle2d(N, spec["bscale"], rows=(r0, r1), scaled=bool(spec.get("scaled")))
     else:
         N = spec["N"]
         P = N * N
@@ -98,6 +111,7 @@ def generate(spec, rank, size):
     pr.ub = np.concatenate([c.ub for c in chunks]) if chunks[0].ub is not None else None
     pr.x0 = np.zeros(rows[1] - rows[0])
     pr.r0, pr.r1 = rows
+    pr.meta = {}
     return pr
 
 
@@ -186,109 +200,81 @@ def algorithmic_bytes(n, nnz, counts, both_bounds=False, matrix_bytes=None):
 
 
 # ----------------------------------------------------------------------------------------------------------
-# reference arm / cpu baseline: the oracle on the host cores
+# the oracle on the host cores: reference arm, cpu_baseline and the parity checker
 # ----------------------------------------------------------------------------------------------------------
-def run_oracle(pr, warmup, steps, budget_s, maxeig=None):
+def oracle_window(pr, Kp, maxeig=None):
+    """Kp MPGP iterations from x0 on all host cores; returns (x, dict).  The timed region is the iteration loop (the power
+    method of the set-up is outside, as on the GPU side's `value`)."""
     from oracle import oracle_py as O
     threads = os.cpu_count() or 1
     op = O.Operator(pr.ia, pr.ja, pr.a)
     bx = O.BoxC(pr.n, pr.lb, pr.ub)
-    kw = dict(nthreads=threads)
+    kw = dict(nthreads=threads, max_it=Kp - 1, rtol=1e-30, atol=1e-300)
     if maxeig:
         kw["maxeig"] = float(maxeig)
-    x, r0 = O.mpgp_solve(op, pr.b, bx, pr.x0, O.mpgp_opts(max_it=max(warmup - 1, 0), **kw))
-    t_it = r0["seconds"] / max(r0["its"], 1)
-    n_t = int(max(5, min(steps, budget_s / max(t_it, 1e-9))))
-    x2, r = O.mpgp_solve(op, pr.b, bx, x, O.mpgp_opts(max_it=n_t - 1, maxeig=r0["maxeig"], nthreads=threads))
-    its = r["its"]
-    return dict(value=its / r["seconds"], its=its, seconds=r["seconds"], threads=threads, counts={k: r[k] for k in ("ncg", "nexp", "nprop", "nmv")},
-                sample=f"{its} MPGP iterations (after {r0['its']} warm-up iterations) of the full-size workload, {threads} OpenMP threads standing in for MPI ranks")
+    x, r = O.mpgp_solve(op, pr.b, bx, pr.x0, O.mpgp_opts(**kw))
+    f = O.objective(op, pr.b, x)
+    return x, dict(value=r["its"] / r["seconds"], its=r["its"], seconds=r["seconds"], threads=threads, maxeig=r["maxeig"], objective=f,
+                   counts={k: r[k] for k in ("ncg", "nexp", "nprop", "nmv")}, op=op)
 
 
-def short_device_leg(P, torch, dev, stream, pr, W, K):
-    """device-resident MPGP window on one GPU, no profiling / e2e: used for the N = 1 point of the C3 strong-scaling series"""
-    A = P.MatCreateAIJ(pr.ia, pr.ja, pr.a, ncols_local=pr.n)
-    d = {k: torch.from_numpy(np.ascontiguousarray(getattr(pr, k))).to(dev) for k in ("b", "lb")}
-    d["x"] = torch.zeros(pr.n, dtype=torch.float64, device=dev)
-    vb, vlb, vx = (P.VecFromDevicePointer(d[k].data_ptr(), pr.n) for k in ("b", "lb", "x"))
-    qp = P.QPCreate()
-    P.QPSetOperator(qp, A); P.QPSetRhs(qp, vb); P.QPSetInitialVector(qp, vx); P.QPSetBox(qp, None, vlb, None)
-    qps = P.QPSCreate()
-    P.QPSSetType(qps, "mpgp"); P.QPSSetQP(qps, qp); P.QPSSetAutoPostSolve(qps, False)
-    P.QPSSetTolerances(qps, rtol=1e-30, atol=1e-300, maxits=W - 1)
-    P.QPSSetUp(qps)
-    P.QPSSolve(qps)
-    c0 = P.QPSMPGPGetStepCounts(qps)
-    P.QPSSetTolerances(qps, maxits=K - 1)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    torch.cuda.synchronize()
-    e0.record(stream)
-    P.QPSSolve(qps)
-    e1.record(stream)
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1)
-    assert P.QPSGetIterationNumber(qps) == K
-    c1 = P.QPSMPGPGetStepCounts(qps)
-    P.QPSDestroy(qps); P.QPDestroy(qp)
-    for v in (vb, vlb, vx):
-        P.VecDestroy(v)
-    P.MatDestroy(A)
-    del d
-    torch.cuda.empty_cache()
-    return dict(value=round(K / (ms * 1e-3), 2), unit=UNIT, ms_per_step=round(ms / K, 5), steps=K, warmup=W, step_mix={k: c1[k] - c0[k] for k in c1})
+def oracle_sample_size(n_global, nnz_global, K, budget_s):
+    """iterations the CPU sample may take: ~5.5e-10 s per (non-zero + 8 dofs) and iteration on 16 cores (measured: C2 45 ms, C3 ~0.45 s)"""
+    cores = os.cpu_count() or 1
+    t_it = 6.0e-10 * (nnz_global + 8.0 * n_global) * 16.0 / max(cores, 1)
+    return int(max(5, min(K, budget_s / max(t_it, 1e-9))))
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=2000)
-    ap.add_argument("--warmup", type=int, default=50)
-    ap.add_argument("--impl", default="ours")
-    ap.add_argument("--workload", default="auto")
-    ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--no-scaling-base", action="store_true")
-    ap.add_argument("--cpu-budget", type=float, default=20.0)
-    args = ap.parse_args()
-    K, W = max(1, args.steps), max(3, args.warmup)
-    rank = int(os.environ.get("RANK", "0"))
-    size = int(os.environ.get("WORLD_SIZE", "1"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    spec = workload_spec(args.workload, max(args.gpus, size))
+def parity_compare(pr, x_gpu, f_gpu, counts_gpu, x_cpu, res_cpu, Kp):
+    """BASELINE.json tolerances at the cut after Kp iterations (SURVEY 8d 'truncated runs')"""
+    from oracle import oracle_py as O
+    nx = float(np.linalg.norm(x_cpu))
+    relx = float(np.linalg.norm(x_gpu - x_cpu) / nx) if nx > 0 else float(np.linalg.norm(x_gpu - x_cpu))
+    f_cpu = res_cpu["objective"]
+    f_gpu_on_cpu = O.objective(res_cpu["op"], pr.b, np.ascontiguousarray(x_gpu))      # same evaluator on both iterates
+    obj_rel = abs(f_gpu_on_cpu - f_cpu) / max(abs(f_cpu), 1e-300)
+    mism = 0
+    for bound in (pr.lb, pr.ub):
+        if bound is None:
+            continue
+        dg, dc = np.abs(x_gpu - bound), np.abs(x_cpu - bound)
+        diff = (dg <= ASTOL) != (dc <= ASTOL)
+        mism += int(np.count_nonzero(diff & (np.maximum(dg, dc) > 1e-12)))       # excused: within 1e-12 of the bound on both sides
+    cg = {k: int(counts_gpu[k]) for k in ("ncg", "nexp", "nprop", "nmv")}
+    cc = {k: int(res_cpu["counts"][k]) for k in cg}
+    out = dict(iterations=Kp, relx=relx, objective_rel_diff=obj_rel, objective_cpu=f_cpu, objective_gpu_x_cpu_evaluator=f_gpu_on_cpu,
+               active_set_mismatches=mism, step_mix_gpu=cg, step_mix_cpu=cc, step_mix_equal=(cg == cc),
+               x_norm2_cpu=nx, x_sum_gpu=float(np.sum(x_gpu)), x_sum_cpu=float(np.sum(x_cpu)),
+               tolerances=dict(relx=1e-7, objective_rel_diff=1e-10, active_set_mismatches=0))
+    if f_gpu is not None:
+        out["objective_gpu"] = f_gpu
+        out["objective_gpu_rel_diff"] = abs(f_gpu - f_cpu) / max(abs(f_cpu), 1e-300)
+    out["ok"] = bool(relx <= 1e-7 and obj_rel <= 1e-10 and mism == 0 and cg == cc)
+    return out
 
-    if args.impl == "reference":
-        # the reference's own CPU implementation cannot be built here (PETSc/MPI absent): time the oracle port
-        if rank != 0:
-            return
-        pr = generate(spec, 0, 1)
-        res = run_oracle(pr, W, K, budget_s=60.0)
-        line = dict(metric=METRIC, value=res["value"], unit=UNIT, n_gpus=args.gpus, steps=K, warmup=W, ms_per_step=1e3 / res["value"],
-                    higher_is_better=True, scaling="strong", vs_baseline=None, dtype="f64", data="synthetic", impl="reference",
-                    config=dict(workload=spec["label"], n=pr.N, nnz=pr.nnz, step_mix=res["counts"]),
-                    cpu_baseline=dict(value=res["value"], unit=UNIT, cores=res["threads"], kind="port", sample=res["sample"]),
-                    e2e=dict(value=res["value"], unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
-        print(json.dumps(line), flush=True)
-        return
 
-    import torch
-    from permon_b200 import api as P
+def load_traffic(workload_name):
+    """DRAM bytes per launch from the committed `ncu --set full` captures (never measured inside a bench run)"""
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+        e = tj.get(workload_name)
+        if e:
+            return e["dram_bytes_per_launch"], e["source"]
+    except Exception:
+        pass
+    return {}, None
 
-    if P.device_count() == 0:
-        raise SystemExit("bench.py: no CUDA device -- the product has no CPU path")
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    P.call("PermonB200SetDevice", local_rank)
-    P.initialize()
-    if size > 1:
-        import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=dev)
-        idt = torch.zeros(128, dtype=torch.uint8, device=dev)
-        if rank == 0:
-            idt.copy_(torch.frombuffer(bytearray(P.get_unique_id()), dtype=torch.uint8))
-        dist.broadcast(idt, 0)
-        P.comm_init_rank(size, rank, bytes(idt.cpu().numpy().tobytes()))
-    stream = torch.cuda.current_stream()
-    P.set_stream(stream.cuda_stream)
+
+# ----------------------------------------------------------------------------------------------------------
+# one workload, all legs
+# ----------------------------------------------------------------------------------------------------------
+class Env:
+    pass
+
+
+def measure(env, spec, K, W, want_e2e=True, want_cpu=True, want_parity=True, cpu_budget=20.0, sampler=None):
+    P, torch, dev, stream, rank, size = env.P, env.torch, env.dev, env.stream, env.rank, env.size
+    dist = env.dist
 
     def barrier():
         torch.cuda.synchronize()
@@ -303,16 +289,24 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    def sum_over_ranks(vals):
+        if size == 1:
+            return [float(v) for v in vals]
+        t = torch.tensor(list(vals), dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return [float(v) for v in t.cpu()]
+
     t_gen = time.time()
     pr = generate(spec, rank, size)
     t_gen = time.time() - t_gen
     n_loc, nnz_loc = pr.n, pr.nnz
-    # pinned host buffers (the e2e leg copies from these)
+    n_glob, nnz_glob = [int(v) for v in sum_over_ranks([n_loc, nnz_loc])]
     vec_keys = ("b", "lb") + (("ub",) if pr.ub is not None else ())
+    # pinned host buffers (the e2e leg copies from these)
     host = {k: torch.from_numpy(np.ascontiguousarray(getattr(pr, k))).pin_memory() for k in ("ia", "ja", "a") + vec_keys}
     both = pr.ub is not None
 
-    def make_solver(device_resident, keep):
+    def make_solver(device_resident):
         """QP + QPS through the C ABI; returns handles"""
         h = {}
         if device_resident:
@@ -338,7 +332,6 @@ def main():
         P.QPSSetQP(qps, qp)
         P.QPSSetAutoPostSolve(qps, False)
         h["qp"], h["qps"] = qp, qps
-        keep.append(h)
         return h
 
     def destroy(h):
@@ -347,16 +340,14 @@ def main():
             P.VecDestroy(h[k])
         P.MatDestroy(h["A"])
 
-    keep = []
-    sampler = ClockSampler(local_rank)
-    sampler.start()
     # ---------------- device-resident leg -----------------------------------------------------------------
-    h = make_solver(True, keep)
+    h = make_solver(True)
     P.QPSSetTolerances(h["qps"], rtol=1e-30, atol=1e-300, maxits=W - 1)     # never converge inside the window
     P.QPSSetUp(h["qps"])                                                      # upload done, power method done
     maxeig = P.QPSMPGPGetOperatorMaxEigenvalue(h["qps"])
     storage = P.MatStorageInfo(h["A"])
-    sampler.wait_first()
+    if sampler:
+        sampler.wait_first()
     P.QPSSolve(h["qps"])                                                      # W warm-up iterations
     assert P.QPSGetIterationNumber(h["qps"]) == W, (P.QPSGetIterationNumber(h["qps"]), W)
     x_after_warmup = h["dev"]["x"].clone()
@@ -365,13 +356,14 @@ def main():
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     launches0 = P.launch_count()
     barrier()
-    sampler.window_open()
+    if sampler:
+        sampler.window_open()
     e0.record(stream)
     P.QPSSolve(h["qps"])                                                      # exactly K timed iterations
     e1.record(stream)
     barrier()
-    sampler.window_close()
-    clocks = sampler.stop()
+    if sampler:
+        sampler.window_close()
     ms = max_over_ranks(e0.elapsed_time(e1))
     launches = P.launch_count() - launches0
     its = P.QPSGetIterationNumber(h["qps"])
@@ -380,14 +372,14 @@ def main():
     counts = {k: c_all[k] - c_warm[k] for k in c_all}
     value = K / (ms * 1e-3)
 
-    # ---------------- roofline of the dominant kernel (K_A), measured in a repeat of the timed region ----------
+    # ---------------- roofline: every fused kernel timed per launch in a repeat of the timed region ----------
     h["dev"]["x"].copy_(x_after_warmup)
     barrier()
     P.profile_begin()
     P.QPSSolve(h["qps"])
     prof = P.profile_end()
     if os.environ.get("PERMON_B200_TIMELINE"):
-        P.call("PermonB200ProfileDump", (os.environ["PERMON_B200_TIMELINE"] + f".rank{rank}.csv").encode())
+        P.call("PermonB200ProfileDump", (os.environ["PERMON_B200_TIMELINE"] + f".{spec['name']}.rank{rank}.csv").encode())
     barrier()
     peak, peak_src = peaks()
     nb = 1 + (1 if both else 0)                      # bound vectors
@@ -401,39 +393,31 @@ def main():
         "K_A' spmv+grad+split": M + 8 * n_loc * (4 + nb),                                                 # x b bounds -> g p
         "K_C direction": 8 * n_loc * 3.125,                                                                # g, byte mask, p -> p
     }
-    klaunch = {"K_A spmv+dots+feas": None, "K_B update+split": None, "K_A' spmv+grad+split": n_ex, "K_C direction": n_cg}
+    # launches that did work, by the step counters: K_A and K_B once per iteration, K_A' per expansion step, K_C (sweep) per CG /
+    # proportioning step.  The per-launch timings classify the same way (early exits take a few microseconds): both are reported.
+    expect = {"K_A spmv+dots+feas": n_cg + n_ex, "K_B update+split": n_cg + n_ex, "K_A' spmv+grad+split": n_ex, "K_C direction": n_cg}
     per_kernel = {}
     for fam, byts in kbytes.items():
         pf = prof.get(fam)
-        if not pf or not pf["launches"]:
+        if not pf or not pf["launches"] or not expect[fam]:
             continue
-        real = klaunch[fam] if klaunch[fam] is not None else pf["launches"]   # launches that did work (the rest exit at once)
-        if fam == "K_A spmv+dots+feas" and size > 1:
-            real = pf["launches"] / 2                                           # diagonal pass + ghost pass per SpMV
-        if not real:
-            continue
-        avg = pf["total_ms"] / real
+        real = expect[fam]
+        work_ms = pf["working_ms"] if pf["working_launches"] else pf["total_ms"]
+        avg = work_ms / real
         gbs = byts / (avg * 1e-3) / 1e9
-        per_kernel[fam] = dict(total_ms=round(pf["total_ms"], 3), working_launches=int(real), avg_ms=round(avg, 5), bytes_per_launch=int(byts),
-                               achieved_gbs=round(gbs, 1), frac_of_measured_peak=round(gbs / peak, 4))
+        per_kernel[fam] = dict(total_ms=round(pf["total_ms"], 3), launches=int(pf["launches"]), working_launches=int(real),
+                               working_launches_by_timing=int(pf["working_launches"]), working_ms=round(work_ms, 3), avg_ms=round(avg, 5),
+                               bytes_per_launch=int(byts), achieved_gbs=round(gbs, 1), frac_of_measured_peak=round(gbs / peak, 4))
     fam_ms = {k: round(v["total_ms"], 3) for k, v in prof.items() if v["launches"]}
     total_prof_ms = sum(v["total_ms"] for v in prof.values())
-    dom = max(per_kernel, key=lambda k: per_kernel[k]["total_ms"]) if per_kernel else None
-    dk = per_kernel.get(dom, dict(achieved_gbs=0.0, avg_ms=0.0, bytes_per_launch=0, working_launches=0, total_ms=0.0))
+    dom = max(per_kernel, key=lambda k: per_kernel[k]["working_ms"]) if per_kernel else None
+    dk = per_kernel.get(dom, dict(achieved_gbs=0.0, avg_ms=0.0, bytes_per_launch=0, working_launches=0, working_ms=0.0))
     csr_M = 12 * nnz_loc + 4 * (n_loc + 1)
-    # DRAM traffic of the dominant kernel: taken from the committed `ncu --set full` capture of the same workload (never measured
-    # inside a bench run); null when no capture exists for this workload / rank count
-    traffic, traffic_src = None, None
-    try:
-        tj = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r1b_ncu_traffic.json")))
-        if size == 1 and spec["label"].startswith(tj["workload"] + " ") and dom in tj["dram_bytes_per_launch"]:
-            traffic, traffic_src = tj["dram_bytes_per_launch"][dom], tj["source"]
-    except Exception:
-        pass
-    roofline = dict(bound="hbm", kernel=dom, achieved=dk["achieved_gbs"], peak=peak, unit="GB/s", frac=round(dk["achieved_gbs"] / peak, 4), traffic=traffic,
-                    traffic_source=traffic_src,
+    tr, tr_src = load_traffic(spec["name"]) if size == 1 else ({}, None)
+    roofline = dict(bound="hbm", kernel=dom, achieved=dk["achieved_gbs"], peak=peak, unit="GB/s", frac=round(dk["achieved_gbs"] / peak, 4),
+                    traffic=tr.get(dom), traffic_source=tr_src if tr.get(dom) else None,
                     peak_source=peak_src, launches=dk["working_launches"], avg_launch_ms=dk["avg_ms"], algorithmic_bytes_per_launch=dk["bytes_per_launch"],
-                    kernel_share_of_step=round(dk["total_ms"] / total_prof_ms, 4) if total_prof_ms else None,
+                    kernel_share_of_step=round(dk["working_ms"] / total_prof_ms, 4) if total_prof_ms else None,
                     bytes_note="bytes of the layout the kernels stream (packed matrix tiles + fp64 vectors); with the CSR formula of SURVEY 8d K_A / K_A' "
                                "would count csr_matrix_bytes instead of matrix_bytes",
                     matrix_bytes=int(M), csr_matrix_bytes=int(csr_M), per_kernel=per_kernel, family_ms=fam_ms)
@@ -442,79 +426,198 @@ def main():
     whole_iter_gbs = step_bytes / (ms * 1e-3) / 1e9
     whole_iter_gbs_csr = step_bytes_csr / (ms * 1e-3) / 1e9
     destroy(h)
-    keep.clear()
     del h, x_after_warmup
     torch.cuda.empty_cache()
 
     # ---------------- e2e leg: host buffers, every copy inside the timed region ------------------------------
-    e2e = None
-    if not args.no_e2e:
-        keep2 = []
+    e2e, h2 = None, None
+    if want_e2e or want_parity:
         host_in = sum(host[k].numel() * host[k].element_size() for k in host) + n_loc * 8      # CSR + b, bounds, x0 handed over in host memory
         d2h = n_loc * 8
         barrier()
         t0 = time.perf_counter()
-        h2 = make_solver(False, keep2)
+        h2 = make_solver(False)
         P.QPSSetTolerances(h2["qps"], rtol=1e-30, atol=1e-300, maxits=K - 1)
         P.QPSSolve(h2["qps"])                                                 # set-up (upload, power method) + K iterations
         P.VecSyncToHost(h2["x"])                                              # D2H of the iterate into the caller's (pinned) x buffer
         torch.cuda.synchronize()
         t1 = time.perf_counter()
-        xres = h2["xh"].numpy()
         barrier()
         te = max_over_ranks(t1 - t0)
         assert P.QPSGetIterationNumber(h2["qps"]) == K
         # what crosses PCIe: the matrix as the library stores it (packed tiles) + the vectors; the CSR itself is read on the host only
         h2d = P.MatStorageInfo(h2["A"])["stream_bytes"] + sum(host[k].numel() * host[k].element_size() for k in vec_keys) + n_loc * 8
-        e2e = dict(value=K / te, unit=UNIT, h2d_bytes_per_step=h2d / K, d2h_bytes_per_step=d2h / K, seconds=round(te, 4), host_input_bytes=host_in,
-                   note="host CSR + vectors -> re-code + upload + power-method set-up + K iterations + one download per QPSSolve; bytes are the totals of the solve divided by K",
-                   x_checksum=float(np.sum(xres)))
+        e2e = dict(value=K / te, unit=UNIT, h2d_bytes_per_step=h2d / K, d2h_bytes_per_step=d2h / K, seconds=round(te, 4),
+                   seconds_outside_iterations=round(te - ms * 1e-3, 4), host_input_bytes=host_in,
+                   x_checksum=float(sum_over_ranks([float(np.sum(h2["xh"].numpy()))])[0]),
+                   note="host CSR + vectors -> re-code + upload + power-method set-up + K iterations + one download per QPSSolve; bytes are the totals of the solve divided by K")
+
+    # ---------------- parity + CPU baseline (oracle on rank 0, same full-size problem) -----------------------
+    cpu, parity = None, None
+    if want_parity or want_cpu:
+        Kp = oracle_sample_size(n_glob, nnz_glob, K, cpu_budget)
+        x_gpu, f_gpu, counts_gpu = None, None, None
+        if want_parity:
+            # the GPU iterate after Kp iterations from x0: the e2e solve itself when Kp == K, else one more (short) solve on its handles
+            if Kp != K:
+                P.VecSetArray(h2["x"], np.zeros(n_loc))
+                P.QPSSetTolerances(h2["qps"], maxits=Kp - 1)
+                c0 = P.QPSMPGPGetStepCounts(h2["qps"])
+                P.QPSSolve(h2["qps"])
+                P.VecSyncToHost(h2["x"])
+                torch.cuda.synchronize()
+                c1 = P.QPSMPGPGetStepCounts(h2["qps"])
+                counts_gpu = {k: c1[k] - c0[k] for k in c1}
+            else:
+                counts_gpu = P.QPSMPGPGetStepCounts(h2["qps"])
+            f_gpu = P.QPComputeObjective(h2["qp"], h2["x"])
+            x_loc = h2["xh"].numpy().copy()
+            if size == 1:
+                x_gpu = x_loc
+            else:
+                # rank 0 collects the slabs (NCCL send/recv of device copies)
+                sizes = [int(v) for v in env.all_gather_int(n_loc)]
+                mine = torch.from_numpy(x_loc).to(dev)
+                if rank == 0:
+                    parts = [x_loc]
+                    for r in range(1, size):
+                        buf = torch.empty(sizes[r], dtype=torch.float64, device=dev)
+                        dist.recv(buf, src=r)
+                        parts.append(buf.cpu().numpy())
+                    x_gpu = np.concatenate(parts)
+                else:
+                    dist.send(mine, dst=0)
+                del mine
+        if rank == 0:
+            t_or = time.time()
+            prf = pr if size == 1 else generate(spec, 0, 1)        # the whole problem on rank 0
+            x_cpu, res = oracle_window(prf, Kp, maxeig=maxeig)
+            cores = res["threads"]
+            sample = (f"{res['its']} MPGP iterations from x0 of the full-size workload ({n_glob} dofs), {cores} OpenMP threads standing in for MPI ranks; "
+                      "iteration loop timed, power-method set-up outside (as for `value`)")
+            if want_cpu and size == 1:
+                cpu = dict(value=round(res["value"], 3), unit=UNIT, cores=cores, kind="port", sample=sample, seconds=round(res["seconds"], 2),
+                           note="restatement of the reference CPU path (un-fused PETSc call sequence), not PETSc itself; the reference cannot be built here")
+            if want_parity:
+                parity = parity_compare(prf, x_gpu, f_gpu, counts_gpu, x_cpu, res, Kp)
+                parity["oracle_wall_s"] = round(time.time() - t_or, 1)
+            del prf, x_cpu, res
+        if size > 1:
+            dist.barrier()
+    if h2 is not None:
         destroy(h2)
+    if not want_e2e:
+        e2e = None
 
-    # ---------------- CPU baseline (rank 0, N = 1 only) -----------------------------------------------------
-    cpu = None
-    if rank == 0 and size == 1 and not args.no_cpu_baseline:
-        res = run_oracle(pr, W, K, budget_s=args.cpu_budget, maxeig=maxeig)
-        cpu = dict(value=round(res["value"], 3), unit=UNIT, cores=res["threads"], kind="port", sample=res["sample"],
-                   note="restatement of the reference CPU path (un-fused PETSc call sequence), not PETSc itself; the reference cannot be built here")
+    out = dict(value=round(value, 2), unit=UNIT, ms_per_step=round(ms / K, 5), steps=K, warmup=W,
+               config=dict(workload=spec["label"], n=n_glob, nnz=nnz_glob, l2=L2_NOTE),
+               details=dict(n_local=n_loc, nnz_local=nnz_loc, step_mix=counts, matrix_storage=storage, maxeig=maxeig,
+                            bytes_per_cg_step=b_cg, bytes_per_expansion_step=b_exp,
+                            bytes_per_cg_step_csr_formula=b_cg_csr, bytes_per_expansion_step_csr_formula=b_exp_csr,
+                            csr_equivalent_gbs_whole_iteration=round(whole_iter_gbs_csr * size, 1),
+                            achieved_gbs_whole_iteration=round(whole_iter_gbs * size, 1),
+                            frac_of_measured_hbm_whole_iteration=round(whole_iter_gbs / peak, 4), frac_of_8tbs_whole_iteration=round(whole_iter_gbs / 8000.0, 4),
+                            generate_s=round(t_gen, 1)),
+               e2e=e2e, gpu_launches=int(launches), roofline=roofline, cpu_baseline=cpu, parity=parity)
+    del host, pr
+    torch.cuda.empty_cache()
+    return out
 
-    # ---------------- N = 1 point of the strong-scaling series --------------------------------------------------
-    # BASELINE.json quotes the metric on C2 for one GPU and on C3 for 1/2/4/8 GPUs: the N = 1 headline is C2, the N > 1 lines are
-    # C3, so the one-GPU C3 number that the scaling efficiency has to be computed against is measured here as well
-    scaling_base = None
-    if size == 1 and args.workload == "auto" and not args.no_scaling_base:
-        spec3 = workload_spec("c3", 1)
-        t3 = time.time()
-        pr3 = generate(spec3, 0, 1)
-        sb = short_device_leg(P, torch, dev, stream, pr3, 20, min(K, 300))
-        sb.update(workload=spec3["label"], seconds_total=round(time.time() - t3, 1),
-                  note="N = 1 point of the C3 strong-scaling series that `bench.py --gpus N` (N > 1) reports: efficiency(N) = value(N) / (N * scaling_base.value)")
-        scaling_base = sb
-        del pr3
-    scaling_note = None
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2000)
+    ap.add_argument("--warmup", type=int, default=50)
+    ap.add_argument("--impl", default="ours")
+    ap.add_argument("--workload", default="auto")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--no-c2", action="store_true", help="N = 1, workload auto: skip the nested C2 object")
+    ap.add_argument("--cpu-budget", type=float, default=20.0)
+    args = ap.parse_args()
+    K, W = max(1, args.steps), max(3, args.warmup)
+    rank = int(os.environ.get("RANK", "0"))
+    size = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    spec = workload_spec(args.workload)
+
+    if args.impl == "reference":
+        # the reference's own CPU implementation cannot be built here (PETSc/MPI absent): time the oracle port on all host cores.
+        # A bounded sample of the same workload: min(K, what ~60 s of CPU time allow) iterations from x0, iteration loop timed.
+        if rank != 0:
+            return
+        pr = generate(spec, 0, 1)
+        Kp = oracle_sample_size(pr.N, pr.nnz, K, 60.0)
+        _, res = oracle_window(pr, Kp)
+        sample = (f"{res['its']} MPGP iterations from x0 of the full-size workload ({pr.N} dofs), {res['threads']} OpenMP threads standing in for MPI ranks; "
+                  "iteration loop timed, power-method set-up outside")
+        line = dict(metric=METRIC, value=res["value"], unit=UNIT, n_gpus=args.gpus, steps=K, warmup=W, ms_per_step=1e3 / res["value"],
+                    higher_is_better=True, scaling="strong", vs_baseline=None, dtype="f64", data="synthetic", impl="reference",
+                    config=dict(workload=spec["label"], n=int(pr.N), nnz=int(pr.nnz), l2=L2_NOTE),
+                    details=dict(step_mix=res["counts"], objective=res["objective"]),
+                    cpu_baseline=dict(value=res["value"], unit=UNIT, cores=res["threads"], kind="port", sample=sample),
+                    e2e=dict(value=res["value"], unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
+        print(json.dumps(line), flush=True)
+        return
+
+    import torch
+    from permon_b200 import api as P
+
+    if P.device_count() == 0:
+        raise SystemExit("bench.py: no CUDA device -- the product has no CPU path")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    P.call("PermonB200SetDevice", local_rank)
+    P.initialize()
+    env = Env()
+    env.P, env.torch, env.dev, env.rank, env.size, env.dist = P, torch, dev, rank, size, None
     if size > 1:
-        scaling_note = ("strong scaling of C3 (fixed 134M-dof problem); its one-GPU point is the `scaling_base` object of the N = 1 line, "
-                        "whose headline `value` is C2 as BASELINE.json asks")
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+        env.dist = dist
+        idt = torch.zeros(128, dtype=torch.uint8, device=dev)
+        if rank == 0:
+            idt.copy_(torch.frombuffer(bytearray(P.get_unique_id()), dtype=torch.uint8))
+        dist.broadcast(idt, 0)
+        P.comm_init_rank(size, rank, bytes(idt.cpu().numpy().tobytes()))
+
+        def all_gather_int(v):
+            t = torch.zeros(size, dtype=torch.int64, device=dev)
+            t[rank] = int(v)
+            dist.all_reduce(t)
+            return t.cpu().tolist()
+        env.all_gather_int = all_gather_int
+    env.stream = torch.cuda.current_stream()
+    P.set_stream(env.stream.cuda_stream)
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    res = measure(env, spec, K, W, want_e2e=not args.no_e2e, want_cpu=not args.no_cpu_baseline, want_parity=not args.no_parity,
+                  cpu_budget=args.cpu_budget, sampler=sampler)
+    clocks = sampler.stop()
+
+    c2 = None
+    if size == 1 and args.workload == "auto" and not args.no_c2:
+        # BASELINE.json also quotes the metric on C2 (16.7M dofs, one GPU): same legs, nested
+        c2 = measure(env, workload_spec("c2"), K, W, want_e2e=not args.no_e2e, want_cpu=not args.no_cpu_baseline, want_parity=not args.no_parity,
+                     cpu_budget=min(args.cpu_budget, 10.0))
+        c2["note"] = "C2 = BASELINE.json configs[1] (the 16.7M-dof single-GPU case); the headline workload of this line is C3 so that the --gpus N series is one workload"
 
     if rank == 0:
-        line = dict(metric=METRIC, value=round(value, 2), unit=UNIT, n_gpus=size, steps=K, warmup=W, ms_per_step=round(ms / K, 5), higher_is_better=True,
-                    scaling="strong", vs_baseline=None, dtype="f64", data="synthetic",
-                    config=dict(workload=spec["label"], n=pr.N, n_local=n_loc, nnz_local=nnz_loc, step_mix=counts,
-                                l2="inputs larger than L2 (every kernel streams >= 3 vectors of 8n bytes, n >= 8.4M per GPU, vs 126 MB L2)",
-                                matrix_storage=storage, maxeig=maxeig, bytes_per_cg_step=b_cg, bytes_per_expansion_step=b_exp,
-                                bytes_per_cg_step_csr_formula=b_cg_csr, bytes_per_expansion_step_csr_formula=b_exp_csr,
-                                csr_equivalent_gbs_whole_iteration=round(whole_iter_gbs_csr * size, 1),
-                                achieved_gbs_whole_iteration=round(whole_iter_gbs * size, 1),
-                                frac_of_measured_hbm_whole_iteration=round(whole_iter_gbs / peak, 4), frac_of_8tbs_whole_iteration=round(whole_iter_gbs / 8000.0, 4),
-                                generate_s=round(t_gen, 1)),
-                    clocks=clocks, e2e=e2e, gpu_launches=int(launches), roofline=roofline, cpu_baseline=cpu)
-        if scaling_base:
-            line["scaling_base"] = scaling_base
-        if scaling_note:
-            line["scaling_note"] = scaling_note
+        line = dict(metric=METRIC, value=res["value"], unit=UNIT, n_gpus=size, steps=K, warmup=W, ms_per_step=res["ms_per_step"], higher_is_better=True,
+                    scaling="strong", vs_baseline=None, dtype="f64", data="synthetic", config=res["config"], details=res["details"],
+                    clocks=clocks, e2e=res["e2e"], gpu_launches=res["gpu_launches"], roofline=res["roofline"], cpu_baseline=res["cpu_baseline"],
+                    parity=res["parity"])
+        if c2 is not None:
+            line["c2"] = c2
+        if size > 1:
+            line["scaling_note"] = ("strong scaling of the fixed C3 problem; efficiency(N) = value(N) / (N * value(1)) with value(1) the headline of the "
+                                    "--gpus 1 line (same workload, same W)")
         print(json.dumps(line), flush=True)
     if size > 1:
-        dist.destroy_process_group()
+        env.dist.destroy_process_group()
 
 
 if __name__ == "__main__":

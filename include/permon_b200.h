@@ -125,6 +125,7 @@ PERMON_EXTERN PetscErrorCode PermonB200CommSetHostExchange(int nranks, int rank,
 PERMON_EXTERN PetscErrorCode PermonB200ProfileBegin(void);
 PERMON_EXTERN PetscErrorCode PermonB200ProfileEnd(int *nfamilies);
 PERMON_EXTERN PetscErrorCode PermonB200ProfileGet(int family, const char **name, int64_t *launches, double *total_ms, double *bytes_per_launch);
+PERMON_EXTERN PetscErrorCode PermonB200ProfileGetWorking(int family, int64_t *launches, double *total_ms);   /* launches that did work (device-driven kernels exit at once when they have nothing to do) */
 PERMON_EXTERN PetscErrorCode PermonB200ProfileDump(const char *csv_path);   /* per-launch timeline of the last profiled region */
 PERMON_EXTERN PetscErrorCode PermonB200GetLaunchCount(int64_t *launches);
 PERMON_EXTERN const char    *PermonB200GetLastErrorMessage(void);

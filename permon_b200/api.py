@@ -148,7 +148,9 @@ def profile_end():
     for f in range(n.value):
         name, cnt, ms, bpl = C.c_char_p(), C.c_int64(), C.c_double(), C.c_double()
         call("PermonB200ProfileGet", C.c_int(f), C.byref(name), C.byref(cnt), C.byref(ms), C.byref(bpl))
-        out[name.value.decode()] = dict(launches=cnt.value, total_ms=ms.value, bytes_per_launch=bpl.value)
+        wn, wms = C.c_int64(), C.c_double()
+        call("PermonB200ProfileGetWorking", C.c_int(f), C.byref(wn), C.byref(wms))
+        out[name.value.decode()] = dict(launches=cnt.value, total_ms=ms.value, bytes_per_launch=bpl.value, working_launches=wn.value, working_ms=wms.value)
     return out
 
 

@@ -36,12 +36,22 @@ int     cuda_fail(cudaError_t e, const char *what, const char *file, int line);
     if (ierr_) return ierr_;    \
   } while (0)
 
+// ---- wall-clock phase timer (PERMON_B200_TIMING=1): synchronises the device on both sides and prints one line to stderr ----
+struct PhaseTimer {
+  const char *name;
+  double      t0;
+  bool        on;
+  explicit PhaseTimer(const char *name);
+  ~PhaseTimer();
+};
+
 // ---- profiling (bench.py roofline) -----------------------------------------------------------------
 enum KFamily { KF_SPMV_A = 0, KF_UPDATE_B, KF_SPMV_A2, KF_DIR_C, KF_CTRL, KF_SPMV_PLAIN, KF_VEC, KF_QPC, KF_HALO, KF_COUNT };
 const char *family_name(int f);
 void        prof_begin();
 int         prof_end();
 int         prof_get(int family, int64_t *launches, double *ms, double *bytes_per_launch);
+int         prof_get_working(int family, int64_t *launches, double *ms);   // launches that did work (not early exits) and their time
 int         prof_dump(const char *path);
 void        prof_pre(int family, double bytes);
 void        prof_post(int family);

@@ -23,6 +23,7 @@
 #include <stdarg.h>
 #include <stdio.h>
 #include <string.h>
+#include <time.h>
 
 #include <string>
 #include <type_traits>
@@ -87,6 +88,28 @@ int dev_init()
   return 0;
 }
 
+static double phase_now()
+{
+  struct timespec ts;
+  clock_gettime(CLOCK_MONOTONIC, &ts);
+  return ts.tv_sec + 1e-9 * ts.tv_nsec;
+}
+PhaseTimer::PhaseTimer(const char *nm) : name(nm), t0(0.0), on(false)
+{
+  static const bool enabled = getenv("PERMON_B200_TIMING") != nullptr;
+  on = enabled;
+  if (on) {
+    if (g_ctx.ready) cudaDeviceSynchronize();
+    t0 = phase_now();
+  }
+}
+PhaseTimer::~PhaseTimer()
+{
+  if (!on) return;
+  if (g_ctx.ready) cudaDeviceSynchronize();
+  fprintf(stderr, "[permon_b200 timing] %-44s %9.2f ms\n", name, 1e3 * (phase_now() - t0));
+}
+
 static const char *g_family_names[KF_COUNT] = {"K_A spmv+dots+feas", "K_B update+split", "K_A' spmv+grad+split", "K_C direction", "ctrl", "spmv plain", "vec", "qpc", "halo"};
 const char        *family_name(int f) { return (f >= 0 && f < KF_COUNT) ? g_family_names[f] : "?"; }
 
@@ -98,8 +121,8 @@ struct ProfRec {
 static bool                 g_prof_on = false;
 static std::vector<ProfRec> g_prof;
 static size_t               g_prof_used = 0;
-static double               g_prof_ms[KF_COUNT], g_prof_bytes[KF_COUNT];
-static int64_t              g_prof_n[KF_COUNT];
+static double               g_prof_ms[KF_COUNT], g_prof_bytes[KF_COUNT], g_prof_work_ms[KF_COUNT];
+static int64_t              g_prof_n[KF_COUNT], g_prof_work_n[KF_COUNT];
 
 void prof_begin()
 {
@@ -134,13 +157,26 @@ int prof_end()
 {
   g_prof_on = false;
   cudaStreamSynchronize(g_ctx.stream);
-  for (int f = 0; f < KF_COUNT; f++) g_prof_ms[f] = g_prof_bytes[f] = 0.0, g_prof_n[f] = 0;
+  for (int f = 0; f < KF_COUNT; f++) g_prof_ms[f] = g_prof_bytes[f] = g_prof_work_ms[f] = 0.0, g_prof_n[f] = g_prof_work_n[f] = 0;
+  std::vector<float> ms(g_prof_used, 0.f);
+  float              mx[KF_COUNT];
+  for (int f = 0; f < KF_COUNT; f++) mx[f] = 0.f;
   for (size_t i = 0; i < g_prof_used; i++) {
-    float ms = 0.f;
-    cudaEventElapsedTime(&ms, g_prof[i].a, g_prof[i].b);
-    g_prof_ms[g_prof[i].fam] += ms;
-    g_prof_bytes[g_prof[i].fam] += g_prof[i].bytes;
-    g_prof_n[g_prof[i].fam]++;
+    cudaEventElapsedTime(&ms[i], g_prof[i].a, g_prof[i].b);
+    const int f = g_prof[i].fam;
+    g_prof_ms[f] += ms[i];
+    g_prof_bytes[f] += g_prof[i].bytes;
+    g_prof_n[f]++;
+    if (ms[i] > mx[f]) mx[f] = ms[i];
+  }
+  // "working" launches: a device-driven kernel that has nothing to do (K_A' outside expansion steps, anything enqueued behind
+  // the stopping iteration) exits within a few microseconds; launches above a quarter of the family's longest one did the work
+  for (size_t i = 0; i < g_prof_used; i++) {
+    const int f = g_prof[i].fam;
+    if (ms[i] > 0.25f * mx[f]) {
+      g_prof_work_ms[f] += ms[i];
+      g_prof_work_n[f]++;
+    }
   }
   return KF_COUNT;
 }
@@ -156,6 +192,13 @@ int prof_dump(const char *path)
     fprintf(f, "%s,%.4f,%.4f\n", family_name(g_prof[i].fam), a, b);
   }
   fclose(f);
+  return 0;
+}
+int prof_get_working(int f, int64_t *launches, double *ms)
+{
+  if (f < 0 || f >= KF_COUNT) return 63;
+  *launches = g_prof_work_n[f];
+  *ms       = g_prof_work_ms[f];
   return 0;
 }
 int prof_get(int f, int64_t *launches, double *ms, double *bytes_per_launch)

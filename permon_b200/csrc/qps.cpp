@@ -17,6 +17,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <memory>
 
 #include "objects.h"
 
@@ -356,7 +357,11 @@ PetscErrorCode QPSSetUp(QPS qps)
   if (qps->setupcalled) return 0;
   if (!qps->topQP) return err(PETSC_ERR_ORDER, "QPSSetQP must be called first");
   PB_CHK(dev_init());   // fail loudly: no CPU execution path
-  PB_CHK(QPChainSetUp(qps->topQP));
+  PhaseTimer pt_all("QPSSetUp");
+  {
+    PhaseTimer pt("QPSSetUp: QPChainSetUp");
+    PB_CHK(QPChainSetUp(qps->topQP));
+  }
   if (!qps->solQP) {
     PB_CHK(QPChainGetLast(qps->topQP, &qps->solQP));
     pb::ref(qps->solQP);
@@ -365,7 +370,10 @@ PetscErrorCode QPSSetUp(QPS qps)
   PetscBool flg;
   PB_CHK(QPSIsQPCompatible(qps, qps->solQP, &flg));
   if (!flg) return err(PETSC_ERR_ARG_INCOMP, "QPS solver %s is not compatible with its attached QP", qps->type.c_str());
-  PB_CHK(qps->impl->setup(qps));
+  {
+    PhaseTimer pt("QPSSetUp: solver set-up (work vectors, maxeig)");
+    PB_CHK(qps->impl->setup(qps));
+  }
   PB_CHK(QPChainSetUp(qps->solQP));
   qps->setupcalled = true;
   return 0;
@@ -393,7 +401,10 @@ PetscErrorCode QPSReset(QPS qps)
 PetscErrorCode QPSSolve(QPS qps)
 {   // qps.c:537-555
   PB_CHK(QPSSetUp(qps));
-  PB_CHK(qps->impl->solve(qps));
+  {
+    PhaseTimer pt("QPSSolve: solve");
+    PB_CHK(qps->impl->solve(qps));
+  }
   qps->iterations_accumulated += qps->iteration;
   qps->nsolves++;
   qps->postsolvecalled = false;
@@ -594,7 +605,10 @@ PetscErrorCode MpgpImpl::setup(QPS qps)
   else if (explengthtype == QPS_MPGP_EXPANSION_LENGTH_BB) nw = 9;
   const bool fused = fused_eligible(qps);
   if (driver == "fused" && !fused) return err(PETSC_ERR_SUP, "-qps_mpgp_b200_driver fused needs expansion std/fixed, no fallback and an AIJ (or product-of-AIJ) Hessian");
-  PB_CHK(set_work(qps, nw));
+  {
+    PhaseTimer pt("MPGP set-up: work vectors");
+    PB_CHK(set_work(qps, nw));
+  }
   if (bchop_tol) return err(PETSC_ERR_SUP, "-qps_mpgp_bound_chop_tol is not supported");
   expproject = true;   // QPSCreate_MPGP :839 (re-evaluated at every set-up here)
   switch (exptype) {
@@ -611,7 +625,10 @@ PetscErrorCode MpgpImpl::setup(QPS qps)
   default: return err(PETSC_ERR_PLIB, "Unknown MPGP expansion type");
   }
   if (alpha_type == QPS_ARG_MULTIPLE) {   // :417-425
-    if (maxeig == PETSC_DECIDE) PB_CHK(MatGetMaxEigenvalue(qps->solQP->A, NULL, &maxeig, maxeig_tol, maxeig_iter));
+    if (maxeig == PETSC_DECIDE) {
+      PhaseTimer pt("MPGP set-up: MatGetMaxEigenvalue");
+      PB_CHK(MatGetMaxEigenvalue(qps->solQP->A, NULL, &maxeig, maxeig_tol, maxeig_iter));
+    }
     if (alpha_user == PETSC_DECIDE) alpha_user = 2.0;
     alpha = alpha_user / maxeig;
   } else {
@@ -637,6 +654,7 @@ int MpgpImpl::solve_fused(QPS qps)
 {
   QP  qp = qps->solQP;
   Mat A = qp->A, base = A;
+  std::unique_ptr<PhaseTimer> pt_pre(new PhaseTimer("MPGP fused: engine init + vector uploads"));
   PB_CHK(engine_init(qps));
   PB_CHK(mat_ensure_device(A));
   cudaStream_t s = ctx().stream;
@@ -809,6 +827,8 @@ int MpgpImpl::solve_fused(QPS qps)
     return 0;
   };
 
+  pt_pre.reset();
+  PhaseTimer pt_loop("MPGP fused: initial phase + iterations");
   // ---- initial phase: x = P(x); g = A x - b; split; p = gf  (mpgp.c:497-507)
   PB_CHK(k_fused_project(v, S1, red(RB, 1, true)));
   if (v.m > 0) PB_CHK(gather_ctrl_E());
@@ -822,8 +842,15 @@ int MpgpImpl::solve_fused(QPS qps)
   if (!stop) PB_CHK(step_C(!fold));
 
   // ---- main loop
+  // iterations still allowed by max_it (qps.c:684: DIVERGED_ITS once i > max_it; the SMALXE inner rule counts the accumulated
+  // inner iterations, smalxe.c:633): the last batch is cut to that, so that no launch is enqueued behind the stopping iteration
+  long long allowed = (long long)S.max_it + 1 - (inner_smalxe ? (long long)S.inner_iter_accu : 0);
+  if (allowed < 1) allowed = 1;
+  long long enq = 0;
   while (!stop) {
-    const int nb = host_conv ? 1 : batch;
+    int nb = host_conv ? 1 : batch;
+    if (!host_conv && allowed - enq >= 1 && allowed - enq < nb) nb = (int)(allowed - enq);
+    enq += nb;
     for (int it = 0; it < nb && !stop; it++) {
       const double *xin = v.p;
       if (prod) {

@@ -261,6 +261,7 @@ int vec_host_read(Vec v, const double **h)
   PB_CHK(vec_alloc_host(v));
   if (!v->h_valid) {
     if (v->d_valid) {
+      PhaseTimer pt("Vec download (D2H)");
       PB_CUDA(cudaMemcpyAsync(v->h, v->d, sizeof(double) * (size_t)v->n, cudaMemcpyDeviceToHost, ctx().stream));
       PB_CUDA(cudaStreamSynchronize(ctx().stream));
     } else {
@@ -593,6 +594,11 @@ PetscErrorCode PermonB200ProfileGet(int family, const char **name, int64_t *laun
 {
   if (name) *name = family_name(family);
   return prof_get(family, launches, total_ms, bytes_per_launch);
+}
+PetscErrorCode PermonB200ProfileGetWorking(int family, int64_t *launches, double *total_ms)
+{
+  if (!launches || !total_ms) return err(PETSC_ERR_ARG_NULL, "null output");
+  return prof_get_working(family, launches, total_ms);
 }
 PetscErrorCode PermonB200ProfileDump(const char *path) { return prof_dump(path); }
 PetscErrorCode PermonB200GetLaunchCount(int64_t *launches)
@@ -1009,6 +1015,7 @@ PetscErrorCode MatCreateSeqAIJWithArrays(MPI_Comm comm, PetscInt m, PetscInt n, 
   if (comm->size > 1) return MatCreateMPIAIJWithArrays(comm, m, n, PETSC_DECIDE, PETSC_DECIDE, i, j, a, mat);
   PB_CHK(dev_init());
   if (!i || (i[m] > 0 && (!j || !a))) return err(PETSC_ERR_ARG_NULL, "null CSR array");
+  PhaseTimer pt("MatCreateSeqAIJWithArrays");
   _p_Mat *A = new _p_Mat;
   A->comm = comm;
   A->kind = MK_AIJ;
@@ -1063,6 +1070,7 @@ PetscErrorCode MatCreateMPIAIJWithArrays(MPI_Comm comm, PetscInt m, PetscInt n, 
     return MatCreateSeqAIJWithArrays(comm, m, n, const_cast<PetscInt *>(i), const_cast<PetscInt *>(j), const_cast<PetscScalar *>(a), mat);
   }
   if (!comm->agi || !comm->agv) return err(PETSC_ERR_ARG_WRONGSTATE, "communicator has no host exchange");
+  PhaseTimer pt("MatCreateMPIAIJWithArrays (host split + plan)");
   const int size = comm->size, rank = comm->rank;
   std::vector<int64_t> rows_all(size), cols_all(size);
   if (comm->agi(comm->agctx, m, rows_all.data()) || comm->agi(comm->agctx, n, cols_all.data())) return err(PETSC_ERR_LIB, "host all-gather failed");
@@ -1345,6 +1353,7 @@ int mat_ensure_device(Mat A)
   HaloPlan            *H = A->halo;
   HaloPlan::HostSplit *S = H->host;
   PB_CHK(dev_init());
+  PhaseTimer pt("mat_ensure_device (pack + upload + halo set-up)");
   const PetscInt m = A->m;
   PB_CHK(upload_csr(A->Ad, m, A->n, S->dia.data(), S->dja.data(), S->da.data(), nullptr));
   PB_CHK(upload_csr(A->Ao, (int)S->orow.size(), (int)H->garray.size(), S->oia.data(), S->oja.data(), S->oa.data(), S->orow.data()));

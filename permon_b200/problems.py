@@ -211,8 +211,10 @@ def jbearing2(nx, ny, ecc=0.1, bb=10.0):
 # synthetic configurations
 # ---------------------------------------------------------------------------------------------------
 
-def obstacle2d(N, bscale=-30.0, rows=None):
-    """C1/C2: N x N interior grid, h = 1/(N+1), 5-point Laplacian (4,-1), b = bscale*h^2, sinusoidal obstacle."""
+def obstacle2d(N, bscale=-30.0, rows=None, scaled=False):
+    """C1/C2: N x N interior grid, h = 1/(N+1), 5-point Laplacian (4,-1), b = bscale*h^2, sinusoidal obstacle.
+    ``scaled``: the Hessian becomes D A D with d_i = 1 + u01(i)/2 (counter-based, partition independent): every value is
+    distinct, so no tile of the packed format can be dictionary-coded (the incompressible case, 12 B per non-zero)."""
     n = N * N
     r0, r1 = (0, n) if rows is None else rows
     h = 1.0 / (N + 1)
@@ -222,6 +224,9 @@ def obstacle2d(N, bscale=-30.0, rows=None):
     cols = np.stack([r - N, r - 1, r, r + 1, r + N], axis=1)
     mask = np.stack([j > 0, i > 0, np.ones_like(i, bool), i < N - 1, j < N - 1], axis=1)
     vals = np.broadcast_to(np.array([-1.0, -1.0, 4.0, -1.0, -1.0]), cols.shape)
+    if scaled:
+        dsc = lambda idx: 1.0 + 0.5 * u01(np.asarray(idx).astype(np.uint64), 9)
+        vals = vals * dsc(r)[:, None] * dsc(np.clip(cols, 0, n - 1))
     ia, ja, a = _csr_from_candidates(cols, vals, mask)
     x = (i + 1) * h
     y = (j + 1) * h
