@@ -136,6 +136,8 @@ struct RedBuf {
   double   *partials = nullptr;   // [maxblocks][PB_NRED]
   unsigned *counter  = nullptr;
   double   *out      = nullptr;   // where the last block stores the record (PB_NRED doubles)
+  const double *add1 = nullptr;   // optional scalar produced by an earlier kernel, added into slot add1_slot of the record
+  int           add1_slot = 0;
   const P2PWin      *win = nullptr;   // when set: also publish the record to every peer (kind, seq)
   int                kind = 0;
   unsigned long long seq = 0;
@@ -170,16 +172,25 @@ struct PushRanges {
   unsigned           *counter = nullptr;
   int                 gap_lo = 0, gap_hi = 0;   // largest run of rows outside every range
 };
-// rows whose K_A / K_A' epilogue is deferred to the ghost pass (multi-GPU): byte flags, consulted only outside [lo, hi) --
-// the widest run of rows without ghost columns, i.e. the interior of a slab
-struct SkipRows {
-  const unsigned char *flags = nullptr;
-  int                  lo = 0, hi = 0;
-};
-struct HaloWait {
-  const unsigned long long *flags = nullptr;   // local: one flag slot (PB_FLAG_STRIDE apart) per neighbour
-  int                       n = 0;
+// Off-diagonal (ghost column) part of a row-partitioned matrix, merged into K_A / K_A' (multi-GPU): rows outside [lo, hi) -- the
+// widest run of rows without ghost columns, i.e. the interior of a slab -- look up their compressed off-diagonal row, wait (once per
+// thread) until every neighbour's halo push of this sequence number has landed, and add the ghost products to the row sum before
+// the fused epilogue (the order of PETSc's MatMult_MPIAIJ: diagonal block first, then MatMultAdd of the off-diagonal block).
+// The tiles that hold such rows are processed LAST (TileOrder), so the wait is over by the time it is reached.
+struct GhostMerge {
+  const int                *row_map = nullptr;   // [lo + (n - hi)] index into the compressed off-diagonal rows, -1: no ghost column
+  int                       lo = 0, hi = 0;
+  const int                *oia = nullptr, *oja = nullptr;
+  const double             *oa = nullptr;
+  const double             *ghost = nullptr;     // ghost values (written by the neighbours over NVLink, or by ncclRecv)
+  const unsigned long long *flags = nullptr;     // peer-memory mode: local flag slots (PB_FLAG_STRIDE apart), one per neighbour
+  int                       nflags = 0;
   unsigned long long        seq = 0;
+};
+// order in which the persistent SpMV grid walks the 256-row tiles: tiles [ta, tb) first (ascending, or descending when the
+// sweep direction of the iteration says so), then the tiles outside that range
+struct TileOrder {
+  int ta = 0, tb = 0;
 };
 
 // ---- kernels: generic vector ops (deterministic) -----------------------------------------------------
@@ -220,11 +231,9 @@ struct MpgpVecs {
   double *t = nullptr;           // inner-dimension work vector for product operators
 };
 // K_A  : Ap = A xin (xin = p, or t for product operators) + [p.Ap, g.p, B p, alpha_f]
-int k_fused_A(const CsrDev &A, const double *xin, const MpgpVecs &v, const MpgpCtl *S, RedBuf rb, SkipRows skip_epilogue);
+int k_fused_A(const CsrDev &A, const double *xin, const MpgpVecs &v, const MpgpCtl *S, RedBuf rb, const GhostMerge &gm);
 // K_A' : g = A xin - b (+rho B^T Bu), split, p = gf, [|gP|^2, |gc|^2, |gf|^2]; runs when step=='e' or init
-int k_fused_A2(const CsrDev &A, const double *xin, const MpgpVecs &v, const MpgpCtl *S, RedBuf rb, SkipRows skip_epilogue);
-// off-diagonal (ghost) contribution + deferred epilogue for boundary rows (multi-GPU)
-int k_fused_A_ghost(const CsrDev &Ao, const double *ghost, const MpgpVecs &v, const MpgpCtl *S, RedBuf rb, int second, HaloWait hw);
+int k_fused_A2(const CsrDev &A, const double *xin, const MpgpVecs &v, const MpgpCtl *S, RedBuf rb, const GhostMerge &gm);
 // peer-memory halo push (which: 0 = p before K_A, 1 = x before K_A' [gated on step 'e' / init])
 int k_halo_push(const HaloPush &hp, const double *vec, int gated, unsigned long long seq, const MpgpCtl *S);
 // ctrl kernels that first wait for every rank's pushed record (peer-memory all-gather)
@@ -234,7 +243,7 @@ int k_ctrl_B_p2p(MpgpCtl *S, const P2PWin *win, const double *my_slot, const uns
 // K_B  : the c / p / e update of x, g (+ split, reductions)
 int k_fused_B(const MpgpVecs &v, const CtrlFold &cf, RedBuf rb, const PushRanges *d_push_x, unsigned long long push_seq);   // d_push_x: device memory or NULL
 // K_C  : direction update p = gf - bcg p | p = gc | nothing
-int k_fused_C(const MpgpVecs &v, const CtrlFold &cf, const PushRanges *d_push_p, unsigned long long push_seq);
+int k_fused_C(const MpgpVecs &v, const CtrlFold &cf, RedBuf rc, const PushRanges *d_push_p, unsigned long long push_seq);   // rc.out[RA_GP] = local g.p of the new direction (CG steps)
 // initial projection x = P(x) (+ B u)
 int k_fused_project(const MpgpVecs &v, const MpgpCtl *S, RedBuf rb);
 // plain product-operator first factor, device-driven: t = M2 xin when the phase is active

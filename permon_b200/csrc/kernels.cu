@@ -27,6 +27,7 @@
 
 #include <string>
 #include <type_traits>
+#include <utility>
 #include <vector>
 
 #include "device.h"
@@ -218,6 +219,40 @@ int prof_get(int f, int64_t *launches, double *ms, double *bytes_per_launch)
 
 static bool aligned16(const void *p) { return (((uintptr_t)p) & 15) == 0; }
 
+// Programmatic dependent launch: every kernel of the fused iteration starts with pdl_enter() -- wait until the previous kernel of
+// the stream has completed and its writes are visible, then let the NEXT kernel's CTAs be scheduled as soon as SM resources free
+// up (they block in their own pdl_enter()).  Launch latency and the ramp-up of kernel N+1 overlap the tail of kernel N.  Nothing
+// that an earlier kernel produced may be read before pdl_enter().  Without the launch attribute both instructions are no-ops.
+__device__ __forceinline__ void pdl_enter()
+{
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+static bool pdl_enabled()
+{
+  static int on = -1;
+  if (on < 0) {
+    const char *e = getenv("PERMON_B200_PDL");
+    on = (e && !strcmp(e, "0")) ? 0 : 1;
+  }
+  return on != 0;
+}
+template <class... KArgs, class... Args>
+static void launch_k(void (*kernel)(KArgs...), int grid, int block, size_t smem, Args &&...args)
+{
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim          = dim3((unsigned)grid);
+  cfg.blockDim         = dim3((unsigned)block);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream           = g_ctx.stream;
+  cudaLaunchAttribute at[1];
+  at[0].id                                         = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs    = at;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, kernel, KArgs(std::forward<Args>(args))...);
+}
+
 static constexpr int NT = 256;   // threads per CTA everywhere
 
 int elementwise_grid() { return g_ctx.sm_count * 8; }
@@ -290,9 +325,10 @@ __device__ void grid_reduce8(double (&v)[PB_NRED], RedBuf rb, const double *prev
     if (threadIdx.x == 0) {
 #pragma unroll
       for (int k = 0; k < PB_NRED; k++) {
-        const double f = prev ? red_op<MINMASK>(k, prev[k], w[k]) : w[k];
-        rb.out[k]      = f;
-        sm[k][0]       = f;
+        double f = prev ? red_op<MINMASK>(k, prev[k], w[k]) : w[k];
+        if (rb.add1 && k == rb.add1_slot) f += __ldcg(rb.add1);
+        rb.out[k] = f;
+        sm[k][0]  = f;
       }
       *rb.counter = 0u;
     }
@@ -306,6 +342,48 @@ __device__ void grid_reduce8(double (&v)[PB_NRED], RedBuf rb, const double *prev
         for (int k = 0; k < PB_NRED; k++) dst[k] = sm[k][0];
         __threadfence_system();
         *(volatile unsigned long long *)(W->flag[q] + p2p_flag_index(rb.kind, W->rank)) = rb.seq;
+      }
+    }
+  }
+}
+
+// one-value variant (sum) for kernels with a tight register budget: the result lands in rb.out[slot]
+__device__ void grid_reduce1(double v, RedBuf rb, int slot)
+{
+  __shared__ double sm1[32];
+  __shared__ int    s_last1;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  if (lane == 0) sm1[warp] = v;
+  __syncthreads();
+  if (warp == 0) {
+    double t = (lane < nw) ? sm1[lane] : 0.0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    if (lane == 0) {
+      rb.partials[(size_t)blockIdx.x * PB_NRED] = t;
+      __threadfence();
+      s_last1 = (atomicAdd(rb.counter, 1u) == gridDim.x - 1);
+    }
+  }
+  __syncthreads();
+  if (s_last1) {
+    __threadfence();
+    double t = 0.0;
+    for (int b = threadIdx.x; b < (int)gridDim.x; b += blockDim.x) t += __ldcg(&rb.partials[(size_t)b * PB_NRED]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    __syncthreads();
+    if (lane == 0) sm1[warp] = t;
+    __syncthreads();
+    if (warp == 0) {
+      double u = (lane < nw) ? sm1[lane] : 0.0;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) u += __shfl_xor_sync(0xffffffffu, u, o);
+      if (lane == 0) {
+        rb.out[slot] = u;
+        *rb.counter  = 0u;
       }
     }
   }
@@ -423,21 +501,11 @@ __device__ __forceinline__ double box_project(double x, const BoxVal &b)
 // tile-streamed CSR ("CSR-stream"): the CTA reads the nnz range of a 256-row tile with unit-stride loads,
 // multiplies with the gathered x on the fly and parks the products in shared memory; then one thread per
 // row adds its segment in storage order (== the reference's running sum) and runs the fused epilogue.
-template <class Epi, class = void>
-struct EpiHasWait : std::false_type {};
-template <class Epi>
-struct EpiHasWait<Epi, std::void_t<decltype(std::declval<const Epi &>().wait())>> : std::true_type {};
-template <class Epi>
-__device__ __forceinline__ void epi_wait(const Epi &epi)
-{
-  if constexpr (EpiHasWait<Epi>::value) epi.wait();
-}
-
 template <class Epi>
 __global__ void __launch_bounds__(NT) k_spmv_stream(CsrDev A, const double *__restrict__ x, Epi epi)
 {
+  pdl_enter();
   if (!epi.active()) return;
-  epi_wait(epi);
   extern __shared__ double s_prod[];
   typename Epi::Acc acc;
   epi.init(acc);
@@ -464,8 +532,8 @@ __global__ void __launch_bounds__(NT) k_spmv_stream(CsrDev A, const double *__re
 template <class Epi, int W>
 __global__ void __launch_bounds__(NT) k_spmv_vector(CsrDev A, const double *__restrict__ x, Epi epi)
 {
+  pdl_enter();
   if (!epi.active()) return;
-  epi_wait(epi);
   typename Epi::Acc acc;
   epi.init(acc);
   const int lane    = threadIdx.x & (W - 1);
@@ -554,6 +622,7 @@ static constexpr int TMA_MAX_STAGES = 4;
 template <class Epi>
 __global__ void __launch_bounds__(NT + 32) k_spmv_tma(CsrDev A, const double *__restrict__ x, Epi epi, int cap, int nstages)
 {
+  pdl_enter();
   if (!epi.active()) return;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ uint64_t full_bar[TMA_MAX_STAGES], empty_bar[TMA_MAX_STAGES];
@@ -830,9 +899,85 @@ __device__ __forceinline__ double pk_row_raw(uint32_t a_a, uint32_t ja_a, int le
   return sum;
 }
 
-template <class Epi>
-__global__ void __launch_bounds__(PK_CT + 32) k_spmv_pk(CsrDev A, const double *__restrict__ x, Epi epi, int blob_cap, int nstages, int vec_tma)
+// stencil tile (kind 2): every row of the tile is the tile's pattern -- L <= 8 (col - row, value) pairs in storage order -- with some
+// entries missing (rows next to a grid boundary); one presence byte per row instead of one code byte per non-zero.  Deltas and values
+// are warp-uniform (broadcast shared-memory loads), a row costs its gathers and multiply-adds only.  A missing entry is skipped
+// (predicated load and multiply-add), so the sum runs over the row's stored entries in storage order: bit-identical to the CSR kernels.
+template <int L>
+__device__ __forceinline__ void st_row2_fixed(uint32_t m0, uint32_t m1, uint32_t dv_a, uint32_t dd_a, const double *__restrict__ x, int r0, int r1, double &s0, double &s1)
 {
+  constexpr uint32_t FULL = (1u << L) - 1u;
+  int                d[L];
+  double             x0[L], x1[L];
+#pragma unroll
+  for (int j = 0; j < L; j++) d[j] = lds_s32(dd_a + 4u * j);
+  const double *xr0 = x + r0, *xr1 = x + r1;
+  const bool    f0 = __all_sync(0xffffffffu, m0 == FULL), f1 = __all_sync(0xffffffffu, m1 == FULL);
+  if (f0) {
+#pragma unroll
+    for (int j = 0; j < L; j++) x0[j] = __ldg(xr0 + d[j]);
+  } else {
+#pragma unroll
+    for (int j = 0; j < L; j++) x0[j] = ((m0 >> j) & 1u) ? __ldg(xr0 + d[j]) : 0.0;
+  }
+  if (f1) {
+#pragma unroll
+    for (int j = 0; j < L; j++) x1[j] = __ldg(xr1 + d[j]);
+  } else {
+#pragma unroll
+    for (int j = 0; j < L; j++) x1[j] = ((m1 >> j) & 1u) ? __ldg(xr1 + d[j]) : 0.0;
+  }
+  __syncwarp();   // scheduling fence: every gather above is issued before the first multiply-add below
+  double v[L];
+#pragma unroll
+  for (int j = 0; j < L; j++) v[j] = lds_f64(dv_a + 8u * j);
+  s0 = 0.0;
+  s1 = 0.0;
+  if (f0) {
+#pragma unroll
+    for (int j = 0; j < L; j++) s0 += v[j] * x0[j];
+  } else {
+#pragma unroll
+    for (int j = 0; j < L; j++)
+      if ((m0 >> j) & 1u) s0 += v[j] * x0[j];
+  }
+  if (f1) {
+#pragma unroll
+    for (int j = 0; j < L; j++) s1 += v[j] * x1[j];
+  } else {
+#pragma unroll
+    for (int j = 0; j < L; j++)
+      if ((m1 >> j) & 1u) s1 += v[j] * x1[j];
+  }
+}
+__device__ __forceinline__ void st_row2_dispatch(uint32_t L, uint32_t m0, uint32_t m1, uint32_t dv_a, uint32_t dd_a, const double *__restrict__ x, int r0, int r1, double &s0,
+                                                 double &s1)
+{
+  switch (L) {
+  case 1: st_row2_fixed<1>(m0, m1, dv_a, dd_a, x, r0, r1, s0, s1); break;
+  case 2: st_row2_fixed<2>(m0, m1, dv_a, dd_a, x, r0, r1, s0, s1); break;
+  case 3: st_row2_fixed<3>(m0, m1, dv_a, dd_a, x, r0, r1, s0, s1); break;
+  case 4: st_row2_fixed<4>(m0, m1, dv_a, dd_a, x, r0, r1, s0, s1); break;
+  case 5: st_row2_fixed<5>(m0, m1, dv_a, dd_a, x, r0, r1, s0, s1); break;
+  case 6: st_row2_fixed<6>(m0, m1, dv_a, dd_a, x, r0, r1, s0, s1); break;
+  case 7: st_row2_fixed<7>(m0, m1, dv_a, dd_a, x, r0, r1, s0, s1); break;
+  default: st_row2_fixed<8>(m0, m1, dv_a, dd_a, x, r0, r1, s0, s1); break;
+  }
+}
+
+// i-th tile of the walk: tiles [ta, tb) first -- ascending, or descending when `rev` -- then the tiles outside that range
+__device__ __forceinline__ int tile_at(int i, int ta, int tb, bool rev)
+{
+  const int ni = tb - ta;
+  if (i < ni) return rev ? tb - 1 - i : ta + i;
+  const int j = i - ni;
+  return j < ta ? j : tb + (j - ta);
+}
+
+template <class Epi, int MINB>
+__global__ void __launch_bounds__(PK_CT + 32, MINB) k_spmv_pk(CsrDev A, const double *__restrict__ x, Epi epi, int blob_cap, int nstages, int vec_tma, TileOrder ord)
+{
+  pdl_enter();
   if (!epi.active()) return;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ uint64_t full_bar[TMA_MAX_STAGES], empty_bar[TMA_MAX_STAGES];
@@ -840,6 +985,7 @@ __global__ void __launch_bounds__(PK_CT + 32) k_spmv_pk(CsrDev A, const double *
   const int stage_bytes = blob_cap + nv * TR * 8;
   const int ntiles = (A.n + TR - 1) / TR;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool rev = epi.reverse();
   typename Epi::Acc acc;
   epi.init(acc);
   if (threadIdx.x == 0) {
@@ -855,15 +1001,18 @@ __global__ void __launch_bounds__(PK_CT + 32) k_spmv_pk(CsrDev A, const double *
     // ------------------------------ producer warp ------------------------------
     unsigned o0n = 0, o1n = 0;
     if (blockIdx.x < ntiles) {
-      o0n = __ldg(A.pk_off + blockIdx.x);
-      o1n = __ldg(A.pk_off + blockIdx.x + 1);
+      const int t0 = tile_at(blockIdx.x, ord.ta, ord.tb, rev);
+      o0n = __ldg(A.pk_off + t0);
+      o1n = __ldg(A.pk_off + t0 + 1);
     }
     int      s = 0, filled = 0;
     uint32_t ph = 0;
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    for (int i = blockIdx.x; i < ntiles; i += gridDim.x) {
+      const int      tile = tile_at(i, ord.ta, ord.tb, rev);
       const unsigned o0 = o0n, o1 = o1n;
-      const int      nt = tile + gridDim.x;
-      if (nt < ntiles) {   // directory entry of the next tile: in flight while this one is issued
+      const int      ni = i + gridDim.x;
+      if (ni < ntiles) {   // directory entry of the next tile: in flight while this one is issued
+        const int nt = tile_at(ni, ord.ta, ord.tb, rev);
         o0n = __ldg(A.pk_off + nt);
         o1n = __ldg(A.pk_off + nt + 1);
       }
@@ -901,7 +1050,8 @@ __global__ void __launch_bounds__(PK_CT + 32) k_spmv_pk(CsrDev A, const double *
     const uint32_t smem_a = smem_u32(smem_raw);
     int            s = 0;
     uint32_t       ph = 0;
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    for (int i = blockIdx.x; i < ntiles; i += gridDim.x) {
+      const int tile = tile_at(i, ord.ta, ord.tb, rev);
       mbar_wait(&full_bar[s], ph);
       const uint32_t st_a = smem_a + (uint32_t)s * (uint32_t)stage_bytes;
       const uint32_t vs_a = st_a + (uint32_t)blob_cap + 8u * threadIdx.x;
@@ -913,8 +1063,17 @@ __global__ void __launch_bounds__(PK_CT + 32) k_spmv_pk(CsrDev A, const double *
       const uint32_t dd_a = dv_a + ((nd + 1u) & ~1u) * 8u;
       const uint32_t q_a = dd_a + ((nd + 3u) & ~3u) * 4u;
       bool           done = false;
-      if (kind == 1 && ulen != 0xFFFFu && nrows == TR) {
-        // full tile of equal-length coded rows (the bulk of a stencil matrix): both rows together, loads up front
+      if (kind == 2) {
+        // stencil tile: pattern of nd entries + one presence byte per row (rows beyond the matrix end carry an empty mask)
+        const uint32_t m0 = (threadIdx.x < nrows) ? lds_u8(q_a + threadIdx.x) : 0u;
+        const uint32_t m1 = (threadIdx.x + PK_CT < nrows) ? lds_u8(q_a + threadIdx.x + PK_CT) : 0u;
+        double         s0, s1;
+        st_row2_dispatch(nd, m0, m1, dv_a, dd_a, x, r0, r1, s0, s1);
+        if (r0 < A.n) epi.row_s(r0, vs_a, s0, acc);
+        if (r1 < A.n) epi.row_s(r1, vs_a + PK_CT * 8u, s1, acc);
+        done = true;
+      } else if (kind == 1 && ulen != 0xFFFFu && nrows == TR) {
+        // full tile of equal-length coded rows: both rows together, loads up front
         const uint32_t ca0 = q_a + threadIdx.x * ulen, ca1 = ca0 + PK_CT * ulen;
         double         s0 = 0.0, s1 = 0.0;
         done = pad != 0xFFFFFFFFu ? pk_row2_dispatch<true>(ulen, ca0, ca1, dv_a, dd_a, x, r0, r1, pad, s0, s1)
@@ -1037,7 +1196,7 @@ static void launch_tma(const CsrDev &A, const double *x, const Epi &epi)
 
 
 template <class Epi>
-static int launch_pk(const CsrDev &A, const double *x, const Epi &epi)
+static int launch_pk(const CsrDev &A, const double *x, const Epi &epi, TileOrder ord)
 {
   if constexpr (!EpiHasStaged<Epi>::value) {
     set_error("internal: epilogue without staged vectors on a packed matrix");
@@ -1056,36 +1215,47 @@ static int launch_pk(const CsrDev &A, const double *x, const Epi &epi)
       set_error("packed SpMV tile does not fit in shared memory (%zu bytes)", smem);
       return 76;
     }
+    // register budget: 5 CTAs per SM (72 registers) by default, PERMON_B200_PK_OCC=4 lets the compiler use 96 (A/B measurements)
+    static int minb = 0;
+    if (!minb) {
+      const char *e = getenv("PERMON_B200_PK_OCC");
+      minb = (e && atoi(e) == 4) ? 4 : 5;
+    }
+    auto kern = (minb == 4) ? k_spmv_pk<Epi, 4> : k_spmv_pk<Epi, 5>;
     static size_t attr_smem = 0;
     if (smem > attr_smem) {
-      cudaFuncSetAttribute(k_spmv_pk<Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       attr_smem = smem;
     }
     static int    occ = 0;
     static size_t occ_smem = (size_t)-1;
     if (!occ || occ_smem != smem) {
       int nb = 0;
-      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_spmv_pk<Epi>, PK_CT + 32, smem) != cudaSuccess || nb < 1) nb = 1;
+      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, PK_CT + 32, smem) != cudaSuccess || nb < 1) nb = 1;
       occ      = nb;
       occ_smem = smem;
     }
     int ntiles = (A.n + TR - 1) / TR, grid = g_ctx.sm_count * occ;
     if (grid > ntiles) grid = ntiles;
     if (grid > max_red_blocks()) grid = max_red_blocks();
-    k_spmv_pk<Epi><<<grid, PK_CT + 32, smem, g_ctx.stream>>>(A, x, epi, blob_cap, nstages, vec_tma);
+    if (ord.tb <= ord.ta || ord.tb > ntiles) {   // no preference: all tiles in index order
+      ord.ta = 0;
+      ord.tb = ntiles;
+    }
+    launch_k(kern, grid, PK_CT + 32, smem, A, x, epi, blob_cap, nstages, vec_tma, ord);
     return 0;
   }
 }
 
 template <class Epi>
-static int launch_spmv(const CsrDev &A, const double *x, const Epi &epi, int family, double bytes)
+static int launch_spmv(const CsrDev &A, const double *x, const Epi &epi, int family, double bytes, TileOrder ord = TileOrder())
 {
   prof_pre(family, bytes);
   if (A.n == 0) {
     // still run one CTA so that reductions publish their (identity) record
     k_spmv_vector<Epi, 32><<<1, NT, 0, g_ctx.stream>>>(A, x, epi);
   } else if (A.kind == 3) {
-    PB_CHK(launch_pk(A, x, epi));
+    PB_CHK(launch_pk(A, x, epi, ord));
   } else if (A.kind == 2) {
     launch_tma(A, x, epi);
   } else if (A.kind == 0) {
@@ -1165,6 +1335,7 @@ struct EpiPlain {
   int     accumulate;
   struct Acc {};
   __device__ bool active() const { return true; }
+  __device__ bool reverse() const { return false; }
   __device__ void init(Acc &) const {}
   __device__ void row(int r, double ax, Acc &) const { y[r] = accumulate ? y[r] + ax : ax; }
   __device__ void finalize(Acc &) const {}
@@ -1185,6 +1356,7 @@ struct EpiGated {   // plain SpMV that only runs in the right phase of the devic
     if (S->reason != 0) return false;
     return phase == 0 ? true : (S->step == 'e' || S->init);
   }
+  __device__ bool reverse() const { return false; }
   __device__ void init(Acc &) const {}
   __device__ void row(int r, double ax, Acc &) const { y[r] = ax; }
   __device__ void finalize(Acc &) const {}
@@ -1197,57 +1369,73 @@ struct EpiGated {   // plain SpMV that only runs in the right phase of the devic
 
 struct AccRed {
   double v[PB_NRED];
+  int    halo_ok;   // this thread has seen every neighbour's halo flag (GhostMerge)
 };
 
-// K_A epilogue: Ap_r = (A p)_r ; p.Ap ; g.p ; B p ; max feasible step (QPCFeas)
+// off-diagonal part of row r (multi-GPU): MatMultAdd order, the ghost products are added one by one to the diagonal-block sum.
+// Out of line: it runs for the few rows next to a partition boundary only and must not cost the streaming loop any registers.
+__device__ __noinline__ double ghost_slow(const GhostMerge &gm, int r, double ax, int &halo_ok)
+{
+  const int k = __ldg(gm.row_map + (r < gm.lo ? r : r - gm.hi + gm.lo));
+  if (k < 0) return ax;
+  if (!halo_ok) {
+    for (int q = 0; q < gm.nflags; q++) wait_flag(gm.flags + (size_t)q * PB_FLAG_STRIDE, gm.seq);
+    halo_ok = 1;
+  }
+  const int e0 = __ldg(gm.oia + k), e1 = __ldg(gm.oia + k + 1);
+  for (int e = e0; e < e1; e++) ax += __ldg(gm.oa + e) * __ldcg(gm.ghost + __ldg(gm.oja + e));
+  return ax;
+}
+__device__ __forceinline__ double ghost_apply(const GhostMerge &gm, int r, double ax, int &halo_ok)
+{
+  if (gm.row_map == nullptr || (r >= gm.lo && r < gm.hi)) return ax;
+  return ghost_slow(gm, r, ax, halo_ok);
+}
+
+// K_A epilogue: Ap_r = (A p)_r ; p.Ap ; B p ; max feasible step (QPCFeas).  (g.p comes from the kernel that wrote p, see mpgp_ctl.h.)
 // MODE 1: lower bound only, no equality rows (the obstacle problems); MODE 2: lower and upper bound arrays, no equality rows
 // (two-sided boxes, C5); MODE 0: anything.  In modes 1 and 2 the staged path sheds every run-time flag.
 template <int MODE>
 struct EpiAT {
-  const double        *p, *g, *x;
+  const double        *p, *x;
   double              *Ap;
   BoxDev               bx;
   const double        *B;
   int                  m, n;
   const MpgpCtl       *S;
   RedBuf               rb;
-  SkipRows             skip;    // rows whose epilogue is deferred to the ghost pass (multi-GPU)
-  __device__ bool skipped(int r) const { return skip.flags && (r < skip.lo || r >= skip.hi) && skip.flags[r]; }
+  GhostMerge           gm;
   typedef AccRed       Acc;
   __device__ bool active() const { return S->reason == 0; }
+  __device__ bool reverse() const { return S->sweep != 0; }
   __device__ void init(Acc &a) const
   {
 #pragma unroll
     for (int k = 0; k < PB_NRED; k++) a.v[k] = 0.0;
     a.v[RA_FEAS] = HUGE_VAL;
+    a.halo_ok    = 0;
   }
-  __device__ void epilogue(int r, double ax, Acc &a) const
+  __device__ void row(int r, double ax, Acc &a) const
   {
+    ax    = ghost_apply(gm, r, ax, a.halo_ok);
+    Ap[r] = ax;
     const double pr = p[r];
     a.v[RA_PAP] += pr * ax;
-    a.v[RA_GP] += g[r] * pr;
 #pragma unroll
     for (int j = 0; j < PB_MAXEQ; j++)
       if (j < m) a.v[RA_BP + j] += B[(size_t)j * n + r] * pr;
     a.v[RA_FEAS] = box_feas_lazy(x[r], pr, load_box(bx, r), a.v[RA_FEAS]);
   }
-  __device__ void row(int r, double ax, Acc &a) const
-  {
-    Ap[r] = ax;
-    if (skipped(r)) return;
-    epilogue(r, ax, a);
-  }
   __device__ void finalize(Acc &a) const { grid_reduce8<(1 << RA_FEAS)>(a.v, rb, nullptr); }
-  // staged row vectors for the TMA kernel: p, g, x, [lb], [ub], [B_0..B_{m-1}]
-  __host__ __device__ int nvec() const { return 3 + (bx.lb ? 1 : 0) + (bx.ub ? 1 : 0) + m; }
+  // staged row vectors for the TMA kernels: p, x, [lb], [ub], [B_0..B_{m-1}]
+  __host__ __device__ int nvec() const { return 2 + (bx.lb ? 1 : 0) + (bx.ub ? 1 : 0) + m; }
   int nvec_host() const { return nvec(); }
   const double *vsrc_host(int i) const { return vsrc(i); }
   __host__ __device__ const double *vsrc(int i) const
   {
     if (i == 0) return p;
-    if (i == 1) return g;
-    if (i == 2) return x;
-    int k = 3;
+    if (i == 1) return x;
+    int k = 2;
     if (bx.lb) {
       if (i == k) return bx.lb;
       k++;
@@ -1261,22 +1449,21 @@ struct EpiAT {
   // va: shared-memory address of this row's slot in the first staged vector; vector k sits k * TR * 8 bytes further
   __device__ void row_s(int r, uint32_t va, double ax, Acc &a) const
   {
+    ax    = ghost_apply(gm, r, ax, a.halo_ok);
     Ap[r] = ax;
-    if (skipped(r)) return;
     const double pr = lds_f64(va);
     a.v[RA_PAP] += pr * ax;
-    a.v[RA_GP] += lds_f64(va + TR * 8) * pr;
-    const double xr = lds_f64(va + 2 * TR * 8);
+    const double xr = lds_f64(va + TR * 8);
     if constexpr (MODE != 0) {
       BoxVal b;
       b.has_lb = true;
       b.has_ub = (MODE == 2);
-      b.lb     = lds_f64(va + 3 * TR * 8);
-      b.ub     = (MODE == 2) ? lds_f64(va + 4 * TR * 8) : 0.0;
+      b.lb     = lds_f64(va + 2 * TR * 8);
+      b.ub     = (MODE == 2) ? lds_f64(va + 3 * TR * 8) : 0.0;
       a.v[RA_FEAS] = box_feas_lazy(xr, pr, b, a.v[RA_FEAS]);
     } else {
       BoxVal   b;
-      uint32_t k = 3;
+      uint32_t k = 2;
       b.has_lb = bx.lb != nullptr;
       b.has_ub = bx.ub != nullptr;
       b.lb     = b.has_lb ? lds_f64(va + (k++) * TR * 8) : 0.0;
@@ -1300,18 +1487,19 @@ struct EpiA2T {
   int                  m, n;
   const MpgpCtl       *S;
   RedBuf               rb;
-  SkipRows             skip;
-  __device__ bool skipped(int r) const { return skip.flags && (r < skip.lo || r >= skip.hi) && skip.flags[r]; }
+  GhostMerge           gm;
   typedef AccRed       Acc;
   __device__ bool active() const { return S->reason == 0 && (S->step == 'e' || S->init); }
+  __device__ bool reverse() const { return S->sweep != 0; }
   __device__ void init(Acc &a) const
   {
 #pragma unroll
     for (int k = 0; k < PB_NRED; k++) a.v[k] = 0.0;
+    a.halo_ok = 0;
   }
-  __device__ void epilogue(int r, double ax, Acc &a) const
+  __device__ void row(int r, double ax, Acc &a) const
   {
-    double gr = ax;
+    double gr = ghost_apply(gm, r, ax, a.halo_ok);
     if (m > 0) {
       double t = 0.0;
       for (int j = 0; j < m; j++) t += B[(size_t)j * n + r] * S->Bu[j];
@@ -1327,16 +1515,8 @@ struct EpiA2T {
     a.v[RB_GC2] += gc * gc;
     a.v[RB_GF2] += gf * gf;
   }
-  __device__ void row(int r, double ax, Acc &a) const
-  {
-    if (skipped(r)) {
-      g[r] = ax;   // partial product parked in g until the ghost pass
-      return;
-    }
-    epilogue(r, ax, a);
-  }
   __device__ void finalize(Acc &a) const { grid_reduce8<0>(a.v, rb, nullptr); }
-  // staged row vectors for the TMA kernel: x, b, [lb], [ub], [B_0..B_{m-1}]
+  // staged row vectors for the TMA kernels: x, b, [lb], [ub], [B_0..B_{m-1}]
   __host__ __device__ int nvec() const { return 2 + (bx.lb ? 1 : 0) + (bx.ub ? 1 : 0) + m; }
   int nvec_host() const { return nvec(); }
   const double *vsrc_host(int i) const { return vsrc(i); }
@@ -1357,12 +1537,8 @@ struct EpiA2T {
   }
   __device__ void row_s(int r, uint32_t va, double ax, Acc &a) const
   {
-    if (skipped(r)) {
-      g[r] = ax;
-      return;
-    }
     BoxVal bv;
-    double gr = ax;
+    double gr = ghost_apply(gm, r, ax, a.halo_ok);
     if constexpr (MODE != 0) {
       bv.has_lb = true;
       bv.has_ub = (MODE == 2);
@@ -1395,45 +1571,6 @@ struct EpiA2T {
 };
 typedef EpiA2T<0> EpiA2;
 
-// ghost pass (multi-GPU): add the off-diagonal block product to the parked partial result, then run the
-// deferred epilogue of K_A (SECOND = false) or K_A' (SECOND = true) for the boundary rows
-template <bool SECOND>
-struct EpiGhost {
-  EpiA          ea;
-  EpiA2         e2;
-  const double *prev;   // record of the diagonal pass, combined by the last CTA
-  HaloWait      hw;     // peer-memory halo: wait for the neighbours' pushes before touching the ghost buffer
-  typedef AccRed Acc;
-  __device__ void wait() const
-  {
-    if (hw.n > 0) {
-      if ((int)threadIdx.x < hw.n) wait_flag(hw.flags + (size_t)threadIdx.x * PB_FLAG_STRIDE, hw.seq);
-      __syncthreads();
-    }
-  }
-  __device__ bool active() const { return SECOND ? e2.active() : ea.active(); }
-  __device__ void init(Acc &a) const
-  {
-    if (SECOND) e2.init(a);
-    else ea.init(a);
-  }
-  __device__ void row(int r, double ax, Acc &a) const
-  {
-    if (SECOND) {
-      e2.epilogue(r, e2.g[r] + ax, a);
-    } else {
-      const double f = ea.Ap[r] + ax;
-      ea.Ap[r]       = f;
-      ea.epilogue(r, f, a);
-    }
-  }
-  __device__ void finalize(Acc &a) const
-  {
-    if (SECOND) grid_reduce8<0>(a.v, e2.rb, prev);
-    else grid_reduce8<(1 << RA_FEAS)>(a.v, ea.rb, prev);
-  }
-};
-
 int k_spmv(const CsrDev &A, const double *x, double *y, int accumulate)
 {
   EpiPlain e{y, accumulate};
@@ -1447,55 +1584,58 @@ int k_spmv_gated(const CsrDev &A, const double *x, double *y, const MpgpCtl *S, 
 }
 
 static double bytes_A(const CsrDev &A, const MpgpVecs &v)
-{   // CSR + p(gather) + g + x + lb[+ub] + B rows, write Ap
-  return csr_stream_bytes(A) + 8.0 * v.n * (4 + (v.bx.lb ? 1 : 0) + (v.bx.ub ? 1 : 0) + v.m);
+{   // matrix + p (gather; its row slice comes from the same lines) + x + lb[+ub] + B rows, write Ap
+  return csr_stream_bytes(A) + 8.0 * v.n * (3 + (v.bx.lb ? 1 : 0) + (v.bx.ub ? 1 : 0) + v.m);
 }
 static double bytes_A2(const CsrDev &A, const MpgpVecs &v)
-{   // CSR + x(gather) + b + lb[+ub] + B rows, write g, p
+{   // matrix + x (gather) + b + lb[+ub] + B rows, write g, p
   return csr_stream_bytes(A) + 8.0 * v.n * (4 + (v.bx.lb ? 1 : 0) + (v.bx.ub ? 1 : 0) + v.m);
 }
-
-int k_fused_A(const CsrDev &A, const double *xin, const MpgpVecs &v, const MpgpCtl *S, RedBuf rb, SkipRows skip)
+// tiles that lie entirely inside the rows without ghost columns go first (multi-GPU); otherwise index order
+static TileOrder tile_order(const CsrDev &A, const GhostMerge &gm)
 {
-  if (v.bx.lb && !v.bx.ub && v.m == 0) {
-    EpiAT<1> e{v.p, v.g, v.x, v.Ap, v.bx, v.B, v.m, v.n, S, rb, skip};
-    return launch_spmv(A, xin, e, KF_SPMV_A, bytes_A(A, v));
+  TileOrder o;
+  const int ntiles = (A.n + TR - 1) / TR;
+  o.ta = 0;
+  o.tb = ntiles;
+  if (gm.row_map) {
+    int ta = (gm.lo + TR - 1) / TR, tb = gm.hi / TR;
+    if (tb > ta) {
+      o.ta = ta;
+      o.tb = tb;
+    }
   }
-  if (v.bx.lb && v.bx.ub && v.m == 0) {
-    EpiAT<2> e{v.p, v.g, v.x, v.Ap, v.bx, v.B, v.m, v.n, S, rb, skip};
-    return launch_spmv(A, xin, e, KF_SPMV_A, bytes_A(A, v));
-  }
-  EpiA e{v.p, v.g, v.x, v.Ap, v.bx, v.B, v.m, v.n, S, rb, skip};
-  return launch_spmv(A, xin, e, KF_SPMV_A, bytes_A(A, v));
+  return o;
 }
 
-int k_fused_A2(const CsrDev &A, const double *xin, const MpgpVecs &v, const MpgpCtl *S, RedBuf rb, SkipRows skip)
+int k_fused_A(const CsrDev &A, const double *xin, const MpgpVecs &v, const MpgpCtl *S, RedBuf rb, const GhostMerge &gm)
 {
+  const TileOrder ord = tile_order(A, gm);
   if (v.bx.lb && !v.bx.ub && v.m == 0) {
-    EpiA2T<1> e{v.x, v.b, v.g, v.p, v.bx, v.B, v.m, v.n, S, rb, skip};
-    return launch_spmv(A, xin, e, KF_SPMV_A2, bytes_A2(A, v));
+    EpiAT<1> e{v.p, v.x, v.Ap, v.bx, v.B, v.m, v.n, S, rb, gm};
+    return launch_spmv(A, xin, e, KF_SPMV_A, bytes_A(A, v), ord);
   }
   if (v.bx.lb && v.bx.ub && v.m == 0) {
-    EpiA2T<2> e{v.x, v.b, v.g, v.p, v.bx, v.B, v.m, v.n, S, rb, skip};
-    return launch_spmv(A, xin, e, KF_SPMV_A2, bytes_A2(A, v));
+    EpiAT<2> e{v.p, v.x, v.Ap, v.bx, v.B, v.m, v.n, S, rb, gm};
+    return launch_spmv(A, xin, e, KF_SPMV_A, bytes_A(A, v), ord);
   }
-  EpiA2 e{v.x, v.b, v.g, v.p, v.bx, v.B, v.m, v.n, S, rb, skip};
-  return launch_spmv(A, xin, e, KF_SPMV_A2, bytes_A2(A, v));
+  EpiA e{v.p, v.x, v.Ap, v.bx, v.B, v.m, v.n, S, rb, gm};
+  return launch_spmv(A, xin, e, KF_SPMV_A, bytes_A(A, v), ord);
 }
 
-int k_fused_A_ghost(const CsrDev &Ao, const double *ghost, const MpgpVecs &v, const MpgpCtl *S, RedBuf rb, int second, HaloWait hw)
+int k_fused_A2(const CsrDev &A, const double *xin, const MpgpVecs &v, const MpgpCtl *S, RedBuf rb, const GhostMerge &gm)
 {
-  // rb.out: final record; the diagonal pass left its record in rb.out as well -> read it as `prev`
-  RedBuf rd = rb;
-  EpiA  ea{v.p, v.g, v.x, v.Ap, v.bx, v.B, v.m, v.n, S, rd, SkipRows()};
-  EpiA2 e2{v.x, v.b, v.g, v.p, v.bx, v.B, v.m, v.n, S, rd, SkipRows()};
-  double bytes = 12.0 * (double)Ao.nnz + 8.0 * Ao.n * 8;
-  if (second) {
-    EpiGhost<true> e{ea, e2, rb.out, hw};
-    return launch_spmv(Ao, ghost, e, KF_SPMV_A2, bytes);
+  const TileOrder ord = tile_order(A, gm);
+  if (v.bx.lb && !v.bx.ub && v.m == 0) {
+    EpiA2T<1> e{v.x, v.b, v.g, v.p, v.bx, v.B, v.m, v.n, S, rb, gm};
+    return launch_spmv(A, xin, e, KF_SPMV_A2, bytes_A2(A, v), ord);
   }
-  EpiGhost<false> e{ea, e2, rb.out, hw};
-  return launch_spmv(Ao, ghost, e, KF_SPMV_A, bytes);
+  if (v.bx.lb && v.bx.ub && v.m == 0) {
+    EpiA2T<2> e{v.x, v.b, v.g, v.p, v.bx, v.B, v.m, v.n, S, rb, gm};
+    return launch_spmv(A, xin, e, KF_SPMV_A2, bytes_A2(A, v), ord);
+  }
+  EpiA2 e{v.x, v.b, v.g, v.p, v.bx, v.B, v.m, v.n, S, rb, gm};
+  return launch_spmv(A, xin, e, KF_SPMV_A2, bytes_A2(A, v), ord);
 }
 
 // peer-memory halo push: dst_q[k] = vec[send_idx[k]] written straight into the neighbours' ghost buffers, then a
@@ -1640,6 +1780,7 @@ __global__ void __launch_bounds__(NT, EQ ? 3 : 4) k_update_B(MpgpVecs v, CtrlFol
 {
   __shared__ MpgpCtl sS;
   __shared__ int     s_plast;
+  pdl_enter();
   const MpgpCtl     *S = cf.Sin;
   if (cf.fold) {   // ctrl_A in the prologue: step selection from the K_A records (mpgp.c:541-547,617-621)
     if (cf.Sin->reason != 0) {
@@ -1670,6 +1811,9 @@ __global__ void __launch_bounds__(NT, EQ ? 3 : 4) k_update_B(MpgpVecs v, CtrlFol
   for (int k = 0; k < PB_NRED; k++) acc[k] = 0.0;
   const bool has_lb = v.bx.lb != nullptr, has_ub = v.bx.ub != nullptr;
   const int  stride = gridDim.x * NT;
+  // serpentine sweeps: K_B walks the rows against the direction K_A just used, so that the tail of K_A's stream (the last
+  // Ap / p / x / lb lines it touched) is still in L2 when K_B starts there
+  const bool rev = S->serp && (S->sweep == 0);
 
   if (VEC2) {
     const int      n2 = n >> 1;
@@ -1681,7 +1825,8 @@ __global__ void __launch_bounds__(NT, EQ ? 3 : 4) k_update_B(MpgpVecs v, CtrlFol
       glo = hp->gap_lo;
       ghi = hp->gap_hi;
     }
-    for (int i = blockIdx.x * NT + threadIdx.x; i < n2; i += stride) {
+    for (int i0 = blockIdx.x * NT + threadIdx.x; i0 < n2; i0 += stride) {
+      const int     i = rev ? n2 - 1 - i0 : i0;
       const double2 xr = x2[i], pr = p2[i], g0 = g2[i], ap = A2[i];
       BoxVal        b0, b1;
       b0.has_lb = b1.has_lb = has_lb;
@@ -1731,7 +1876,8 @@ __global__ void __launch_bounds__(NT, EQ ? 3 : 4) k_update_B(MpgpVecs v, CtrlFol
       glo = hp->gap_lo;
       ghi = hp->gap_hi;
     }
-    for (int r = blockIdx.x * NT + threadIdx.x; r < n; r += stride) {
+    for (int r0 = blockIdx.x * NT + threadIdx.x; r0 < n; r0 += stride) {
+      const int    r = rev ? n - 1 - r0 : r0;
       const double xr = v.x[r], pr = v.p[r], g0 = v.g[r];
       double       brow[PB_MAXEQ];
       const double apr = penal_apr<EQ>(v.Ap[r], rho, v.B, n, r, m, bp, brow);
@@ -1757,8 +1903,8 @@ __global__ void __launch_bounds__(NT, EQ ? 3 : 4) k_update_B(MpgpVecs v, CtrlFol
 template <bool EQ, bool VEC2>
 static void launch_B(int grid, const MpgpVecs &v, const CtrlFold &cf, RedBuf rb, const PushRanges *hp, unsigned long long seq)
 {
-  if (hp) k_update_B<EQ, VEC2, true><<<grid, NT, 0, g_ctx.stream>>>(v, cf, rb, hp, seq);
-  else k_update_B<EQ, VEC2, false><<<grid, NT, 0, g_ctx.stream>>>(v, cf, rb, nullptr, 0);
+  if (hp) launch_k(k_update_B<EQ, VEC2, true>, grid, NT, 0, v, cf, rb, hp, seq);
+  else launch_k(k_update_B<EQ, VEC2, false>, grid, NT, 0, v, cf, rb, (const PushRanges *)nullptr, 0ull);
 }
 int k_fused_B(const MpgpVecs &v, const CtrlFold &cf, RedBuf rb, const PushRanges *hp, unsigned long long push_seq)
 {
@@ -1786,10 +1932,11 @@ int k_fused_B(const MpgpVecs &v, const CtrlFold &cf, RedBuf rb, const PushRanges
 // K_C: direction update  (mpgp.c:560 p = gf - bcg p ; :623 p = gc)
 // =====================================================================================================
 template <bool PUSH>
-__global__ void __launch_bounds__(NT, 8) k_direction_C(MpgpVecs v, CtrlFold cf, const PushRanges *__restrict__ hp, unsigned long long push_seq, int vec2)
+__global__ void __launch_bounds__(NT, 8) k_direction_C(MpgpVecs v, CtrlFold cf, RedBuf rc, const PushRanges *__restrict__ hp, unsigned long long push_seq, int vec2)
 {
   __shared__ MpgpCtl sS;
   __shared__ int     s_plast;
+  pdl_enter();
   const MpgpCtl     *S = cf.Sin;
   if (cf.fold) {   // ctrl_B in the prologue: norms, stopping test, beta, next step kind (mpgp.c:514-535,558-559)
     if (cf.Sin->reason != 0) return;
@@ -1807,7 +1954,9 @@ __global__ void __launch_bounds__(NT, 8) k_direction_C(MpgpVecs v, CtrlFold cf, 
   const int    pmode = S->pmode;
   const double bcg = S->bcg, astol = v.bx.astol;
   const int    stride = gridDim.x * NT;
+  const bool   rev = S->serp && (S->sweep == 0);   // the direction of this iteration's K_A (ctrl_B has already flipped `sweep`)
   if (pmode == 1) {
+    double gp = 0.0;   // g.p of the new direction (mpgp.c:541 of the coming iteration): K_A's record carries it
     if (vec2) {
       const double2 *g2 = reinterpret_cast<const double2 *>(v.g);
       const uchar2  *a2 = reinterpret_cast<const uchar2 *>(v.gf);   // K_B's byte mask lives in the gf array
@@ -1818,25 +1967,32 @@ __global__ void __launch_bounds__(NT, 8) k_direction_C(MpgpVecs v, CtrlFold cf, 
         glo = hp->gap_lo;
         ghi = hp->gap_hi;
       }
-      for (int i = blockIdx.x * NT + threadIdx.x; i < n2; i += stride) {
+      for (int i0 = blockIdx.x * NT + threadIdx.x; i0 < n2; i0 += stride) {
+        const int     i = rev ? n2 - 1 - i0 : i0;
         const double2 gg = g2[i], q = p2[i];
         const uchar2  am = a2[i];
         double2       pn;
         pn.x  = (am.x ? 0.0 : gg.x) - bcg * q.x;
         pn.y  = (am.y ? 0.0 : gg.y) - bcg * q.y;
         p2[i] = pn;
+        gp += gg.x * pn.x;
+        gp += gg.y * pn.y;
         if (PUSH && (2 * i < glo || 2 * i + 1 >= ghi)) {
           push_boundary(hp, 2 * i, pn.x);
           push_boundary(hp, 2 * i + 1, pn.y);
         }
       }
     } else {
-      for (int r = blockIdx.x * NT + threadIdx.x; r < v.n; r += stride) {
-        const double pn = (reinterpret_cast<const unsigned char *>(v.gf)[r] ? 0.0 : v.g[r]) - bcg * v.p[r];
+      for (int r0 = blockIdx.x * NT + threadIdx.x; r0 < v.n; r0 += stride) {
+        const int    r = rev ? v.n - 1 - r0 : r0;
+        const double gg = v.g[r];
+        const double pn = (reinterpret_cast<const unsigned char *>(v.gf)[r] ? 0.0 : gg) - bcg * v.p[r];
         v.p[r]          = pn;
+        gp += gg * pn;
         if (PUSH) push_boundary(hp, r, pn);
       }
     }
+    grid_reduce1(gp, rc, RA_GP);
   } else if (pmode == 2) {
     for (int r = blockIdx.x * NT + threadIdx.x; r < v.n; r += stride) {
       double gf, gc;
@@ -1855,7 +2011,7 @@ __global__ void __launch_bounds__(NT, 8) k_direction_C(MpgpVecs v, CtrlFold cf, 
   if (PUSH) push_signal(hp, push_seq, &s_plast);
 }
 
-int k_fused_C(const MpgpVecs &v, const CtrlFold &cf, const PushRanges *hp, unsigned long long push_seq)
+int k_fused_C(const MpgpVecs &v, const CtrlFold &cf, RedBuf rc, const PushRanges *hp, unsigned long long push_seq)
 {
   int grid = elementwise_grid();
   int need = (v.n + NT - 1) / NT;
@@ -1863,8 +2019,8 @@ int k_fused_C(const MpgpVecs &v, const CtrlFold &cf, const PushRanges *hp, unsig
   if (grid > need) grid = need;
   const int vec2 = (v.n % 2 == 0) && aligned16(v.gf) && aligned16(v.g) && aligned16(v.p) && !getenv("PERMON_B200_NOVEC");
   prof_pre(KF_DIR_C, 8.0 * v.n * 3.125);
-  if (hp) k_direction_C<true><<<grid, NT, 0, g_ctx.stream>>>(v, cf, hp, push_seq, vec2);
-  else k_direction_C<false><<<grid, NT, 0, g_ctx.stream>>>(v, cf, nullptr, 0, vec2);
+  if (hp) launch_k(k_direction_C<true>, grid, NT, 0, v, cf, rc, hp, push_seq, vec2);
+  else launch_k(k_direction_C<false>, grid, NT, 0, v, cf, rc, (const PushRanges *)nullptr, 0ull, vec2);
   prof_post(KF_DIR_C);
   LAUNCH_CHECK();
   return 0;
@@ -1873,6 +2029,7 @@ int k_fused_C(const MpgpVecs &v, const CtrlFold &cf, const PushRanges *hp, unsig
 // initial projection x = P(x) (mpgp.c:497) + B u of the projected iterate
 __global__ void __launch_bounds__(NT) k_project_init(MpgpVecs v, const MpgpCtl *__restrict__ S, RedBuf rb)
 {
+  pdl_enter();
   if (S->reason != 0) return;
   double acc[PB_NRED];
 #pragma unroll

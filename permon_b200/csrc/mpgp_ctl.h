@@ -21,6 +21,9 @@
 #define PB_MAXRANKS 16
 
 // reduction record after the SpMV kernel K_A:   [pAp, g.p, Bp_0..3, afeas(min), unused]
+//   g.p is not computed by K_A itself: whoever produces the direction p knows it.  After p = gf (initial gradient, expansion,
+//   proportioning update) g.p = |gf|^2 and after p = gc it is |gc|^2, term by term (gf_i is g_i or 0) -- ctrl_B keeps that
+//   value (gp_known); after p = gf - beta p (CG) K_C accumulates g.p while it writes p and K_A's record carries that partial sum.
 // reduction record after K_B / K_A':            [gP2, gc2, gf2, Ap.gf, Bu_0..3]
 enum { RA_PAP = 0, RA_GP = 1, RA_BP = 2, RA_FEAS = 6 };
 enum { RB_GP2 = 0, RB_GC2 = 1, RB_GF2 = 2, RB_APGF = 3, RB_BU = 4 };
@@ -33,6 +36,7 @@ struct MpgpCtl {
   int    inner_mode;      // 0: QPSConvergedDefault, 1: QPSConverged_Inner_SMALXE
   int    host_conv;       // 1: the host runs monitors / the convergence test (ctrl_B leaves `reason` alone)
   int    nranks, m;       // ranks in the rank-ordered reductions; equality rows in the fused rank-m update
+  int    serp;            // 1: serpentine sweeps (consecutive kernels walk the rows in opposite directions)
   double gamma2, alpha, rho;
   double rtol, atol, ttol, divtol, norm_rhs_div;          // QPSConvergedDefaultCtx (qpsimpl.h:73-76)
   // SMALXE inner test (smalxeimpl.h:5-11 and the outer QPS fields it reads)
@@ -45,8 +49,10 @@ struct MpgpCtl {
   int    do_prop;         // the coming step is a proportioning step
   int    pmode;           // what K_C does: 0 nothing, 1 p = gf - bcg p, 2 p = gc
   int    init;            // the initial gradient evaluation is in flight
+  int    gp_known;        // g.p of the coming K_A is gp_next (p = gf or p = gc), not the record sum
+  int    sweep;           // direction of the coming K_A sweep (0 ascending rows); K_B runs the other way, K_A' / K_C this way again
   int    nmv, ncg, nexp, nprop, M1_hits, eta_hits;
-  double rnorm, gP2, gc2, gf2, Apgf, pAp, gp, afeas, acg, bcg;
+  double rnorm, gP2, gc2, gf2, Apgf, pAp, gp, afeas, acg, bcg, gp_next;
   double normBu, enorm, outer_rnorm, MNormBu;
   double Bp[PB_MAXEQ], Bu[PB_MAXEQ];
 };
@@ -60,7 +66,7 @@ PB_HD inline void mpgp_ctrl_A(MpgpCtl *S, const double *ra)
   for (int r = 0; r < S->nranks; r++) {
     const double *q = ra + r * PB_NRED;
     pAp += q[RA_PAP];
-    gp += q[RA_GP];
+    gp += q[RA_GP];   // K_C's partial sums of g.p (CG direction update), carried by the K_A records
     for (int j = 0; j < S->m; j++) bp[j] += q[RA_BP + j];
     if (q[RA_FEAS] < afeas) afeas = q[RA_FEAS];
   }
@@ -68,6 +74,7 @@ PB_HD inline void mpgp_ctrl_A(MpgpCtl *S, const double *ra)
     pAp += S->rho * bp[j] * bp[j];
     S->Bp[j] = bp[j];
   }
+  if (S->gp_known) gp = S->gp_next;   // p = gf / p = gc: VecDot(g,p) is |gf|^2 / |gc|^2
   S->pAp   = pAp;
   S->gp    = gp;
   S->afeas = afeas;
@@ -185,4 +192,8 @@ PB_HD inline void mpgp_ctrl_B(MpgpCtl *S, const double *rb)
   S->do_prop = !(gc2 <= S->gamma2 * gf2);   // mpgp.c:535
   S->pmode   = S->do_prop ? 2 : (was_cg ? 1 : 0);
   if (S->reason != PB_REASON_ITERATING) S->pmode = 0;
+  // VecDot(g, p) of the coming iteration (mpgp.c:541): p = gc -> sum g_i gc_i = |gc|^2 ; p = gf -> |gf|^2 ; CG direction: K_C sums it
+  S->gp_known = (S->pmode != 1);
+  S->gp_next  = (S->pmode == 2) ? gc2 : gf2;
+  S->sweep ^= S->serp;
 }

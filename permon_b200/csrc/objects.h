@@ -70,7 +70,7 @@ struct HaloPlan {
   std::vector<PetscInt> send_idx;    // local indices to pack, grouped by neighbour
   int                  *d_send_idx = nullptr;
   double               *d_send = nullptr, *d_ghost = nullptr;
-  unsigned char        *d_skip = nullptr;   // [n] 1 for rows with ghost columns
+  int                  *d_row_map = nullptr;   // rows outside [skip_lo, skip_hi): index of the row in the compressed off-diagonal block, -1 = none
   int                   skip_lo = 0, skip_hi = 0;   // widest run of rows without ghost columns
   PetscInt              nboundary = 0;
   cudaEvent_t           ev_packed = nullptr, ev_arrived = nullptr, ev_consumed = nullptr;

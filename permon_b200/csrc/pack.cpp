@@ -18,6 +18,11 @@
 //   "skip" code (= ndict, stored in the header as pad = code + 1; its dictionary slot is (0, 0.0) and is never multiplied),
 //   so that the kernel's unrolled equal-length path handles them too.
 //   raw:   double a[nnz2] ; int ja[nnz4] ; u16 rowoff[ro8]
+//   stencil (kind 2): double val[L2] ; int delta[L4] ; u8 present[nrows16]
+//          every row of the tile is the tile's PATTERN -- the L <= 8 (col - row, value) pairs of its longest row, in storage order --
+//          with some entries missing (constant-coefficient stencils: rows next to a grid boundary lack the neighbours that fall
+//          outside); one presence byte per ROW replaces the code byte per non-zero, and the kernel reads deltas and values as
+//          warp-uniform operands.  PERMON_B200_PACK_STENCIL=0 turns the form off (A/B measurements, tests of the coded form).
 #include "device.h"
 #include <omp.h>
 #include <algorithm>
@@ -35,6 +40,7 @@ size_t pk_coded_bytes(int ndict, int nrows, int nnz, bool uniform)
   b += up(nnz, 16);
   return up(b, 16);
 }
+size_t pk_stencil_bytes(int L, int nrows) { return up(sizeof(PkHeader) + up(L, 2) * 8 + up(L, 4) * 4 + up((size_t)nrows, 16), 16); }
 size_t pk_raw_bytes(int nrows, int nnz)
 {
   return up(sizeof(PkHeader) + up(nnz, 2) * 8 + up(nnz, 4) * 4 + up((size_t)nrows + 1, 8) * 2, 16);
@@ -95,8 +101,11 @@ int pk_build(int n, const int *ia, const int *ja, const double *a, RawBuf &blob,
   std::vector<int>           tthr(ntiles, 0);    // which thread's arena holds the tile's dictionary ...
   std::vector<size_t>        tdoff(ntiles, 0);   // ... and where
   const int64_t  nnz_all = n > 0 ? ia[n] : 0;
-  unsigned char *codes_tmp = (unsigned char *)malloc((size_t)std::max<int64_t>(nnz_all, 1));
+  unsigned char *codes_tmp = (unsigned char *)malloc((size_t)std::max<int64_t>(nnz_all, 1) + (size_t)std::max(n, 1));
   if (!codes_tmp) return 55;
+  unsigned char *masks_tmp = codes_tmp + (size_t)std::max<int64_t>(nnz_all, 1);   // one presence byte per row (stencil tiles)
+  const char    *env_st = getenv("PERMON_B200_PACK_STENCIL");
+  const bool     use_stencil = !(env_st && env_st[0] == '0');
   const int nthr = omp_get_max_threads();
   std::vector<std::vector<int>>      arena_d(nthr);
   std::vector<std::vector<uint64_t>> arena_b(nthr);
@@ -115,6 +124,68 @@ int pk_build(int n, const int *ia, const int *ja, const double *a, RawBuf &blob,
       if (nnz > 65535) {
         bad = true;
         continue;
+      }
+      if (use_stencil) {
+        // stencil form: the pattern is the ordered union of the rows' (delta, value) pairs -- rows must be sorted by column, a delta
+        // must always carry the same value bits, and the union must not exceed 8 entries; every row is then a sub-sequence of it
+        int      L = 0, pd[8];
+        uint64_t pb[8];
+        bool     st = (nnz > 0);
+        for (int r = r0; r < r1 && st; r++) {
+          int j = 0, prev_d = 0;
+          for (int k = ia[r]; k < ia[r + 1]; k++) {
+            uint64_t b;
+            memcpy(&b, &a[k], 8);
+            const int d = ja[k] - r;
+            if (k > ia[r] && d <= prev_d) {
+              st = false;
+              break;
+            }
+            prev_d = d;
+            while (j < L && pd[j] < d) j++;
+            if (j < L && pd[j] == d) {
+              if (pb[j] != b) {
+                st = false;
+                break;
+              }
+            } else {
+              if (L == 8) {
+                st = false;
+                break;
+              }
+              for (int q = L; q > j; q--) {
+                pd[q] = pd[q - 1];
+                pb[q] = pb[q - 1];
+              }
+              pd[j] = d;
+              pb[j] = b;
+              L++;
+            }
+            j++;
+          }
+        }
+        if (st) {
+          for (int r = r0; r < r1; r++) {
+            int      j = 0;
+            unsigned m = 0;
+            for (int k = ia[r]; k < ia[r + 1]; k++) {
+              const int d = ja[k] - r;
+              while (pd[j] != d) j++;
+              m |= 1u << j;
+              j++;
+            }
+            masks_tmp[r] = (unsigned char)m;
+          }
+          tkind[t] = 2;
+          tnd[t]   = (uint16_t)L;
+          tthr[t]  = me;
+          tdoff[t] = ad.size();
+          ad.insert(ad.end(), pd, pd + L);
+          ab.insert(ab.end(), pb, pb + L);
+          tbytes[t] = (unsigned)pk_stencil_bytes(L, r1 - r0);
+          coded++;
+          continue;
+        }
       }
       D.reset();
       bool      ok = true, uniform = true;
@@ -198,7 +269,15 @@ int pk_build(int n, const int *ia, const int *ja, const double *a, RawBuf &blob,
     H.kind  = tkind[t];
     H.nnz   = (uint32_t)nnz;
     H.nrows = (uint16_t)nrows;
-    if (tkind[t] == 1) {
+    if (tkind[t] == 2) {
+      const int L = tnd[t];
+      H.ndict = (uint16_t)L;
+      H.ulen  = (uint16_t)L;
+      const size_t o_val = sizeof(PkHeader), o_del = o_val + up(L, 2) * 8, o_mask = o_del + up(L, 4) * 4;
+      memcpy(p + o_val, arena_b[tthr[t]].data() + tdoff[t], (size_t)L * 8);
+      memcpy(p + o_del, arena_d[tthr[t]].data() + tdoff[t], (size_t)L * 4);
+      memcpy(p + o_mask, masks_tmp + r0, (size_t)nrows);
+    } else if (tkind[t] == 1) {
       const int plen = tpad[t];                     // > 0: rows padded to this length with the skip code
       const int nd0 = tnd[t], nd = nd0 + (plen ? 1 : 0);   // the skip code owns a (0, 0.0) slot at the end of the dictionary
       H.ndict = (uint16_t)nd;

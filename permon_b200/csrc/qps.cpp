@@ -476,7 +476,7 @@ struct MpgpImpl : QPSImpl {   // QPS_MPGP mpgpimpl.h:5-38
   Vec              expdirection = nullptr, explengthvec = nullptr, explengthvecold = nullptr, xold = nullptr;
   // device-driven engine
   MpgpCtl *dS = nullptr, *hS = nullptr;
-  Reducer  RA, RB;
+  Reducer  RA, RB, RC;   // records after K_A, after K_B / K_A', and K_C's local g.p
   bool     engine_ready = false;
 
   ~MpgpImpl() override { free_all(); }
@@ -489,6 +489,7 @@ struct MpgpImpl : QPSImpl {   // QPS_MPGP mpgpimpl.h:5-38
       cudaFreeHost(hS);
       RA.destroy();
       RB.destroy();
+      RC.destroy();
       engine_ready = false;
     }
   }
@@ -645,6 +646,7 @@ int MpgpImpl::engine_init(QPS qps)
   PB_CUDA(cudaMallocHost(&hS, sizeof(MpgpCtl)));
   PB_CHK(RA.init(qps->comm));
   PB_CHK(RB.init(qps->comm));
+  PB_CHK(RC.init(qps->comm));
   engine_ready = true;
   return 0;
 }
@@ -671,13 +673,6 @@ int MpgpImpl::solve_fused(QPS qps)
   Mat        M1 = prod ? base->M1 : base, M2 = prod ? base->M2 : nullptr;
   const bool multi = (qps->comm->size > 1);
   HaloPlan  *H = multi ? M1->halo : nullptr;
-  SkipRows skip;
-  if (H) {
-    skip.flags = H->d_skip;
-    skip.lo    = H->skip_lo;
-    skip.hi    = H->skip_hi;
-  }
-
   v.n = qp->x->n;
   PB_CHK(vec_dev_rw(qp->x, &v.x));
   PB_CHK(vec_dev_read(qp->b, &v.b));
@@ -711,6 +706,10 @@ int MpgpImpl::solve_fused(QPS qps)
   }
   S.host_conv = host_conv ? 1 : 0;
   S.iteration = 0; S.reason = 0; S.step = ' '; S.do_prop = 0; S.pmode = 0; S.init = 1;
+  {
+    const char *e = getenv("PERMON_B200_SERPENTINE");
+    S.serp = (e && !strcmp(e, "0")) ? 0 : 1;
+  }
   *hS = S;
   PB_CUDA(cudaMemcpyAsync(dS, hS, sizeof(MpgpCtl), cudaMemcpyHostToDevice, s));
 
@@ -728,6 +727,10 @@ int MpgpImpl::solve_fused(QPS qps)
   const bool fused_push = p2p && H->contig && !getenv("PERMON_B200_NOFUSEDPUSH");
   auto red = [&](Reducer &R, int kind, bool publish) -> RedBuf {
     RedBuf rb = R.rb;
+    if (kind == 0) {   // K_A: slot RA_GP of its record is the local g.p that K_C summed while it wrote p
+      rb.add1      = RC.rb.out + RA_GP;
+      rb.add1_slot = RA_GP;
+    }
     if (p2p && publish) {
       rb.win  = comm->d_win;
       rb.kind = kind;
@@ -744,6 +747,25 @@ int MpgpImpl::solve_fused(QPS qps)
     PB_CHK(RB.gather());
     return k_ctrl_E(S1, RB.d_all);
   };
+  auto ghost_merge = [&](int which) -> GhostMerge {   // which: 0 = ghosts of p (K_A), 1 = ghosts of x (K_A')
+    GhostMerge gm;
+    if (!H) return gm;
+    gm.row_map = H->d_row_map;
+    gm.lo      = H->skip_lo;
+    gm.hi      = H->skip_hi;
+    gm.oia     = M1->Ao.ia;
+    gm.oja     = M1->Ao.ja;
+    gm.oa      = M1->Ao.a;
+    if (p2p) {
+      gm.ghost  = H->d_ghost2[which];
+      gm.flags  = H->my_hflags[which];
+      gm.nflags = (int)H->neigh.size();
+      gm.seq    = H->hseq[which];
+    } else {
+      gm.ghost = H->d_ghost;   // ncclRecv target; the stream already waits for the transfer (mat_halo_end)
+    }
+    return gm;
+  };
   auto second_spmv = [&](bool x_already_pushed) -> int {   // K_A' with its halo / product plumbing
     const double *xin = v.x;
     if (prod) {
@@ -757,16 +779,8 @@ int MpgpImpl::solve_fused(QPS qps)
         PB_CHK(mat_halo_begin(M1, v.x));
       }
     }
-    PB_CHK(k_fused_A2(M1->Ad, xin, v, S1, red(RB, 2, !H), skip));
-    if (H) {
-      if (p2p) {
-        HaloWait hw{H->my_hflags[1], (int)H->neigh.size(), H->hseq[1]};
-        PB_CHK(k_fused_A_ghost(M1->Ao, H->d_ghost2[1], v, S1, red(RB, 2, true), 1, hw));
-      } else {
-        PB_CHK(mat_halo_end(M1));
-        PB_CHK(k_fused_A_ghost(M1->Ao, H->d_ghost, v, S1, RB.rb, 1, HaloWait()));
-      }
-    }
+    if (H && !p2p) PB_CHK(mat_halo_end(M1));
+    PB_CHK(k_fused_A2(M1->Ad, xin, v, S1, red(RB, 2, true), ghost_merge(1)));
     return 0;
   };
   auto step_B = [&]() -> int {   // [all-gather] -> ctrl_A -> K_B (+ x halo push in expansion steps)
@@ -801,8 +815,8 @@ int MpgpImpl::solve_fused(QPS qps)
       cf.seq0   = comm->seq[1];
       cf.seq1   = comm->seq[2];
     }
-    if (fused_push) return k_fused_C(v, cf, H->d_ranges, ++H->hseq[0]);
-    return k_fused_C(v, cf, nullptr, 0);
+    if (fused_push) return k_fused_C(v, cf, RC.rb, H->d_ranges, ++H->hseq[0]);
+    return k_fused_C(v, cf, RC.rb, nullptr, 0);
   };
   auto ctrl_B_standalone = [&]() -> int {
     if (p2p) return k_ctrl_B_p2p(S0, comm->d_win, comm->my_slot, comm->my_flag, comm->seq[1], comm->seq[2]);
@@ -864,16 +878,8 @@ int MpgpImpl::solve_fused(QPS qps)
           PB_CHK(mat_halo_begin(M1, v.p));
         }
       }
-      PB_CHK(k_fused_A(M1->Ad, xin, v, S0, red(RA, 0, !H), skip));
-      if (H) {
-        if (p2p) {
-          HaloWait hw{H->my_hflags[0], (int)H->neigh.size(), H->hseq[0]};
-          PB_CHK(k_fused_A_ghost(M1->Ao, H->d_ghost2[0], v, S0, red(RA, 0, true), 0, hw));
-        } else {
-          PB_CHK(mat_halo_end(M1));
-          PB_CHK(k_fused_A_ghost(M1->Ao, H->d_ghost, v, S0, RA.rb, 0, HaloWait()));
-        }
-      }
+      if (H && !p2p) PB_CHK(mat_halo_end(M1));
+      PB_CHK(k_fused_A(M1->Ad, xin, v, S0, red(RA, 0, true), ghost_merge(0)));
       PB_CHK(step_B());
       if (v.m > 0) PB_CHK(gather_ctrl_E());
       PB_CHK(second_spmv(fused_push));

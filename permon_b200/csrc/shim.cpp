@@ -910,7 +910,7 @@ _p_Mat::~_p_Mat()
     cudaFree(halo->d_send_idx);
     cudaFree(halo->d_send);
     cudaFree(halo->d_ghost);
-    cudaFree(halo->d_skip);
+    cudaFree(halo->d_row_map);
     if (halo->ev_packed) cudaEventDestroy(halo->ev_packed);
     if (halo->ev_arrived) cudaEventDestroy(halo->ev_arrived);
     if (halo->ev_consumed) cudaEventDestroy(halo->ev_consumed);
@@ -1360,9 +1360,15 @@ int mat_ensure_device(Mat A)
   PB_CUDA(cudaMalloc(&H->d_send_idx, sizeof(int) * std::max<size_t>(H->send_idx.size(), 1)));
   PB_CUDA(cudaMalloc(&H->d_send, sizeof(double) * std::max<size_t>(H->send_idx.size(), 1)));
   PB_CUDA(cudaMalloc(&H->d_ghost, sizeof(double) * std::max<size_t>(H->garray.size(), 1)));
-  PB_CUDA(cudaMalloc(&H->d_skip, std::max<PetscInt>(m, 1)));
+  // rows outside the ghost-free run [skip_lo, skip_hi) -> their row in the compressed off-diagonal block (GhostMerge)
+  std::vector<int> row_map((size_t)std::max<PetscInt>(H->skip_lo + (m - H->skip_hi), 1), -1);
+  for (size_t q = 0; q < S->orow.size(); q++) {
+    const int r = S->orow[q];
+    row_map[r < H->skip_lo ? r : r - H->skip_hi + H->skip_lo] = (int)q;
+  }
+  PB_CUDA(cudaMalloc(&H->d_row_map, sizeof(int) * row_map.size()));
   PB_CUDA(cudaMemcpyAsync(H->d_send_idx, H->send_idx.data(), sizeof(int) * H->send_idx.size(), cudaMemcpyHostToDevice, ctx().stream));
-  PB_CUDA(cudaMemcpyAsync(H->d_skip, S->skip.data(), (size_t)m, cudaMemcpyHostToDevice, ctx().stream));
+  PB_CUDA(cudaMemcpyAsync(H->d_row_map, row_map.data(), sizeof(int) * row_map.size(), cudaMemcpyHostToDevice, ctx().stream));
   PB_CUDA(cudaEventCreateWithFlags(&H->ev_packed, cudaEventDisableTiming));
   PB_CUDA(cudaEventCreateWithFlags(&H->ev_arrived, cudaEventDisableTiming));
   PB_CUDA(cudaEventCreateWithFlags(&H->ev_consumed, cudaEventDisableTiming));

@@ -81,10 +81,15 @@ extern "C" int ctl_emulate(int n, const int *ia, const int *ja, const double *a,
       rb[RB_GP2] += gP * gP; rb[RB_GC2] += gc * gc; rb[RB_GF2] += gf * gf;
     }
   };
+  double gp_from_C = 0.0;   // K_C's sum of g.p (the K_A record carries it)
   auto step_C = [&]() {
     if (S.reason != 0) return;
+    gp_from_C = 0.0;
     if (S.pmode == 1) {
-      for (int r = 0; r < n; r++) p[r] = gfv[r] - S.bcg * p[r];
+      for (int r = 0; r < n; r++) {
+        p[r] = gfv[r] - S.bcg * p[r];
+        gp_from_C += g[r] * p[r];
+      }
     } else if (S.pmode == 2) {
       for (int r = 0; r < n; r++) {
         double gf, gc;
@@ -105,7 +110,6 @@ extern "C" int ctl_emulate(int n, const int *ia, const int *ja, const double *a,
     ra[RA_FEAS] = HUGE_VAL;
     for (int r = 0; r < n; r++) {
       ra[RA_PAP] += p[r] * Ap[r];
-      ra[RA_GP] += g[r] * p[r];
       if (p[r] > 0. && lb && lb[r] > -PINF) {
         const double t = (x[r] - lb[r]) / p[r];
         if (t < ra[RA_FEAS]) ra[RA_FEAS] = t;
@@ -115,6 +119,7 @@ extern "C" int ctl_emulate(int n, const int *ia, const int *ja, const double *a,
         if (t < ra[RA_FEAS]) ra[RA_FEAS] = t;
       }
     }
+    ra[RA_GP] = gp_from_C;
     mpgp_ctrl_A(&S, ra);
     // K_B
     memset(rb, 0, sizeof rb);

@@ -44,7 +44,23 @@ def decode(b, o, n):
         pad = int(p[12:16].view(np.uint32)[0])          # skip code + 1, 0 = rows are not padded
         assert nrows == min(TR, n - t * TR)
         q = 16
-        if kind == 1:
+        if kind == 2:
+            # stencil tile: pattern of nd (delta, value) pairs + one presence byte per row
+            L = int(nd)
+            assert 1 <= L <= 8 and ulen == L and pad == 0
+            val = p[q:q + 8 * L].view(np.float64)
+            q += up(L, 2) * 8
+            dlt = p[q:q + 4 * L].view(np.int32)
+            q += up(L, 4) * 4
+            masks = p[q:q + nrows].astype(np.int64)
+            assert masks.max() < (1 << L)
+            bits = (masks[:, None] >> np.arange(L)[None, :]) & 1          # [nrows, L], storage order = pattern order
+            rr, jj = np.nonzero(bits)
+            assert len(rr) == nnz
+            ja.append(rr + t * TR + dlt[jj])
+            a.append(val[jj])
+            ro = np.concatenate([[0], np.cumsum(bits.sum(axis=1))])
+        elif kind == 1:
             val = p[q:q + 8 * nd].view(np.float64)
             q += up(int(nd), 2) * 8
             dlt = p[q:q + 4 * nd].view(np.int32)
@@ -102,8 +118,10 @@ def cases():
     yield "signed_zero_and_nan_bits", np.array([0, 2, 4] + [4] * 62), np.array([0, 1, 0, 1]), np.array([0.0, -0.0, np.inf, 1.0]), "all"
 
 
+@pytest.mark.parametrize("stencil", ["stencil_form", "coded_form"])
 @pytest.mark.parametrize("case", list(cases()), ids=lambda c: c[0])
-def test_blob_decodes_to_the_same_csr(case):
+def test_blob_decodes_to_the_same_csr(case, stencil, monkeypatch):
+    monkeypatch.setenv("PERMON_B200_PACK_STENCIL", "1" if stencil == "stencil_form" else "0")
     _, ia, ja, a, expect = case
     n = len(ia) - 1
     out = pack(ia, ja, a)
@@ -122,7 +140,28 @@ def test_blob_decodes_to_the_same_csr(case):
     assert np.array_equal(np.asarray(a2).view(np.uint64), np.ascontiguousarray(a, dtype=np.float64).view(np.uint64))   # bit pattern, -0.0 != 0.0
 
 
-def test_ragged_short_rows_are_padded_to_a_common_length():
+def tile_kinds(b, o):
+    return [int(b[int(o[t]) * 16:int(o[t]) * 16 + 2].view(np.uint16)[0]) for t in range(len(o) - 1)]
+
+
+def test_constant_coefficient_stencils_become_stencil_tiles(monkeypatch):
+    """every tile of the obstacle Hessians (C1/C2/C3) is a pattern + one presence byte per row; the two-material operator of C5 and
+    matrices with distinct values are not"""
+    monkeypatch.setenv("PERMON_B200_PACK_STENCIL", "1")
+    for pr in (PR.obstacle2d(70), PR.obstacle3d(17), PR.obstacle3d(24)):
+        b, o, ncoded = pack(pr.ia, pr.ja, pr.a)
+        assert set(tile_kinds(b, o)) == {2} and ncoded == len(o) - 1
+        assert len(b) + 4 * len(o) < 0.04 * (12 * len(pr.a) + 4 * (pr.n + 1))
+    pr = PR.varcoef3d(16)
+    b, o, _ = pack(pr.ia, pr.ja, pr.a)
+    assert 1 in set(tile_kinds(b, o))
+    pr = PR.obstacle2d(64, scaled=True)
+    b, o, ncoded = pack(pr.ia, pr.ja, pr.a)
+    assert set(tile_kinds(b, o)) == {0} and ncoded == 0
+
+
+def test_ragged_short_rows_are_padded_to_a_common_length(monkeypatch):
+    monkeypatch.setenv("PERMON_B200_PACK_STENCIL", "0")
     pr = PR.obstacle3d(24)                       # lines of 24 rows: every tile holds boundary rows with 4..6 entries
     b, o, ncoded = pack(pr.ia, pr.ja, pr.a)
     npad = 0
@@ -133,7 +172,8 @@ def test_ragged_short_rows_are_padded_to_a_common_length():
     assert npad > 0 and ncoded == len(o) - 1
 
 
-def test_stencil_matrix_stream_shrinks():
+def test_stencil_matrix_stream_shrinks(monkeypatch):
+    monkeypatch.setenv("PERMON_B200_PACK_STENCIL", "0")
     pr = PR.obstacle2d(128)
     b, o, _ = pack(pr.ia, pr.ja, pr.a)
     csr = 12 * len(pr.a) + 4 * (pr.n + 1)
