@@ -192,7 +192,8 @@ def algorithmic_bytes(n, nnz, counts, both_bounds=False, matrix_bytes=None):
     12 nnz + 4(n+1) for CSR (the survey's formula), or the bytes of the packed tile format the library actually keeps in HBM."""
     V, Ve = (18, 19) if both_bounds else (16, 16)
     if matrix_bytes is not None:
-        V -= 0.75          # layout actually streamed: K_B writes a byte mask instead of gf (-7/8 pass), K_C reads g + the mask (+1/8)
+        V -= 1.75          # layout actually streamed: K_B writes a byte mask instead of gf (-7/8 pass), K_C reads g + the mask (+1/8),
+                           # K_A does not read g (g.p comes from the kernel that wrote p: -1 pass)
     M = 12 * nnz + 4 * (n + 1) if matrix_bytes is None else matrix_bytes
     b_cg = M + 8 * n * V
     b_exp = 2 * M + 8 * n * Ve
@@ -388,7 +389,7 @@ def measure(env, spec, K, W, want_e2e=True, want_cpu=True, want_parity=True, cpu
     # algorithmic bytes per launch of each fused kernel in the layout it streams, averaged over the
     # window's step mix where the kernel does different work per step kind
     kbytes = {
-        "K_A spmv+dots+feas": M + 8 * n_loc * (4 + nb),                                                   # p g x bounds -> Ap
+        "K_A spmv+dots+feas": M + 8 * n_loc * (3 + nb),                                                   # p x bounds -> Ap
         "K_B update+split": 8 * n_loc * ((n_cg * (6.125 + nb) + n_ex * (5 + nb)) / max(n_cg + n_ex, 1)),  # c/p: 4+nb r, x g + byte mask w; e: 4+nb r, 1 w
         "K_A' spmv+grad+split": M + 8 * n_loc * (4 + nb),                                                 # x b bounds -> g p
         "K_C direction": 8 * n_loc * 3.125,                                                                # g, byte mask, p -> p
@@ -401,12 +402,14 @@ def measure(env, spec, K, W, want_e2e=True, want_cpu=True, want_parity=True, cpu
         pf = prof.get(fam)
         if not pf or not pf["launches"] or not expect[fam]:
             continue
-        real = expect[fam]
+        # launches that did work, classified by their duration (an early exit takes microseconds); the step counters give the same
+        # number except for K_C, whose last launch of a window that ends by max_it has nothing left to do
+        real = pf["working_launches"] if pf["working_launches"] else expect[fam]
         work_ms = pf["working_ms"] if pf["working_launches"] else pf["total_ms"]
         avg = work_ms / real
         gbs = byts / (avg * 1e-3) / 1e9
         per_kernel[fam] = dict(total_ms=round(pf["total_ms"], 3), launches=int(pf["launches"]), working_launches=int(real),
-                               working_launches_by_timing=int(pf["working_launches"]), working_ms=round(work_ms, 3), avg_ms=round(avg, 5),
+                               working_launches_by_step_counters=int(expect[fam]), working_ms=round(work_ms, 3), avg_ms=round(avg, 5),
                                bytes_per_launch=int(byts), achieved_gbs=round(gbs, 1), frac_of_measured_peak=round(gbs / peak, 4))
     fam_ms = {k: round(v["total_ms"], 3) for k, v in prof.items() if v["launches"]}
     total_prof_ms = sum(v["total_ms"] for v in prof.values())

@@ -349,7 +349,15 @@ int orc_max_eigenvalue(const orc_op *op, double tol, int maxits, double *lambda_
     vAv    = orc_dot(n, Av, v);    /* VecMDot(v,2,{Av,v}) :491 */
     vv     = orc_dot(n, v, v);
     lambda = vAv / vv;             /* :492 */
-    /* nullspace branch (:493-502) needs PETSc's rand48; it only changes vAv, which is unused after */
+    if (lambda < 2.2204460492503131e-16) { /* :493-502 A v fell into the null space: Av <- VecSetRandom(PETSCRAND48), which becomes the next v */
+      /* PetscRandomCreate seeds with 0x12345678 (+ 76543 * rank, rank 0 here); rand48 draws drand48() per entry, in order:
+         X <- 0x5DEECE66D X + 0xB (mod 2^48) from (seed << 16) | 0x330E, value X / 2^48 */
+      unsigned long long X = (((unsigned long long)0x12345678u) << 16) | 0x330Eull;
+      for (int k = 0; k < n; k++) {
+        X     = (0x5DEECE66Dull * X + 0xBull) & 0xFFFFFFFFFFFFull;
+        Av[k] = (double)X * (1.0 / 281474976710656.0);
+      }
+    }
     err    = fabs(lambda - lambda0); /* :504 */
     relerr = err / fabs(lambda);
     if (relerr < tol) break;       /* :506 */

@@ -5,6 +5,8 @@
 #include <stdint.h>
 #include <stdlib.h>
 
+#include <vector>
+
 #include "mpgp_ctl.h"
 
 namespace pb {
@@ -17,6 +19,7 @@ struct DevCtx {
   cudaStream_t stream      = nullptr;   // compute stream (library-owned or caller-provided)
   cudaStream_t own_stream  = nullptr;
   cudaStream_t comm_stream = nullptr;   // NCCL halo traffic, overlapped with interior rows
+  cudaStream_t copy_stream = nullptr;   // vector prefetches (H2D) that overlap the power method of the set-up
   int64_t      launches    = 0;         // kernels launched by this library (bench.py: gpu_launches)
 };
 DevCtx &ctx();
@@ -35,6 +38,21 @@ int     cuda_fail(cudaError_t e, const char *what, const char *file, int line);
     int ierr_ = (call);         \
     if (ierr_) return ierr_;    \
   } while (0)
+
+// ---- device / pinned memory -----------------------------------------------------------------------------------------------
+// Device buffers come from the stream-ordered CUDA memory pool of the device with the release threshold lifted: memory freed by a
+// destroyed Vec / Mat / solver stays cached in the pool and the next object of the same size gets it back without a trip to the
+// driver (cudaMalloc / cudaFree of 100 MB-1 GB buffers cost milliseconds each and cudaFree synchronises the device).  Buffers that
+// peers map through CUDA IPC are NOT allocated here.  Small pinned host blocks are cached by size for the same reason.
+int   dmalloc_bytes(void **p, size_t bytes);
+void  dfree(const void *p);
+template <class T>
+int dmalloc(T **p, size_t count)
+{
+  return dmalloc_bytes((void **)p, count * sizeof(T));
+}
+void *pinned_get(size_t bytes);             // nullptr when out of memory
+void  pinned_put(void *p, size_t bytes);
 
 // ---- wall-clock phase timer (PERMON_B200_TIMING=1): synchronises the device on both sides and prints one line to stderr ----
 struct PhaseTimer {
@@ -70,6 +88,23 @@ struct PkHeader {
 };
 static_assert(sizeof(PkHeader) == 16, "tile header is one 16-byte line");
 
+// All-stencil matrices (kind 4): every 256-row tile is a stencil tile (pack.cpp) and the matrix has at most PB_ST_MAXPAT distinct
+// patterns.  The device form is one presence byte per row, one pattern id per tile and the pattern table; the SpMV kernel stages the
+// x WINDOWS a tile gathers from -- x[r0 + d .. r0 + d + 256) for every pattern delta d, deltas closer than PB_ST_SPAN share a window --
+// with bulk copies, so that the gathers of the consumer threads are shared-memory loads.
+#define PB_ST_MAXPAT 32
+#define PB_ST_SPAN 64
+#define PB_ST_WCAP ((256 + PB_ST_SPAN + 2) * 8)   // bytes reserved per window in a shared-memory stage (multiple of 16)
+struct StPattern {
+  int    L, nwin;
+  int    d[8];       // col - row of the pattern entries, ascending (storage order)
+  int    wlo[8];     // window w holds x[r0 + wlo[w] .. r0 + wlo[w] + wlen[w]); wlo and wlen are even (16-byte granules)
+  int    wlen[8];
+  int    erel[8];    // byte offset of x[r0 + d[j]] from the start of the stage's window area
+  double v[8];
+};
+static_assert(sizeof(StPattern) % 8 == 0, "pattern table entries are 8-byte aligned");
+
 // uninitialised host byte buffer (std::vector would zero-fill ~100 MB on one thread before the parallel fill)
 struct RawBuf {
   unsigned char *p = nullptr;
@@ -89,6 +124,14 @@ struct RawBuf {
   size_t         size() const { return n; }
 };
 
+struct StencilHost {   // host side of the all-stencil form, filled by pk_build
+  bool                       valid = false;
+  std::vector<StPattern>     pats;
+  std::vector<unsigned char> pid;
+  RawBuf                     masks;   // ntiles * 256 bytes (zero beyond n)
+  int                        nwin = 0;
+};
+
 struct CsrDev {
   int           n      = 0;        // rows
   int           ncols  = 0;
@@ -100,13 +143,18 @@ struct CsrDev {
   int64_t       nnz_alloc = 0;     // elements of ja / a that may be read (allocation incl. padding)
   int           ia_alloc = 0;      // entries of ia that may be read
   int           stages = 2;        // shared-memory stages of the TMA kernel
-  int           kind   = 0;        // 0: tile-streamed plain loads, 1: vector (W lanes per row), 2: TMA-staged CSR tiles, 3: TMA-staged packed tiles
+  int           kind   = 0;        // 0: tile-streamed plain loads, 1: vector (W lanes per row), 2: TMA-staged CSR tiles, 3: TMA-staged packed tiles, 4: stencil windows
   // packed tiles (kind 3): blob + tile directory (offsets in 16-byte units); the raw CSR arrays are then absent
   const unsigned char *pk     = nullptr;
   const unsigned      *pk_off = nullptr;
   int                  pk_max = 0;      // largest tile blob in bytes
   int64_t              pk_bytes = 0;    // blob + directory bytes (what one SpMV streams for the matrix)
   int64_t              pk_coded = 0;    // tiles that are dictionary-coded
+  // all-stencil form (kind 4)
+  const unsigned char *st_masks = nullptr;   // [n] presence byte per row
+  const unsigned char *st_pid = nullptr;     // [ntiles] pattern of each tile
+  const StPattern     *st_pats = nullptr;
+  int                  st_npat = 0, st_nwin = 0;   // patterns; largest number of windows of a pattern
   int           W      = 32;
   int           tile_cap = 0;      // max nnz of a 256-row tile (stream kind)
   int           grid   = 0;        // persistent grid size (fixed => reproducible reductions)
@@ -136,8 +184,8 @@ struct RedBuf {
   double   *partials = nullptr;   // [maxblocks][PB_NRED]
   unsigned *counter  = nullptr;
   double   *out      = nullptr;   // where the last block stores the record (PB_NRED doubles)
-  const double *add1 = nullptr;   // optional scalar produced by an earlier kernel, added into slot add1_slot of the record
-  int           add1_slot = 0;
+  const double *add_part = nullptr;   // optional per-CTA partial sums of an earlier kernel (stride PB_NRED), added into slot add_slot
+  int           add_n = 0, add_slot = 0;
   const P2PWin      *win = nullptr;   // when set: also publish the record to every peer (kind, seq)
   int                kind = 0;
   unsigned long long seq = 0;
@@ -197,6 +245,7 @@ struct TileOrder {
 int k_set(int n, double *x, double a);
 int k_copy(int n, const double *x, double *y);
 int k_scale(int n, double *x, double a);
+int k_scale_to(int n, double *y, double a, const double *x);           // y = a x
 int k_axpy(int n, double *y, double a, const double *x);
 int k_aypx(int n, double *y, double a, const double *x);
 int k_waxpy(int n, double *w, double a, const double *x, const double *y);
@@ -218,6 +267,7 @@ int k_box_mult(int n, const double *r, int has_lb, int has_ub, double *llb, doub
 int k_kkt_box(int n, const double *x, const double *bound, const double *lam, int upper, RedBuf rb);
 
 // SpMV
+int k_power_step(const CsrDev &A, const double *w, double s, double *y, RedBuf rb);   // y = A (s w); rb.out[0] = (s w).y, rb.out[1] = (s w).(s w); packed matrices
 int k_spmv(const CsrDev &A, const double *x, double *y, int accumulate);   // y (+)= A x ; honours A.rows
 
 // ---- fused MPGP kernels -------------------------------------------------------------------------------
@@ -258,6 +308,7 @@ int k_pack(int n, const int *idx, const double *x, double *buf);
 double csr_stream_bytes(const CsrDev &A);   // bytes one SpMV must read for the matrix itself (CSR: 12 nnz + 4(n+1); packed: blob + directory)
 int  spmv_config(CsrDev &A, const int *h_ia);   // picks kind / W / grid from the host row pointer
 int  elementwise_grid();
+int  fused_C_grid(int n);   // CTAs of K_C for n local rows (K_A adds that many partial sums of g.p)
 int  max_red_blocks();
 
 }  // namespace pb

@@ -21,6 +21,7 @@
 #include <climits>
 #include <cuda_runtime.h>
 #include <stdarg.h>
+#include <stddef.h>
 #include <stdio.h>
 #include <string.h>
 #include <time.h>
@@ -84,9 +85,65 @@ int dev_init()
   }
   PB_CUDA(cudaStreamCreateWithFlags(&c.own_stream, cudaStreamNonBlocking));
   PB_CUDA(cudaStreamCreateWithFlags(&c.comm_stream, cudaStreamNonBlocking));
+  PB_CUDA(cudaStreamCreateWithFlags(&c.copy_stream, cudaStreamNonBlocking));
   if (!c.stream) c.stream = c.own_stream;
   c.ready = true;
   return 0;
+}
+
+// ---- memory -----------------------------------------------------------------------------------------------------------
+static bool g_pool_ready = false;
+static bool pool_enabled()
+{
+  static int on = -1;
+  if (on < 0) {
+    const char *e = getenv("PERMON_B200_POOL");
+    on = (e && !strcmp(e, "0")) ? 0 : 1;
+  }
+  return on != 0;
+}
+int dmalloc_bytes(void **p, size_t bytes)
+{
+  PB_CHK(dev_init());
+  if (bytes == 0) bytes = 16;
+  if (pool_enabled()) {
+    if (!g_pool_ready) {
+      cudaMemPool_t pool;
+      PB_CUDA(cudaDeviceGetDefaultMemPool(&pool, g_ctx.device));
+      uint64_t keep = UINT64_MAX;
+      PB_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+      g_pool_ready = true;
+    }
+    PB_CUDA(cudaMallocAsync(p, bytes, g_ctx.stream));
+    return 0;
+  }
+  PB_CUDA(cudaMalloc(p, bytes));
+  return 0;
+}
+void dfree(const void *p)
+{
+  if (!p) return;
+  if (pool_enabled()) cudaFreeAsync((void *)p, g_ctx.stream);
+  else cudaFree((void *)p);
+}
+static std::vector<std::pair<size_t, void *>> g_pinned_cache;
+void *pinned_get(size_t bytes)
+{
+  for (size_t i = 0; i < g_pinned_cache.size(); i++)
+    if (g_pinned_cache[i].first == bytes) {
+      void *p = g_pinned_cache[i].second;
+      g_pinned_cache.erase(g_pinned_cache.begin() + i);
+      return p;
+    }
+  void *p = nullptr;
+  if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) return nullptr;
+  return p;
+}
+void pinned_put(void *p, size_t bytes)
+{
+  if (!p) return;
+  if (bytes <= (1u << 20) && g_pinned_cache.size() < 64) g_pinned_cache.push_back({bytes, p});
+  else cudaFreeHost(p);
 }
 
 static double phase_now()
@@ -319,14 +376,15 @@ __device__ void grid_reduce8(double (&v)[PB_NRED], RedBuf rb, const double *prev
     for (int k = 0; k < PB_NRED; k++) {
       double t = red_identity<MINMASK>(k);
       for (int b = threadIdx.x; b < (int)gridDim.x; b += blockDim.x) t = red_op<MINMASK>(k, t, __ldcg(&rb.partials[(size_t)b * PB_NRED + k]));
+      if (rb.add_part && k == rb.add_slot)   // per-CTA partial sums left by an earlier kernel (K_C's g.p)
+        for (int b = threadIdx.x; b < rb.add_n; b += blockDim.x) t += __ldcg(&rb.add_part[(size_t)b * PB_NRED]);
       w[k] = t;
     }
     block_reduce8<MINMASK>(w, sm);
     if (threadIdx.x == 0) {
 #pragma unroll
       for (int k = 0; k < PB_NRED; k++) {
-        double f = prev ? red_op<MINMASK>(k, prev[k], w[k]) : w[k];
-        if (rb.add1 && k == rb.add1_slot) f += __ldcg(rb.add1);
+        const double f = prev ? red_op<MINMASK>(k, prev[k], w[k]) : w[k];
         rb.out[k] = f;
         sm[k][0]  = f;
       }
@@ -347,11 +405,10 @@ __device__ void grid_reduce8(double (&v)[PB_NRED], RedBuf rb, const double *prev
   }
 }
 
-// one-value variant (sum) for kernels with a tight register budget: the result lands in rb.out[slot]
-__device__ void grid_reduce1(double v, RedBuf rb, int slot)
+// one value per CTA, no ticket: partials[blockIdx.x * PB_NRED] = sum over the CTA; a later kernel's final reduction adds them
+__device__ void block_partial1(double v, double *partials)
 {
   __shared__ double sm1[32];
-  __shared__ int    s_last1;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -361,31 +418,7 @@ __device__ void grid_reduce1(double v, RedBuf rb, int slot)
     double t = (lane < nw) ? sm1[lane] : 0.0;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
-    if (lane == 0) {
-      rb.partials[(size_t)blockIdx.x * PB_NRED] = t;
-      __threadfence();
-      s_last1 = (atomicAdd(rb.counter, 1u) == gridDim.x - 1);
-    }
-  }
-  __syncthreads();
-  if (s_last1) {
-    __threadfence();
-    double t = 0.0;
-    for (int b = threadIdx.x; b < (int)gridDim.x; b += blockDim.x) t += __ldcg(&rb.partials[(size_t)b * PB_NRED]);
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
-    __syncthreads();
-    if (lane == 0) sm1[warp] = t;
-    __syncthreads();
-    if (warp == 0) {
-      double u = (lane < nw) ? sm1[lane] : 0.0;
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) u += __shfl_xor_sync(0xffffffffu, u, o);
-      if (lane == 0) {
-        rb.out[slot] = u;
-        *rb.counter  = 0u;
-      }
-    }
+    if (lane == 0) partials[(size_t)blockIdx.x * PB_NRED] = t;
   }
 }
 
@@ -783,30 +816,22 @@ __device__ __forceinline__ uint4 lds_v4(uint32_t a)
   return v;
 }
 
-// one coded row of compile-time length L (uniform tiles of stencil matrices): no predicates, all loads up front
-template <int L>
-__device__ __forceinline__ double pk_row_fixed(uint32_t code_a, uint32_t dv_a, uint32_t dd_a, const double *__restrict__ x, int r)
-{
-  uint32_t c[L];
-  int      d[L];
-  double   xv[L], vv[L];
-#pragma unroll
-  for (int j = 0; j < L; j++) c[j] = lds_u8(code_a + j);
-#pragma unroll
-  for (int j = 0; j < L; j++) d[j] = lds_s32(dd_a + 4u * c[j]);
-#pragma unroll
-  for (int j = 0; j < L; j++) xv[j] = __ldg(x + (r + d[j]));
-#pragma unroll
-  for (int j = 0; j < L; j++) vv[j] = lds_f64(dv_a + 8u * c[j]);
-  double sum = 0.0;
-#pragma unroll
-  for (int j = 0; j < L; j++) sum += vv[j] * xv[j];
-  return sum;
-}
+// how the SpMV input is read: plain, or scaled on the fly (power method: the normalised iterate v = s * w is never stored)
+struct GatherPlain {
+  const double *x;
+  __device__ __forceinline__ double ld(const double *p) const { return __ldg(p); }
+  __device__ __forceinline__ double sc(double v) const { return v; }
+};
+struct GatherScaled {
+  const double *x;
+  double        s;
+  __device__ __forceinline__ double ld(const double *p) const { return __ldg(p) * s; }
+  __device__ __forceinline__ double sc(double v) const { return v * s; }
+};
 
 // two coded rows of compile-time length at once (each consumer thread owns rows t and t + PK_CT of a tile): 2 L gathers in flight
-template <int L, bool PAD>
-__device__ __forceinline__ void pk_row2_fixed(uint32_t code_a0, uint32_t code_a1, uint32_t dv_a, uint32_t dd_a, const double *__restrict__ x, int r0, int r1,
+template <int L, bool PAD, class G>
+__device__ __forceinline__ void pk_row2_fixed(uint32_t code_a0, uint32_t code_a1, uint32_t dv_a, uint32_t dd_a, const G &gx, int r0, int r1,
                                               uint32_t pad, double &s0, double &s1)
 {
   uint32_t c0[L], c1[L];
@@ -821,9 +846,9 @@ __device__ __forceinline__ void pk_row2_fixed(uint32_t code_a0, uint32_t code_a1
 #pragma unroll
   for (int j = 0; j < L; j++) d1[j] = lds_s32(dd_a + 4u * c1[j]);
 #pragma unroll
-  for (int j = 0; j < L; j++) x0[j] = __ldg(x + (r0 + d0[j]));   // a skip code gathers x[r] (delta 0) and drops it
+  for (int j = 0; j < L; j++) x0[j] = gx.ld(gx.x + (r0 + d0[j]));   // a skip code gathers x[r] (delta 0) and drops it
 #pragma unroll
-  for (int j = 0; j < L; j++) x1[j] = __ldg(x + (r1 + d1[j]));
+  for (int j = 0; j < L; j++) x1[j] = gx.ld(gx.x + (r1 + d1[j]));
   // scheduling fence (the consumer warps are converged here): every gather above is issued before the first multiply-add below
   __syncwarp();
   s0 = 0.0;
@@ -840,25 +865,26 @@ __device__ __forceinline__ void pk_row2_fixed(uint32_t code_a0, uint32_t code_a1
   }
 }
 
-template <bool PAD>
-__device__ __forceinline__ bool pk_row2_dispatch(uint32_t ulen, uint32_t ca0, uint32_t ca1, uint32_t dv_a, uint32_t dd_a, const double *__restrict__ x, int r0,
+template <bool PAD, class G>
+__device__ __forceinline__ bool pk_row2_dispatch(uint32_t ulen, uint32_t ca0, uint32_t ca1, uint32_t dv_a, uint32_t dd_a, const G &gx, int r0,
                                                  int r1, uint32_t pad, double &s0, double &s1)
 {
   switch (ulen) {
-  case 1: pk_row2_fixed<1, PAD>(ca0, ca1, dv_a, dd_a, x, r0, r1, pad, s0, s1); return true;
-  case 2: pk_row2_fixed<2, PAD>(ca0, ca1, dv_a, dd_a, x, r0, r1, pad, s0, s1); return true;
-  case 3: pk_row2_fixed<3, PAD>(ca0, ca1, dv_a, dd_a, x, r0, r1, pad, s0, s1); return true;
-  case 4: pk_row2_fixed<4, PAD>(ca0, ca1, dv_a, dd_a, x, r0, r1, pad, s0, s1); return true;
-  case 5: pk_row2_fixed<5, PAD>(ca0, ca1, dv_a, dd_a, x, r0, r1, pad, s0, s1); return true;
-  case 6: pk_row2_fixed<6, PAD>(ca0, ca1, dv_a, dd_a, x, r0, r1, pad, s0, s1); return true;
-  case 7: pk_row2_fixed<7, PAD>(ca0, ca1, dv_a, dd_a, x, r0, r1, pad, s0, s1); return true;
-  case 8: pk_row2_fixed<8, PAD>(ca0, ca1, dv_a, dd_a, x, r0, r1, pad, s0, s1); return true;
+  case 1: pk_row2_fixed<1, PAD, G>(ca0, ca1, dv_a, dd_a, gx, r0, r1, pad, s0, s1); return true;
+  case 2: pk_row2_fixed<2, PAD, G>(ca0, ca1, dv_a, dd_a, gx, r0, r1, pad, s0, s1); return true;
+  case 3: pk_row2_fixed<3, PAD, G>(ca0, ca1, dv_a, dd_a, gx, r0, r1, pad, s0, s1); return true;
+  case 4: pk_row2_fixed<4, PAD, G>(ca0, ca1, dv_a, dd_a, gx, r0, r1, pad, s0, s1); return true;
+  case 5: pk_row2_fixed<5, PAD, G>(ca0, ca1, dv_a, dd_a, gx, r0, r1, pad, s0, s1); return true;
+  case 6: pk_row2_fixed<6, PAD, G>(ca0, ca1, dv_a, dd_a, gx, r0, r1, pad, s0, s1); return true;
+  case 7: pk_row2_fixed<7, PAD, G>(ca0, ca1, dv_a, dd_a, gx, r0, r1, pad, s0, s1); return true;
+  case 8: pk_row2_fixed<8, PAD, G>(ca0, ca1, dv_a, dd_a, gx, r0, r1, pad, s0, s1); return true;
   default: return false;
   }
 }
 
 // coded row of run-time length: chunks of PK_UNROLL with the same load-first order
-__device__ __forceinline__ double pk_row_var(uint32_t code_a, int len, uint32_t dv_a, uint32_t dd_a, const double *__restrict__ x, int r, uint32_t pad)
+template <class G>
+__device__ __forceinline__ double pk_row_var(uint32_t code_a, int len, uint32_t dv_a, uint32_t dd_a, const G &gx, int r, uint32_t pad)
 {
   double sum = 0.0;
   for (int k = 0; k < len; k += PK_UNROLL) {
@@ -870,7 +896,7 @@ __device__ __forceinline__ double pk_row_var(uint32_t code_a, int len, uint32_t 
 #pragma unroll
     for (int j = 0; j < PK_UNROLL; j++) d[j] = lds_s32(dd_a + 4u * c[j]);
 #pragma unroll
-    for (int j = 0; j < PK_UNROLL; j++) xv[j] = (k + j < len) ? __ldg(x + (r + d[j])) : 0.0;
+    for (int j = 0; j < PK_UNROLL; j++) xv[j] = (k + j < len) ? gx.ld(gx.x + (r + d[j])) : 0.0;
 #pragma unroll
     for (int j = 0; j < PK_UNROLL; j++) vv[j] = lds_f64(dv_a + 8u * c[j]);
 #pragma unroll
@@ -880,7 +906,8 @@ __device__ __forceinline__ double pk_row_var(uint32_t code_a, int len, uint32_t 
   return sum;
 }
 
-__device__ __forceinline__ double pk_row_raw(uint32_t a_a, uint32_t ja_a, int len, const double *__restrict__ x)
+template <class G>
+__device__ __forceinline__ double pk_row_raw(uint32_t a_a, uint32_t ja_a, int len, const G &gx)
 {
   double sum = 0.0;
   for (int k = 0; k < len; k += PK_UNROLL) {
@@ -889,7 +916,7 @@ __device__ __forceinline__ double pk_row_raw(uint32_t a_a, uint32_t ja_a, int le
 #pragma unroll
     for (int j = 0; j < PK_UNROLL; j++) col[j] = (k + j < len) ? lds_s32(ja_a + 4u * (k + j)) : 0;
 #pragma unroll
-    for (int j = 0; j < PK_UNROLL; j++) xv[j] = (k + j < len) ? __ldg(x + col[j]) : 0.0;
+    for (int j = 0; j < PK_UNROLL; j++) xv[j] = (k + j < len) ? gx.ld(gx.x + col[j]) : 0.0;
 #pragma unroll
     for (int j = 0; j < PK_UNROLL; j++) vv[j] = (k + j < len) ? lds_f64(a_a + 8u * (k + j)) : 0.0;
 #pragma unroll
@@ -903,29 +930,29 @@ __device__ __forceinline__ double pk_row_raw(uint32_t a_a, uint32_t ja_a, int le
 // entries missing (rows next to a grid boundary); one presence byte per row instead of one code byte per non-zero.  Deltas and values
 // are warp-uniform (broadcast shared-memory loads), a row costs its gathers and multiply-adds only.  A missing entry is skipped
 // (predicated load and multiply-add), so the sum runs over the row's stored entries in storage order: bit-identical to the CSR kernels.
-template <int L>
-__device__ __forceinline__ void st_row2_fixed(uint32_t m0, uint32_t m1, uint32_t dv_a, uint32_t dd_a, const double *__restrict__ x, int r0, int r1, double &s0, double &s1)
+template <int L, class G>
+__device__ __forceinline__ void st_row2_fixed(uint32_t m0, uint32_t m1, uint32_t dv_a, uint32_t dd_a, const G &gx, int r0, int r1, double &s0, double &s1)
 {
   constexpr uint32_t FULL = (1u << L) - 1u;
   int                d[L];
   double             x0[L], x1[L];
 #pragma unroll
   for (int j = 0; j < L; j++) d[j] = lds_s32(dd_a + 4u * j);
-  const double *xr0 = x + r0, *xr1 = x + r1;
+  const double *xr0 = gx.x + r0, *xr1 = gx.x + r1;
   const bool    f0 = __all_sync(0xffffffffu, m0 == FULL), f1 = __all_sync(0xffffffffu, m1 == FULL);
   if (f0) {
 #pragma unroll
-    for (int j = 0; j < L; j++) x0[j] = __ldg(xr0 + d[j]);
+    for (int j = 0; j < L; j++) x0[j] = gx.ld(xr0 + d[j]);
   } else {
 #pragma unroll
-    for (int j = 0; j < L; j++) x0[j] = ((m0 >> j) & 1u) ? __ldg(xr0 + d[j]) : 0.0;
+    for (int j = 0; j < L; j++) x0[j] = ((m0 >> j) & 1u) ? gx.ld(xr0 + d[j]) : 0.0;
   }
   if (f1) {
 #pragma unroll
-    for (int j = 0; j < L; j++) x1[j] = __ldg(xr1 + d[j]);
+    for (int j = 0; j < L; j++) x1[j] = gx.ld(xr1 + d[j]);
   } else {
 #pragma unroll
-    for (int j = 0; j < L; j++) x1[j] = ((m1 >> j) & 1u) ? __ldg(xr1 + d[j]) : 0.0;
+    for (int j = 0; j < L; j++) x1[j] = ((m1 >> j) & 1u) ? gx.ld(xr1 + d[j]) : 0.0;
   }
   __syncwarp();   // scheduling fence: every gather above is issued before the first multiply-add below
   double v[L];
@@ -950,18 +977,19 @@ __device__ __forceinline__ void st_row2_fixed(uint32_t m0, uint32_t m1, uint32_t
       if ((m1 >> j) & 1u) s1 += v[j] * x1[j];
   }
 }
-__device__ __forceinline__ void st_row2_dispatch(uint32_t L, uint32_t m0, uint32_t m1, uint32_t dv_a, uint32_t dd_a, const double *__restrict__ x, int r0, int r1, double &s0,
+template <class G>
+__device__ __forceinline__ void st_row2_dispatch(uint32_t L, uint32_t m0, uint32_t m1, uint32_t dv_a, uint32_t dd_a, const G &gx, int r0, int r1, double &s0,
                                                  double &s1)
 {
   switch (L) {
-  case 1: st_row2_fixed<1>(m0, m1, dv_a, dd_a, x, r0, r1, s0, s1); break;
-  case 2: st_row2_fixed<2>(m0, m1, dv_a, dd_a, x, r0, r1, s0, s1); break;
-  case 3: st_row2_fixed<3>(m0, m1, dv_a, dd_a, x, r0, r1, s0, s1); break;
-  case 4: st_row2_fixed<4>(m0, m1, dv_a, dd_a, x, r0, r1, s0, s1); break;
-  case 5: st_row2_fixed<5>(m0, m1, dv_a, dd_a, x, r0, r1, s0, s1); break;
-  case 6: st_row2_fixed<6>(m0, m1, dv_a, dd_a, x, r0, r1, s0, s1); break;
-  case 7: st_row2_fixed<7>(m0, m1, dv_a, dd_a, x, r0, r1, s0, s1); break;
-  default: st_row2_fixed<8>(m0, m1, dv_a, dd_a, x, r0, r1, s0, s1); break;
+  case 1: st_row2_fixed<1>(m0, m1, dv_a, dd_a, gx, r0, r1, s0, s1); break;
+  case 2: st_row2_fixed<2>(m0, m1, dv_a, dd_a, gx, r0, r1, s0, s1); break;
+  case 3: st_row2_fixed<3>(m0, m1, dv_a, dd_a, gx, r0, r1, s0, s1); break;
+  case 4: st_row2_fixed<4>(m0, m1, dv_a, dd_a, gx, r0, r1, s0, s1); break;
+  case 5: st_row2_fixed<5>(m0, m1, dv_a, dd_a, gx, r0, r1, s0, s1); break;
+  case 6: st_row2_fixed<6>(m0, m1, dv_a, dd_a, gx, r0, r1, s0, s1); break;
+  case 7: st_row2_fixed<7>(m0, m1, dv_a, dd_a, gx, r0, r1, s0, s1); break;
+  default: st_row2_fixed<8>(m0, m1, dv_a, dd_a, gx, r0, r1, s0, s1); break;
   }
 }
 
@@ -986,6 +1014,7 @@ __global__ void __launch_bounds__(PK_CT + 32, MINB) k_spmv_pk(CsrDev A, const do
   const int ntiles = (A.n + TR - 1) / TR;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const bool rev = epi.reverse();
+  const typename Epi::Gather gx = epi.gather(x);
   typename Epi::Acc acc;
   epi.init(acc);
   if (threadIdx.x == 0) {
@@ -1068,7 +1097,7 @@ __global__ void __launch_bounds__(PK_CT + 32, MINB) k_spmv_pk(CsrDev A, const do
         const uint32_t m0 = (threadIdx.x < nrows) ? lds_u8(q_a + threadIdx.x) : 0u;
         const uint32_t m1 = (threadIdx.x + PK_CT < nrows) ? lds_u8(q_a + threadIdx.x + PK_CT) : 0u;
         double         s0, s1;
-        st_row2_dispatch(nd, m0, m1, dv_a, dd_a, x, r0, r1, s0, s1);
+        st_row2_dispatch(nd, m0, m1, dv_a, dd_a, gx, r0, r1, s0, s1);
         if (r0 < A.n) epi.row_s(r0, vs_a, s0, acc);
         if (r1 < A.n) epi.row_s(r1, vs_a + PK_CT * 8u, s1, acc);
         done = true;
@@ -1076,8 +1105,8 @@ __global__ void __launch_bounds__(PK_CT + 32, MINB) k_spmv_pk(CsrDev A, const do
         // full tile of equal-length coded rows: both rows together, loads up front
         const uint32_t ca0 = q_a + threadIdx.x * ulen, ca1 = ca0 + PK_CT * ulen;
         double         s0 = 0.0, s1 = 0.0;
-        done = pad != 0xFFFFFFFFu ? pk_row2_dispatch<true>(ulen, ca0, ca1, dv_a, dd_a, x, r0, r1, pad, s0, s1)
-                                  : pk_row2_dispatch<false>(ulen, ca0, ca1, dv_a, dd_a, x, r0, r1, pad, s0, s1);
+        done = pad != 0xFFFFFFFFu ? pk_row2_dispatch<true>(ulen, ca0, ca1, dv_a, dd_a, gx, r0, r1, pad, s0, s1)
+                                  : pk_row2_dispatch<false>(ulen, ca0, ca1, dv_a, dd_a, gx, r0, r1, pad, s0, s1);
         if (done) {
           epi.row_s(r0, vs_a, s0, acc);
           epi.row_s(r1, vs_a + PK_CT * 8u, s1, acc);
@@ -1092,21 +1121,188 @@ __global__ void __launch_bounds__(PK_CT + 32, MINB) k_spmv_pk(CsrDev A, const do
           double sum;
           if (kind == 1) {
             if (ulen != 0xFFFFu) {
-              sum = pk_row_var(q_a + t * ulen, (int)ulen, dv_a, dd_a, x, r, pad);
+              sum = pk_row_var(q_a + t * ulen, (int)ulen, dv_a, dd_a, gx, r, pad);
             } else {
               const uint32_t ks = lds_u16(q_a + 2u * t), ke = lds_u16(q_a + 2u * t + 2u);
-              sum = pk_row_var(q_a + ((nrows + 1u + 7u) & ~7u) * 2u + ks, (int)(ke - ks), dv_a, dd_a, x, r, pad);
+              sum = pk_row_var(q_a + ((nrows + 1u + 7u) & ~7u) * 2u + ks, (int)(ke - ks), dv_a, dd_a, gx, r, pad);
             }
           } else {
             const uint32_t a_a = st_a + (uint32_t)sizeof(PkHeader);
             const uint32_t ja_a = a_a + ((nnz + 1u) & ~1u) * 8u;
             const uint32_t ro_a = ja_a + ((nnz + 3u) & ~3u) * 4u;
             const uint32_t ks = lds_u16(ro_a + 2u * t), ke = lds_u16(ro_a + 2u * t + 2u);
-            sum = pk_row_raw(a_a + 8u * ks, ja_a + 4u * ks, (int)(ke - ks), x);
+            sum = pk_row_raw(a_a + 8u * ks, ja_a + 4u * ks, (int)(ke - ks), gx);
           }
           epi.row_s(r, st_a + (uint32_t)blob_cap + 8u * t, sum, acc);
         }
       }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty_bar[s]);
+      if (++s == nstages) {
+        s = 0;
+        ph ^= 1u;
+      }
+    }
+  }
+  epi.finalize(acc);
+}
+
+
+// ---- all-stencil matrices (kind 4): x windows staged by bulk copies, gathers are shared-memory loads ----------------------------
+// Stage layout: [16 B descriptor: pattern id, windowed flag][256 B presence bytes][st_nwin windows of PB_ST_WCAP bytes][nv row slices of
+// the epilogue vectors].  The pattern table sits in front of the stages.  A tile whose windows would reach outside x (the first / last
+// rows of the local block) or that is partial takes the gather path (LDG) with the same pattern; everything else never issues a
+// long-latency load from a consumer warp: the copy engine streams, the consumer warps only do shared-memory loads and DFMAs.
+static constexpr uint32_t ST_MASK_OFF = 16, ST_WIN_OFF = 16 + TR;
+template <int L, class G>
+__device__ __forceinline__ void st_win2_fixed(uint32_t m0, uint32_t m1, uint32_t P_a, uint32_t win_a, const G &gx, double &s0, double &s1)
+{
+  constexpr uint32_t FULL = (1u << L) - 1u;
+  uint32_t           e[L];
+  double             v[L];
+#pragma unroll
+  for (int j = 0; j < L; j++) e[j] = win_a + (uint32_t)lds_s32(P_a + (uint32_t)offsetof(StPattern, erel) + 4u * j);
+#pragma unroll
+  for (int j = 0; j < L; j++) v[j] = lds_f64(P_a + (uint32_t)offsetof(StPattern, v) + 8u * j);
+  s0 = 0.0;
+  s1 = 0.0;
+  if (__all_sync(0xffffffffu, m0 == FULL)) {
+#pragma unroll
+    for (int j = 0; j < L; j++) s0 += v[j] * gx.sc(lds_f64(e[j]));
+  } else {
+#pragma unroll
+    for (int j = 0; j < L; j++)
+      if ((m0 >> j) & 1u) s0 += v[j] * gx.sc(lds_f64(e[j]));
+  }
+  if (__all_sync(0xffffffffu, m1 == FULL)) {
+#pragma unroll
+    for (int j = 0; j < L; j++) s1 += v[j] * gx.sc(lds_f64(e[j] + PK_CT * 8u));
+  } else {
+#pragma unroll
+    for (int j = 0; j < L; j++)
+      if ((m1 >> j) & 1u) s1 += v[j] * gx.sc(lds_f64(e[j] + PK_CT * 8u));
+  }
+}
+template <class G>
+__device__ __forceinline__ void st_win2_dispatch(uint32_t L, uint32_t m0, uint32_t m1, uint32_t P_a, uint32_t win_a, const G &gx, double &s0, double &s1)
+{
+  switch (L) {
+  case 1: st_win2_fixed<1>(m0, m1, P_a, win_a, gx, s0, s1); break;
+  case 2: st_win2_fixed<2>(m0, m1, P_a, win_a, gx, s0, s1); break;
+  case 3: st_win2_fixed<3>(m0, m1, P_a, win_a, gx, s0, s1); break;
+  case 4: st_win2_fixed<4>(m0, m1, P_a, win_a, gx, s0, s1); break;
+  case 5: st_win2_fixed<5>(m0, m1, P_a, win_a, gx, s0, s1); break;
+  case 6: st_win2_fixed<6>(m0, m1, P_a, win_a, gx, s0, s1); break;
+  case 7: st_win2_fixed<7>(m0, m1, P_a, win_a, gx, s0, s1); break;
+  default: st_win2_fixed<8>(m0, m1, P_a, win_a, gx, s0, s1); break;
+  }
+}
+
+template <class Epi>
+__global__ void __launch_bounds__(PK_CT + 32, 4) k_spmv_st(CsrDev A, const double *__restrict__ x, Epi epi, int nstages, int stage_bytes, int pats_bytes, int win_ok, int vec_tma,
+                                                           TileOrder ord)
+{
+  pdl_enter();
+  if (!epi.active()) return;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  __shared__ uint64_t full_bar[TMA_MAX_STAGES], empty_bar[TMA_MAX_STAGES];
+  const int  nv = epi.nvec();
+  const int  vec_off = (int)ST_WIN_OFF + A.st_nwin * PB_ST_WCAP;
+  const int  ntiles = (A.n + TR - 1) / TR;
+  const int  warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool rev = epi.reverse();
+  const typename Epi::Gather gx = epi.gather(x);
+  typename Epi::Acc acc;
+  epi.init(acc);
+  {   // pattern table -> shared memory (a few hundred bytes per pattern)
+    const int      nw = A.st_npat * (int)(sizeof(StPattern) / 4);
+    const int     *src = reinterpret_cast<const int *>(A.st_pats);
+    int           *dst = reinterpret_cast<int *>(smem_raw);
+    for (int k = threadIdx.x; k < nw; k += blockDim.x) dst[k] = __ldg(src + k);
+  }
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < nstages; s++) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], PK_CT / 32);
+    }
+    mbar_fence_init();
+  }
+  __syncthreads();
+  unsigned char *stages = smem_raw + pats_bytes;
+
+  if (warp == PK_CT / 32) {
+    // ------------------------------ producer warp ------------------------------
+    int pidn = 0;
+    if (blockIdx.x < ntiles) pidn = __ldg(A.st_pid + tile_at(blockIdx.x, ord.ta, ord.tb, rev));
+    int      s = 0, filled = 0;
+    uint32_t ph = 0;
+    for (int i = blockIdx.x; i < ntiles; i += gridDim.x) {
+      const int tile = tile_at(i, ord.ta, ord.tb, rev);
+      const int pid = pidn;
+      const int ni = i + gridDim.x;
+      if (ni < ntiles) pidn = __ldg(A.st_pid + tile_at(ni, ord.ta, ord.tb, rev));   // in flight while this tile is issued
+      if (filled >= nstages) mbar_wait(&empty_bar[s], ph ^ 1u);
+      else filled++;
+      unsigned char   *st = stages + (size_t)s * stage_bytes;
+      const StPattern *P = reinterpret_cast<const StPattern *>(smem_raw) + pid;
+      const int        r0 = tile * TR, r1 = min(r0 + TR, A.n);
+      const bool       fullt = (r1 - r0 == TR) && vec_tma;
+      bool             windowed = fullt && win_ok;
+      uint32_t         wbytes = 0;
+      const int        nwin = P->nwin;
+      for (int w = 0; w < nwin; w++) {
+        const int lo = r0 + P->wlo[w];
+        if (lo < 0 || lo + P->wlen[w] > A.ncols) windowed = false;
+        wbytes += (uint32_t)P->wlen[w] * 8u;
+      }
+      if (lane == 0) {
+        reinterpret_cast<int *>(st)[0] = pid;
+        reinterpret_cast<int *>(st)[1] = windowed ? 1 : 0;
+      }
+      if (fullt) {
+        if (lane == 0) {
+          mbar_arrive_expect_tx(&full_bar[s], (uint32_t)TR + (uint32_t)nv * TR * 8u + (windowed ? wbytes : 0u));
+          bulk_g2s(st + ST_MASK_OFF, A.st_masks + r0, (uint32_t)TR, &full_bar[s]);
+          if (windowed)
+            for (int w = 0; w < nwin; w++) bulk_g2s(st + ST_WIN_OFF + (size_t)w * PB_ST_WCAP, x + (r0 + P->wlo[w]), (uint32_t)P->wlen[w] * 8u, &full_bar[s]);
+          for (int v = 0; v < nv; v++) bulk_g2s(st + vec_off + (size_t)v * TR * 8, epi.vsrc(v) + r0, (uint32_t)TR * 8u, &full_bar[s]);
+        }
+      } else {
+        // last (partial) tile, or caller vectors that are not 16-byte aligned: the warp stages masks and vector slices itself
+        for (int t = lane; t < TR; t += 32) st[ST_MASK_OFF + t] = (t < r1 - r0) ? __ldg(A.st_masks + r0 + t) : (unsigned char)0;
+        for (int v = 0; v < nv; v++) {
+          double       *vs = (double *)(st + vec_off) + (size_t)v * TR;
+          const double *src = epi.vsrc(v) + r0;
+          for (int t = lane; t < r1 - r0; t += 32) vs[t] = src[t];
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&full_bar[s]);
+      }
+      if (++s == nstages) {
+        s = 0;
+        ph ^= 1u;
+      }
+    }
+  } else {
+    // ------------------------------ consumer warps: two rows (t, t + PK_CT) per thread ------------------------------
+    const uint32_t smem_a = smem_u32(smem_raw), stages_a = smem_a + (uint32_t)pats_bytes;
+    int            s = 0;
+    uint32_t       ph = 0;
+    for (int i = blockIdx.x; i < ntiles; i += gridDim.x) {
+      const int tile = tile_at(i, ord.ta, ord.tb, rev);
+      mbar_wait(&full_bar[s], ph);
+      const uint32_t st_a = stages_a + (uint32_t)s * (uint32_t)stage_bytes;
+      const uint32_t vs_a = st_a + (uint32_t)vec_off + 8u * threadIdx.x;
+      const uint32_t pid = (uint32_t)lds_s32(st_a), windowed = (uint32_t)lds_s32(st_a + 4u);
+      const uint32_t P_a = smem_a + pid * (uint32_t)sizeof(StPattern);
+      const uint32_t L = (uint32_t)lds_s32(P_a);
+      const uint32_t m0 = lds_u8(st_a + ST_MASK_OFF + threadIdx.x), m1 = lds_u8(st_a + ST_MASK_OFF + threadIdx.x + PK_CT);
+      const int      r0 = tile * TR + threadIdx.x, r1 = r0 + PK_CT;
+      double         s0, s1;
+      if (windowed) st_win2_dispatch(L, m0, m1, P_a, st_a + ST_WIN_OFF + 8u * threadIdx.x, gx, s0, s1);
+      else st_row2_dispatch(L, m0, m1, P_a + (uint32_t)offsetof(StPattern, v), P_a + (uint32_t)offsetof(StPattern, d), gx, r0, r1, s0, s1);
+      if (r0 < A.n) epi.row_s(r0, vs_a, s0, acc);
+      if (r1 < A.n) epi.row_s(r1, vs_a + PK_CT * 8u, s1, acc);
       __syncwarp();
       if (lane == 0) mbar_arrive(&empty_bar[s]);
       if (++s == nstages) {
@@ -1247,6 +1443,54 @@ static int launch_pk(const CsrDev &A, const double *x, const Epi &epi, TileOrder
   }
 }
 
+
+template <class Epi>
+static int launch_st(const CsrDev &A, const double *x, const Epi &epi, TileOrder ord)
+{
+  if constexpr (!EpiHasStaged<Epi>::value) {
+    set_error("internal: epilogue without staged vectors on a stencil matrix");
+    return 76;
+  } else {
+    const int nv = epi.nvec_host();
+    int       vec_tma = aligned16(A.st_masks) ? 1 : 0;
+    for (int v = 0; v < nv && vec_tma; v++) vec_tma = aligned16(epi.vsrc_host(v));
+    const int    win_ok = aligned16(x) ? 1 : 0;
+    const int    pats_bytes = (int)((A.st_npat * sizeof(StPattern) + 127) & ~(size_t)127);
+    const size_t stage = ((size_t)ST_WIN_OFF + (size_t)A.st_nwin * PB_ST_WCAP + (size_t)nv * TR * 8 + 127) & ~(size_t)127;
+    // stages: as many as leave room for 4 CTAs per SM (the windows make a stage 14-20 KB), at least 2
+    int nstages = A.stages > 0 ? A.stages : (int)(((size_t)224 * 1024 / 4 - 1024 - (size_t)pats_bytes) / stage);
+    if (nstages > TMA_MAX_STAGES) nstages = TMA_MAX_STAGES;
+    if (nstages < 2) nstages = 2;
+    const size_t smem = (size_t)pats_bytes + stage * nstages;
+    if (smem > 220 * 1024) {
+      set_error("stencil SpMV stage does not fit in shared memory (%zu bytes)", smem);
+      return 76;
+    }
+    static size_t attr_smem = 0;
+    if (smem > attr_smem) {
+      cudaFuncSetAttribute(k_spmv_st<Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      attr_smem = smem;
+    }
+    static int    occ = 0;
+    static size_t occ_smem = (size_t)-1;
+    if (!occ || occ_smem != smem) {
+      int nb = 0;
+      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_spmv_st<Epi>, PK_CT + 32, smem) != cudaSuccess || nb < 1) nb = 1;
+      occ      = nb;
+      occ_smem = smem;
+    }
+    int ntiles = (A.n + TR - 1) / TR, grid = g_ctx.sm_count * occ;
+    if (grid > ntiles) grid = ntiles;
+    if (grid > max_red_blocks()) grid = max_red_blocks();
+    if (ord.tb <= ord.ta || ord.tb > ntiles) {
+      ord.ta = 0;
+      ord.tb = ntiles;
+    }
+    launch_k(k_spmv_st<Epi>, grid, PK_CT + 32, smem, A, x, epi, nstages, (int)stage, pats_bytes, win_ok, vec_tma, ord);
+    return 0;
+  }
+}
+
 template <class Epi>
 static int launch_spmv(const CsrDev &A, const double *x, const Epi &epi, int family, double bytes, TileOrder ord = TileOrder())
 {
@@ -1254,6 +1498,8 @@ static int launch_spmv(const CsrDev &A, const double *x, const Epi &epi, int fam
   if (A.n == 0) {
     // still run one CTA so that reductions publish their (identity) record
     k_spmv_vector<Epi, 32><<<1, NT, 0, g_ctx.stream>>>(A, x, epi);
+  } else if (A.kind == 4) {
+    PB_CHK(launch_st(A, x, epi, ord));
   } else if (A.kind == 3) {
     PB_CHK(launch_pk(A, x, epi, ord));
   } else if (A.kind == 2) {
@@ -1287,7 +1533,7 @@ static int launch_spmv(const CsrDev &A, const double *x, const Epi &epi, int fam
 
 double csr_stream_bytes(const CsrDev &A)
 {
-  if (A.kind == 3) return (double)A.pk_bytes;
+  if (A.kind == 3 || A.kind == 4) return (double)A.pk_bytes;
   return 12.0 * (double)A.nnz + 4.0 * (A.n + 1);
 }
 
@@ -1331,6 +1577,8 @@ int spmv_config(CsrDev &A, const int *h_ia)
 
 // ---- epilogues ---------------------------------------------------------------------------------------
 struct EpiPlain {
+  typedef GatherPlain Gather;
+  __device__ Gather gather(const double *x) const { return Gather{x}; }
   double *y;
   int     accumulate;
   struct Acc {};
@@ -1346,7 +1594,9 @@ struct EpiPlain {
   __device__ void row_s(int r, uint32_t, double ax, Acc &a) const { row(r, ax, a); }
 };
 
-struct EpiGated {   // plain SpMV that only runs in the right phase of the device-driven iteration
+struct EpiGated {
+  typedef GatherPlain Gather;
+  __device__ Gather gather(const double *x) const { return Gather{x}; }   // plain SpMV that only runs in the right phase of the device-driven iteration
   double        *y;
   const MpgpCtl *S;
   int            phase;
@@ -1397,6 +1647,8 @@ __device__ __forceinline__ double ghost_apply(const GhostMerge &gm, int r, doubl
 // (two-sided boxes, C5); MODE 0: anything.  In modes 1 and 2 the staged path sheds every run-time flag.
 template <int MODE>
 struct EpiAT {
+  typedef GatherPlain Gather;
+  __device__ Gather gather(const double *x) const { return Gather{x}; }
   const double        *p, *x;
   double              *Ap;
   BoxDev               bx;
@@ -1480,6 +1732,8 @@ typedef EpiAT<0> EpiA;
 // K_A' epilogue: g_r = (A x)_r + rho (B^T Bu)_r - b_r ; split ; p = gf ; |gP|^2 |gc|^2 |gf|^2
 template <int MODE>
 struct EpiA2T {
+  typedef GatherPlain Gather;
+  __device__ Gather gather(const double *x) const { return Gather{x}; }
   const double        *x, *b;
   double              *g, *p;
   BoxDev               bx;
@@ -1570,6 +1824,54 @@ struct EpiA2T {
   }
 };
 typedef EpiA2T<0> EpiA2;
+
+// power-method step (MatGetMaxEigenvalue, permonmatutils.c:484-511) in ONE pass: the normalised iterate v = s * w is formed on the
+// fly (the same product VecScale would have stored), y = A v, and the two dot products of VecMDot(v, {Av, v}) ride in the epilogue
+struct EpiPower {
+  typedef GatherScaled Gather;
+  const double *w;
+  double        s;
+  double       *y;
+  RedBuf        rb;
+  __device__ Gather gather(const double *x) const { return Gather{x, s}; }
+  typedef AccRed Acc;
+  __device__ bool active() const { return true; }
+  __device__ bool reverse() const { return false; }
+  __device__ void init(Acc &a) const
+  {
+#pragma unroll
+    for (int k = 0; k < PB_NRED; k++) a.v[k] = 0.0;
+    a.halo_ok = 0;
+  }
+  __device__ void row(int r, double ax, Acc &a) const
+  {
+    y[r] = ax;
+    const double vr = w[r] * s;
+    a.v[0] += ax * vr;
+    a.v[1] += vr * vr;
+  }
+  __device__ void finalize(Acc &a) const { grid_reduce8<0>(a.v, rb, nullptr); }
+  __host__ __device__ int nvec() const { return 1; }
+  __host__ __device__ const double *vsrc(int) const { return w; }
+  int nvec_host() const { return 1; }
+  const double *vsrc_host(int) const { return w; }
+  __device__ void row_s(int r, uint32_t va, double ax, Acc &a) const
+  {
+    y[r] = ax;
+    const double vr = lds_f64(va) * s;
+    a.v[0] += ax * vr;
+    a.v[1] += vr * vr;
+  }
+};
+int k_power_step(const CsrDev &A, const double *w, double s, double *y, RedBuf rb)
+{
+  if (A.kind != 3 && A.kind != 4) {
+    set_error("internal: fused power step needs a packed matrix");
+    return 76;
+  }
+  EpiPower e{w, s, y, rb};
+  return launch_spmv(A, w, e, KF_SPMV_PLAIN, csr_stream_bytes(A) + 16.0 * A.n);
+}
 
 int k_spmv(const CsrDev &A, const double *x, double *y, int accumulate)
 {
@@ -1992,7 +2294,7 @@ __global__ void __launch_bounds__(NT, 8) k_direction_C(MpgpVecs v, CtrlFold cf, 
         if (PUSH) push_boundary(hp, r, pn);
       }
     }
-    grid_reduce1(gp, rc, RA_GP);
+    block_partial1(gp, rc.partials);
   } else if (pmode == 2) {
     for (int r = blockIdx.x * NT + threadIdx.x; r < v.n; r += stride) {
       double gf, gc;
@@ -2011,12 +2313,16 @@ __global__ void __launch_bounds__(NT, 8) k_direction_C(MpgpVecs v, CtrlFold cf, 
   if (PUSH) push_signal(hp, push_seq, &s_plast);
 }
 
-int k_fused_C(const MpgpVecs &v, const CtrlFold &cf, RedBuf rc, const PushRanges *hp, unsigned long long push_seq)
+int fused_C_grid(int n)
 {
   int grid = elementwise_grid();
-  int need = (v.n + NT - 1) / NT;
+  int need = (n + NT - 1) / NT;
   if (need < 1) need = 1;
-  if (grid > need) grid = need;
+  return grid > need ? need : grid;
+}
+int k_fused_C(const MpgpVecs &v, const CtrlFold &cf, RedBuf rc, const PushRanges *hp, unsigned long long push_seq)
+{
+  const int grid = fused_C_grid(v.n);
   const int vec2 = (v.n % 2 == 0) && aligned16(v.gf) && aligned16(v.g) && aligned16(v.p) && !getenv("PERMON_B200_NOVEC");
   prof_pre(KF_DIR_C, 8.0 * v.n * 3.125);
   if (hp) launch_k(k_direction_C<true>, grid, NT, 0, v, cf, rc, hp, push_seq, vec2);
@@ -2177,6 +2483,10 @@ int k_copy(int n, const double *x, double *y)
 int k_scale(int n, double *x, double a)
 {
   return launch_ew(n, [=] __device__(int i) { x[i] *= a; }, KF_VEC, 16.0 * n);
+}
+int k_scale_to(int n, double *y, double a, const double *x)
+{   // y = a x : VecCopy + VecScale in one pass (same products, same rounding)
+  return launch_ew(n, [=] __device__(int i) { y[i] = x[i] * a; }, KF_VEC, 16.0 * n);
 }
 int k_axpy(int n, double *y, double a, const double *x)
 {

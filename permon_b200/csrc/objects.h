@@ -58,6 +58,7 @@ struct _p_Vec : PObj {
   bool     h_valid = false, d_valid = false;
   bool     invalidated = false;
   int64_t  state = 0;
+  cudaEvent_t up_ev = nullptr;   // a prefetch (H2D on the copy stream) is in flight: settled by the next access
   ~_p_Vec() override;
 };
 
@@ -270,6 +271,7 @@ struct Reducer {
 };
 Reducer &reducer(MPI_Comm comm);           // shared scratch reducer of the communicator
 
+int  vec_prefetch(Vec v);                                    // start the H2D copy of a host-valid vector on the copy stream (pinned buffers: truly asynchronous)
 int  vec_dot(Vec x, Vec y, double *val);
 int  vec_norm2(Vec x, double *val);
 int  vec_mdot2(Vec x, Vec y0, Vec y1, double *v0, double *v1);

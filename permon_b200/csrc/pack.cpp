@@ -87,9 +87,12 @@ struct TileDict {
 // k-th entry of a row is first compared with the k-th entry of the previous row (a hit for almost every entry of a stencil
 // matrix), the hash table is only consulted on a miss.  Pass 2 lays the blobs out: dictionary, row offsets and code bytes are
 // copied, nothing is hashed again.
+// st (optional): when every tile is a stencil tile and the matrix has at most PB_ST_MAXPAT patterns, the all-stencil form (device.h)
+// is returned there; with want_blob == false the tile blobs are then not built at all.
 int pk_build(int n, const int *ia, const int *ja, const double *a, RawBuf &blob, std::vector<unsigned> &h_off, int &max_tile_bytes,
-             int64_t &ncoded, bool &packed)
+             int64_t &ncoded, bool &packed, StencilHost *st, bool want_blob)
 {
+  if (st) st->valid = false;
   const int ntiles = (n + TR - 1) / TR;
   packed           = false;
   h_off.assign((size_t)ntiles + 1, 0);
@@ -240,6 +243,70 @@ int pk_build(int n, const int *ia, const int *ja, const double *a, RawBuf &blob,
   if (bad) {
     free(codes_tmp);
     return 0;
+  }
+  if (st && ntiles > 0) {
+    // all-stencil form: dedupe the tiles' patterns (a handful for a structured grid), then lay out the windows of each
+    bool all = true;
+    for (int t = 0; t < ntiles && all; t++) all = (tkind[t] == 2);
+    if (all) {
+      st->pats.clear();
+      st->pid.assign((size_t)ntiles, 0);
+      for (int t = 0; t < ntiles && all; t++) {
+        const int       L = tnd[t];
+        const int      *pd = arena_d[tthr[t]].data() + tdoff[t];
+        const uint64_t *pb = arena_b[tthr[t]].data() + tdoff[t];
+        int             id = -1;
+        // the previous tile's pattern first: consecutive tiles almost always share it
+        const int prev = t > 0 ? st->pid[(size_t)t - 1] : 0;
+        for (int c = 0; c < (int)st->pats.size() && id < 0; c++) {
+          const int        q = (c == 0) ? prev : (c <= prev ? c - 1 : c);
+          if (q >= (int)st->pats.size()) continue;
+          const StPattern &P = st->pats[q];
+          if (P.L == L && !memcmp(P.d, pd, sizeof(int) * L) && !memcmp(P.v, pb, sizeof(double) * L)) id = q;
+        }
+        if (id < 0) {
+          if ((int)st->pats.size() == PB_ST_MAXPAT) {
+            all = false;
+            break;
+          }
+          StPattern P;
+          memset(&P, 0, sizeof P);
+          P.L = L;
+          memcpy(P.d, pd, sizeof(int) * L);
+          memcpy(P.v, pb, sizeof(double) * L);
+          // windows: consecutive deltas within PB_ST_SPAN of the window's first delta share it
+          int w = -1, first = 0;
+          for (int j = 0; j < L; j++) {
+            if (w < 0 || P.d[j] - first > PB_ST_SPAN) {
+              w++;
+              first    = P.d[j];
+              P.wlo[w] = (first & 1) ? first - 1 : first;   // even: 16-byte aligned copies (floor for negative odd values too)
+            }
+            int hi = P.d[j] + TR;
+            if (hi & 1) hi++;
+            P.wlen[w] = hi - P.wlo[w];
+            P.erel[j] = w * PB_ST_WCAP + (P.d[j] - P.wlo[w]) * 8;
+          }
+          P.nwin = w + 1;
+          id     = (int)st->pats.size();
+          st->pats.push_back(P);
+        }
+        st->pid[(size_t)t] = (unsigned char)id;
+      }
+      if (all && st->masks.alloc((size_t)ntiles * TR)) {
+        memcpy(st->masks.data(), masks_tmp, (size_t)n);
+        memset(st->masks.data() + n, 0, (size_t)ntiles * TR - (size_t)n);
+        st->nwin = 0;
+        for (const StPattern &P : st->pats) st->nwin = std::max(st->nwin, P.nwin);
+        st->valid = true;
+        if (!want_blob) {
+          free(codes_tmp);
+          ncoded = coded;
+          packed = true;
+          return 0;
+        }
+      }
+    }
   }
   size_t tot = 0;
   max_tile_bytes = 0;

@@ -1194,7 +1194,7 @@ PetscErrorCode QPTOrthonormalizeEq(QP qp, MatOrthType type, MatOrthForm form)
   TB->m = TB->M = m;
   TB->n      = n;
   TB->N      = qp->BE->N;
-  PB_CUDA(cudaMalloc(&TB->rows_d, sizeof(double) * (size_t)m * std::max(n, 1)));
+  PB_CHK(dmalloc(&TB->rows_d, (size_t)m * std::max(n, 1)));
   std::vector<double> T((size_t)m * m, 0.0);
   for (int i = 0; i < m; i++) T[i * m + i] = 1.0;
   if (type == MAT_ORTH_CHOLESKY) {

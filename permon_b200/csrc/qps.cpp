@@ -485,8 +485,8 @@ struct MpgpImpl : QPSImpl {   // QPS_MPGP mpgpimpl.h:5-38
     for (auto &w : work) pb::unref(w);
     work.clear();
     if (engine_ready) {
-      cudaFree(dS);
-      cudaFreeHost(hS);
+      dfree(dS);
+      pinned_put(hS, sizeof(MpgpCtl));
       RA.destroy();
       RB.destroy();
       RC.destroy();
@@ -625,6 +625,15 @@ PetscErrorCode MpgpImpl::setup(QPS qps)
   case QPS_MPGP_EXPANSION_PROJCG: expdirection = work[1]; explengthvec = work[1]; break;
   default: return err(PETSC_ERR_PLIB, "Unknown MPGP expansion type");
   }
+  {   // the uploads of b, x and the bounds travel on the copy stream while the power method below runs
+    QP qp = qps->solQP;
+    PB_CHK(vec_prefetch(qp->b));
+    PB_CHK(vec_prefetch(qp->x));
+    if (qp->qpc && !qp->qpc->is) {
+      PB_CHK(vec_prefetch(qp->qpc->lb));
+      PB_CHK(vec_prefetch(qp->qpc->ub));
+    }
+  }
   if (alpha_type == QPS_ARG_MULTIPLE) {   // :417-425
     if (maxeig == PETSC_DECIDE) {
       PhaseTimer pt("MPGP set-up: MatGetMaxEigenvalue");
@@ -642,8 +651,9 @@ int MpgpImpl::engine_init(QPS qps)
 {
   if (engine_ready) return 0;
   PB_CHK(dev_init());
-  PB_CUDA(cudaMalloc(&dS, 2 * sizeof(MpgpCtl)));
-  PB_CUDA(cudaMallocHost(&hS, sizeof(MpgpCtl)));
+  PB_CHK(dmalloc(&dS, 2));
+  hS = (MpgpCtl *)pinned_get(sizeof(MpgpCtl));
+  if (!hS) return err(PETSC_ERR_MEM, "out of pinned host memory");
   PB_CHK(RA.init(qps->comm));
   PB_CHK(RB.init(qps->comm));
   PB_CHK(RC.init(qps->comm));
@@ -728,8 +738,9 @@ int MpgpImpl::solve_fused(QPS qps)
   auto red = [&](Reducer &R, int kind, bool publish) -> RedBuf {
     RedBuf rb = R.rb;
     if (kind == 0) {   // K_A: slot RA_GP of its record is the local g.p that K_C summed while it wrote p
-      rb.add1      = RC.rb.out + RA_GP;
-      rb.add1_slot = RA_GP;
+      rb.add_part = RC.rb.partials;
+      rb.add_n    = fused_C_grid(v.n);
+      rb.add_slot = RA_GP;
     }
     if (p2p && publish) {
       rb.win  = comm->d_win;

@@ -104,29 +104,31 @@ int Reducer::init(MPI_Comm c)
   comm = c;
   PB_CHK(dev_init());
   const int size = c->size;
-  PB_CUDA(cudaMalloc(&rb.partials, sizeof(double) * PB_NRED * (size_t)max_red_blocks()));
-  PB_CUDA(cudaMalloc(&rb.counter, sizeof(unsigned)));
-  PB_CUDA(cudaMemset(rb.counter, 0, sizeof(unsigned)));
-  PB_CUDA(cudaMalloc(&d_all, sizeof(double) * PB_NRED * size));
-  PB_CUDA(cudaMemset(d_all, 0, sizeof(double) * PB_NRED * size));
+  cudaStream_t s = ctx().stream;
+  PB_CHK(dmalloc(&rb.partials, PB_NRED * (size_t)max_red_blocks()));
+  PB_CHK(dmalloc(&rb.counter, 4));   // 16 bytes: the counter and its padding
+  PB_CUDA(cudaMemsetAsync(rb.counter, 0, sizeof(unsigned), s));
+  PB_CHK(dmalloc(&d_all, (size_t)PB_NRED * size));
+  PB_CUDA(cudaMemsetAsync(d_all, 0, sizeof(double) * PB_NRED * size, s));
   if (size > 1) {
-    PB_CUDA(cudaMalloc(&d_local, sizeof(double) * PB_NRED));
-    PB_CUDA(cudaMemset(d_local, 0, sizeof(double) * PB_NRED));
+    PB_CHK(dmalloc(&d_local, (size_t)PB_NRED));
+    PB_CUDA(cudaMemsetAsync(d_local, 0, sizeof(double) * PB_NRED, s));
   } else {
     d_local = d_all;
   }
-  PB_CUDA(cudaMallocHost(&h_all, sizeof(double) * PB_NRED * size));
+  h_all = (double *)pinned_get(sizeof(double) * PB_NRED * size);
+  if (!h_all) return err(PETSC_ERR_MEM, "out of pinned host memory");
   rb.out = d_local;
   return 0;
 }
 void Reducer::destroy()
 {
   if (!rb.partials) return;
-  cudaFree(rb.partials);
-  cudaFree(rb.counter);
-  if (d_local != d_all) cudaFree(d_local);
-  cudaFree(d_all);
-  cudaFreeHost(h_all);
+  dfree(rb.partials);
+  dfree(rb.counter);
+  if (d_local != d_all) dfree(d_local);
+  dfree(d_all);
+  pinned_put(h_all, sizeof(double) * PB_NRED * comm->size);
   rb = RedBuf();
   d_local = d_all = h_all = nullptr;
 }
@@ -215,7 +217,7 @@ static int vec_alloc_dev(Vec v)
 {
   if (v->d) return 0;
   PB_CHK(dev_init());
-  PB_CUDA(cudaMalloc(&v->d, sizeof(double) * (size_t)std::max<PetscInt>(v->n, 1)));
+  PB_CHK(dmalloc(&v->d, (size_t)std::max<PetscInt>(v->n, 1)));
   v->d_owned = true;
   return 0;
 }
@@ -227,8 +229,35 @@ static int vec_alloc_host(Vec v)
   v->h_owned = true;
   return 0;
 }
+// a prefetch in flight: device users wait on the stream, host users on the host
+static int vec_settle(Vec v, bool host_side)
+{
+  if (!v->up_ev) return 0;
+  if (host_side) PB_CUDA(cudaEventSynchronize(v->up_ev));
+  else PB_CUDA(cudaStreamWaitEvent(ctx().stream, v->up_ev, 0));
+  PB_CUDA(cudaEventDestroy(v->up_ev));
+  v->up_ev = nullptr;
+  return 0;
+}
+int vec_prefetch(Vec v)
+{
+  if (!v || v->d_valid || !v->h_valid || v->n == 0 || v->up_ev || getenv("PERMON_B200_NOPREFETCH")) return 0;
+  PB_CHK(vec_alloc_dev(v));
+  DevCtx     &c = ctx();
+  cudaEvent_t ea;
+  PB_CUDA(cudaEventCreateWithFlags(&ea, cudaEventDisableTiming));
+  PB_CUDA(cudaEventRecord(ea, c.stream));   // the (stream-ordered) allocation precedes the copy
+  PB_CUDA(cudaStreamWaitEvent(c.copy_stream, ea, 0));
+  PB_CUDA(cudaEventDestroy(ea));
+  PB_CUDA(cudaMemcpyAsync(v->d, v->h, sizeof(double) * (size_t)v->n, cudaMemcpyHostToDevice, c.copy_stream));
+  PB_CUDA(cudaEventCreateWithFlags(&v->up_ev, cudaEventDisableTiming));
+  PB_CUDA(cudaEventRecord(v->up_ev, c.copy_stream));
+  v->d_valid = true;
+  return 0;
+}
 int vec_dev_read(Vec v, const double **d)
 {
+  PB_CHK(vec_settle(v, false));
   PB_CHK(vec_alloc_dev(v));
   if (!v->d_valid) {
     if (v->h_valid) PB_CUDA(cudaMemcpyAsync(v->d, v->h, sizeof(double) * (size_t)v->n, cudaMemcpyHostToDevice, ctx().stream));
@@ -240,6 +269,7 @@ int vec_dev_read(Vec v, const double **d)
 }
 int vec_dev_write(Vec v, double **d)
 {
+  PB_CHK(vec_settle(v, false));
   PB_CHK(vec_alloc_dev(v));
   v->d_valid = true;
   v->h_valid = false;
@@ -258,6 +288,7 @@ int vec_dev_rw(Vec v, double **d)
 }
 int vec_host_read(Vec v, const double **h)
 {
+  PB_CHK(vec_settle(v, true));
   PB_CHK(vec_alloc_host(v));
   if (!v->h_valid) {
     if (v->d_valid) {
@@ -274,6 +305,7 @@ int vec_host_read(Vec v, const double **h)
 }
 int vec_host_write(Vec v, double **h)
 {
+  PB_CHK(vec_settle(v, true));
   PB_CHK(vec_alloc_host(v));
   if (v->d_valid && ctx().ready) PB_CUDA(cudaStreamSynchronize(ctx().stream));   // pending device readers of the old contents
   v->h_valid = true;
@@ -331,8 +363,12 @@ int vec_mdot2(Vec x, Vec y0, Vec y1, double *v0, double *v1)
 
 _p_Vec::~_p_Vec()
 {
+  if (up_ev) {
+    cudaEventSynchronize(up_ev);
+    cudaEventDestroy(up_ev);
+  }
   if (h_owned && h) free(h);
-  if (d_owned && d) cudaFree(d);
+  if (d_owned && d) pb::dfree(d);
 }
 
 // =====================================================================================================
@@ -893,24 +929,27 @@ PetscErrorCode VecIsInvalidated(Vec vec, PetscBool *flg)
 _p_Mat::~_p_Mat()
 {
   if (kind == MK_AIJ && d_owned) {
-    cudaFree((void *)Ad.ia);
-    cudaFree((void *)Ad.ja);
-    cudaFree((void *)Ad.a);
-    cudaFree((void *)Ad.pk);
-    cudaFree((void *)Ad.pk_off);
+    pb::dfree(Ad.ia);
+    pb::dfree(Ad.ja);
+    pb::dfree(Ad.a);
+    pb::dfree(Ad.pk);
+    pb::dfree(Ad.pk_off);
+    pb::dfree(Ad.st_masks);
+    pb::dfree(Ad.st_pid);
+    pb::dfree(Ad.st_pats);
   }
-  if (kind == MK_DENSEROWS) cudaFree(rows_d);
+  if (kind == MK_DENSEROWS) pb::dfree(rows_d);
   if (kind == MK_AIJ) {
-    cudaFree((void *)Ao.ia);
-    cudaFree((void *)Ao.ja);
-    cudaFree((void *)Ao.a);
-    cudaFree((void *)Ao.rows);
+    pb::dfree(Ao.ia);
+    pb::dfree(Ao.ja);
+    pb::dfree(Ao.a);
+    pb::dfree(Ao.rows);
   }
   if (halo) {
-    cudaFree(halo->d_send_idx);
-    cudaFree(halo->d_send);
-    cudaFree(halo->d_ghost);
-    cudaFree(halo->d_row_map);
+    pb::dfree(halo->d_send_idx);
+    pb::dfree(halo->d_send);
+    pb::dfree(halo->d_ghost);
+    pb::dfree(halo->d_row_map);
     if (halo->ev_packed) cudaEventDestroy(halo->ev_packed);
     if (halo->ev_arrived) cudaEventDestroy(halo->ev_arrived);
     if (halo->ev_consumed) cudaEventDestroy(halo->ev_consumed);
@@ -932,7 +971,7 @@ _p_Mat::~_p_Mat()
 
 namespace pb {
 int pk_build(int n, const int *ia, const int *ja, const double *a, RawBuf &blob, std::vector<unsigned> &h_off, int &max_tile_bytes,
-             int64_t &ncoded, bool &packed);
+             int64_t &ncoded, bool &packed, StencilHost *st, bool want_blob);
 }
 
 static double wall_now()
@@ -952,7 +991,7 @@ static int upload_csr(pb::CsrDev &C, int nrows, int ncols, const int *ia, const 
   cudaStream_t s = ctx().stream;
   if (rows) {
     int *dr;
-    PB_CUDA(cudaMalloc(&dr, sizeof(int) * (size_t)std::max(nrows, 1)));
+    PB_CHK(dmalloc(&dr, (size_t)std::max(nrows, 1)));
     PB_CUDA(cudaMemcpyAsync(dr, rows, sizeof(int) * (size_t)nrows, cudaMemcpyHostToDevice, s));
     C.rows = dr;
   }
@@ -966,13 +1005,42 @@ static int upload_csr(pb::CsrDev &C, int nrows, int ncols, const int *ia, const 
     int64_t                    ncoded = 0;
     bool                       packed = false;
     const double t_pk0 = wall_now();
-    PB_CHK(pb::pk_build(nrows, ia, ja, a, blob, off, max_tile, ncoded, packed));
+    pb::StencilHost st;
+    const char     *env_w = getenv("PERMON_B200_ST_WINDOWS");
+    const bool      want_st = !(env_w && env_w[0] == '0') && nrows == ncols;
+    PB_CHK(pb::pk_build(nrows, ia, ja, a, blob, off, max_tile, ncoded, packed, want_st ? &st : nullptr, false));
     const double t_pk1 = wall_now();
+    if (packed && st.valid) {
+      // all-stencil form: presence bytes + pattern ids + pattern table
+      unsigned char *dm, *dp;
+      pb::StPattern *dt;
+      PB_CHK(dmalloc(&dm, st.masks.size()));
+      PB_CHK(dmalloc(&dp, st.pid.size()));
+      PB_CHK(dmalloc(&dt, st.pats.size()));
+      PB_CUDA(cudaMemcpyAsync(dm, st.masks.data(), st.masks.size(), cudaMemcpyHostToDevice, s));
+      PB_CUDA(cudaMemcpyAsync(dp, st.pid.data(), st.pid.size(), cudaMemcpyHostToDevice, s));
+      PB_CUDA(cudaMemcpyAsync(dt, st.pats.data(), sizeof(pb::StPattern) * st.pats.size(), cudaMemcpyHostToDevice, s));
+      PB_CUDA(cudaStreamSynchronize(s));   // st is a local
+      if (verbose_timing())
+        fprintf(stderr, "[permon_b200] matrix %d rows, %lld nnz: all-stencil form (%d patterns, %d windows) built in %.1f ms, %.1f MB uploaded in %.1f ms\n", nrows,
+                (long long)nnz, (int)st.pats.size(), st.nwin, 1e3 * (t_pk1 - t_pk0), (st.masks.size() + st.pid.size()) / 1e6, 1e3 * (wall_now() - t_pk1));
+      C.st_masks = dm;
+      C.st_pid   = dp;
+      C.st_pats  = dt;
+      C.st_npat  = (int)st.pats.size();
+      C.st_nwin  = st.nwin;
+      C.pk_bytes = (int64_t)st.masks.size() + (int64_t)st.pid.size() + (int64_t)(sizeof(pb::StPattern) * st.pats.size());
+      C.pk_coded = ncoded;
+      C.kind     = 4;
+      const char *stg = getenv("PERMON_B200_STAGES");
+      C.stages = stg ? atoi(stg) : 0;   // 0: as many as fit
+      return 0;
+    }
     if (packed) {
       unsigned char *dblob;
       unsigned      *doff;
-      PB_CUDA(cudaMalloc(&dblob, blob.size()));
-      PB_CUDA(cudaMalloc(&doff, sizeof(unsigned) * off.size()));
+      PB_CHK(dmalloc(&dblob, blob.size()));
+      PB_CHK(dmalloc(&doff, off.size()));
       PB_CUDA(cudaMemcpyAsync(dblob, blob.data(), blob.size(), cudaMemcpyHostToDevice, s));
       PB_CUDA(cudaMemcpyAsync(doff, off.data(), sizeof(unsigned) * off.size(), cudaMemcpyHostToDevice, s));
       PB_CUDA(cudaStreamSynchronize(s));   // blob / off are locals
@@ -993,9 +1061,9 @@ static int upload_csr(pb::CsrDev &C, int nrows, int ncols, const int *ia, const 
   int *dia, *dja;
   double *da;
   // 8 elements of padding: the TMA kernel copies 16-byte aligned, 16-byte granular tile ranges
-  PB_CUDA(cudaMalloc(&dia, sizeof(int) * (size_t)(nrows + 1 + 8)));
-  PB_CUDA(cudaMalloc(&dja, sizeof(int) * (size_t)(nnz + 8)));
-  PB_CUDA(cudaMalloc(&da, sizeof(double) * (size_t)(nnz + 8)));
+  PB_CHK(dmalloc(&dia, (size_t)(nrows + 1 + 8)));
+  PB_CHK(dmalloc(&dja, (size_t)(nnz + 8)));
+  PB_CHK(dmalloc(&da, (size_t)(nnz + 8)));
   PB_CUDA(cudaMemsetAsync(dia + nrows + 1, 0, sizeof(int) * 8, s));
   PB_CUDA(cudaMemsetAsync(dja + nnz, 0, sizeof(int) * 8, s));
   PB_CUDA(cudaMemsetAsync(da + nnz, 0, sizeof(double) * 8, s));
@@ -1357,16 +1425,16 @@ int mat_ensure_device(Mat A)
   const PetscInt m = A->m;
   PB_CHK(upload_csr(A->Ad, m, A->n, S->dia.data(), S->dja.data(), S->da.data(), nullptr));
   PB_CHK(upload_csr(A->Ao, (int)S->orow.size(), (int)H->garray.size(), S->oia.data(), S->oja.data(), S->oa.data(), S->orow.data()));
-  PB_CUDA(cudaMalloc(&H->d_send_idx, sizeof(int) * std::max<size_t>(H->send_idx.size(), 1)));
-  PB_CUDA(cudaMalloc(&H->d_send, sizeof(double) * std::max<size_t>(H->send_idx.size(), 1)));
-  PB_CUDA(cudaMalloc(&H->d_ghost, sizeof(double) * std::max<size_t>(H->garray.size(), 1)));
+  PB_CHK(dmalloc(&H->d_send_idx, std::max<size_t>(H->send_idx.size(), 1)));
+  PB_CHK(dmalloc(&H->d_send, std::max<size_t>(H->send_idx.size(), 1)));
+  PB_CHK(dmalloc(&H->d_ghost, std::max<size_t>(H->garray.size(), 1)));
   // rows outside the ghost-free run [skip_lo, skip_hi) -> their row in the compressed off-diagonal block (GhostMerge)
   std::vector<int> row_map((size_t)std::max<PetscInt>(H->skip_lo + (m - H->skip_hi), 1), -1);
   for (size_t q = 0; q < S->orow.size(); q++) {
     const int r = S->orow[q];
     row_map[r < H->skip_lo ? r : r - H->skip_hi + H->skip_lo] = (int)q;
   }
-  PB_CUDA(cudaMalloc(&H->d_row_map, sizeof(int) * row_map.size()));
+  PB_CHK(dmalloc(&H->d_row_map, row_map.size()));
   PB_CUDA(cudaMemcpyAsync(H->d_send_idx, H->send_idx.data(), sizeof(int) * H->send_idx.size(), cudaMemcpyHostToDevice, ctx().stream));
   PB_CUDA(cudaMemcpyAsync(H->d_row_map, row_map.data(), sizeof(int) * row_map.size(), cudaMemcpyHostToDevice, ctx().stream));
   PB_CUDA(cudaEventCreateWithFlags(&H->ev_packed, cudaEventDisableTiming));
@@ -1432,7 +1500,7 @@ PetscErrorCode PermonB200PackTiles(PetscInt n, const PetscInt ia[], const PetscI
   int                        max_tile = 0;
   int64_t                    ncoded = 0;
   bool                       packed = false;
-  PB_CHK(pb::pk_build(n, ia, ja, a, b, off, max_tile, ncoded, packed));
+  PB_CHK(pb::pk_build(n, ia, ja, a, b, off, max_tile, ncoded, packed, nullptr, true));
   *blob     = nullptr;
   *tile_off = nullptr;
   if (ntiles) *ntiles = (n + pb::TR - 1) / pb::TR;
@@ -1670,6 +1738,18 @@ PetscErrorCode MatMultTranspose(Mat A, Vec x, Vec y)
   return VecScale(y, xv);
 }
 
+// PETSCRAND48 (the generator MatGetMaxEigenvalue creates for its null-space restart, permonmatutils.c:496-499): PetscRandomCreate seeds
+// it with 0x12345678 + 76543 * rank, VecSetRandom draws one drand48() per local entry, in order.  drand48 is the 48-bit linear
+// congruential generator X <- 0x5DEECE66D X + 0xB (mod 2^48) started at (seed << 16) | 0x330E, value X / 2^48.
+static void rand48_fill(int rank, PetscInt n, double *out)
+{
+  uint64_t X = (((uint64_t)(uint32_t)(0x12345678 + 76543 * rank)) << 16) | 0x330Eull;
+  for (PetscInt i = 0; i < n; i++) {
+    X      = (0x5DEECE66Dull * X + 0xBull) & 0xFFFFFFFFFFFFull;
+    out[i] = (double)X * (1.0 / 281474976710656.0);
+  }
+}
+
 // MatGetMaxEigenvalue: src/mat/interface/permonmatutils.c:442-522 (power method, v0 = 1)
 PetscErrorCode MatGetMaxEigenvalue(Mat A, Vec v, PetscReal *lambda_out, PetscReal tol, PetscInt maxits)
 {
@@ -1678,6 +1758,46 @@ PetscErrorCode MatGetMaxEigenvalue(Mat A, Vec v, PetscReal *lambda_out, PetscRea
   double lambda = 0.0, lambda0, err_, relerr, vAv, vv;
   if (tol == PETSC_DECIDE || tol == PETSC_DEFAULT) tol = 1e-4;            /* :473 */
   if (maxits == PETSC_DECIDE || maxits == PETSC_DEFAULT) maxits = 50;     /* :474 */
+  // the reference looks for a stashed estimate first (:462-469); nothing in PERMON ever stores one, so there is none to return
+  if (!v && A->kind == MK_AIJ && A->comm->size == 1 && !getenv("PERMON_B200_NOFUSEDPOWER")) {
+    PB_CHK(mat_ensure_device(A));
+    if ((A->Ad.kind == 3 || A->Ad.kind == 4) && A->m == A->n) {
+      // fused form: one kernel per iteration (y = A (s w) with both dot products in its epilogue), the normalised iterate is never stored
+      const PetscInt n = A->m;
+      double        *w = nullptr, *y = nullptr;
+      PB_CHK(dmalloc(&w, (size_t)std::max<PetscInt>(n, 1)));
+      PB_CHK(dmalloc(&y, (size_t)std::max<PetscInt>(n, 1)));
+      PB_CHK(k_set(n, w, 1.0));                                           /* :477 */
+      double   sc = 1.0;
+      Reducer &R = reducer(A->comm);
+      int      ierr = 0;
+      for (PetscInt i = 1; i <= maxits && !ierr; i++) {                   /* :484 */
+        lambda0 = lambda;
+        ierr = k_power_step(A->Ad, w, sc, y, R.rb);                       /* :487-491 */
+        if (!ierr) ierr = R.fetch();
+        if (ierr) break;
+        vAv    = R.sum(0);
+        vv     = R.sum(1);
+        lambda = vAv / vv;                                                /* :492 */
+        if (lambda < PETSC_MACHINE_EPSILON) {                             /* :493-502: A v fell into the null space */
+          std::vector<double> rnd((size_t)std::max<PetscInt>(n, 1));
+          rand48_fill(A->comm->rank, n, rnd.data());
+          cudaMemcpyAsync(y, rnd.data(), sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, ctx().stream);
+          cudaStreamSynchronize(ctx().stream);
+        }
+        err_   = fabs(lambda - lambda0);                                  /* :504 */
+        relerr = err_ / fabs(lambda);
+        if (relerr < tol) break;                                          /* :506 */
+        std::swap(w, y);                                                  /* :509 v = A v ... */
+        sc = 1.0 / sqrt(vv);                                              /* :510 ... / ||v|| (applied by the next gather) */
+      }
+      dfree(w);
+      dfree(y);
+      if (ierr) return ierr;
+      if (lambda_out) *lambda_out = lambda;
+      return 0;
+    }
+  }
   if (!v) {
     PB_CHK(MatCreateVecs(A, &v, NULL));
     PB_CHK(VecSet(v, 1.0));                                               /* :477 */
@@ -1689,11 +1809,21 @@ PetscErrorCode MatGetMaxEigenvalue(Mat A, Vec v, PetscReal *lambda_out, PetscRea
     PB_CHK(mat_mult(A, v, Av));                                           /* :487 */
     PB_CHK(vec_mdot2(v, Av, v, &vAv, &vv));                               /* :491 */
     lambda = vAv / vv;                                                    /* :492 */
+    if (lambda < PETSC_MACHINE_EPSILON) {                                 /* :493-502 */
+      double *h;
+      PB_CHK(vec_host_write(Av, &h));
+      rand48_fill(A->comm->rank, Av->n, h);
+    }
     err_   = fabs(lambda - lambda0);                                      /* :504 */
     relerr = err_ / fabs(lambda);
     if (relerr < tol) break;                                              /* :506 */
-    PB_CHK(VecCopy(Av, v));                                               /* :509 */
-    PB_CHK(VecScale(v, 1.0 / sqrt(vv)));                                  /* :510 */
+    {                                                                     /* :509-510 VecCopy + VecScale in one pass */
+      const double *dAv;
+      double       *dv;
+      PB_CHK(vec_dev_read(Av, &dAv));
+      PB_CHK(vec_dev_write(v, &dv));
+      PB_CHK(k_scale_to(v->n, dv, 1.0 / sqrt(vv), dAv));
+    }
   }
   if (lambda_out) *lambda_out = lambda;
   if (destroy_v) VecDestroy(&v);

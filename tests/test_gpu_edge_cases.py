@@ -205,3 +205,26 @@ def test_fallback_and_remaining_expansion_variants(P, prob, opt, okw):
     assert abs(r.counts["nmv"] - ro["nmv"]) <= max(8, 0.08 * ro["nmv"])
     if ro["reason"] > 0:
         assert np.linalg.norm(r.x - xr) <= 1e-4 * np.linalg.norm(xr)
+
+
+@pytest.mark.parametrize("fused", [True, False])
+def test_power_method_on_a_singular_hessian(P, fused, monkeypatch):
+    """v = 1 lies in the null space of a pure-Neumann Laplacian; the reference restarts from a PETSCRAND48 vector
+    (permonmatutils.c:493-502).  Fused one-kernel power step and the generic Mat/Vec path, both against the oracle."""
+    import scipy.sparse as sp
+    if fused:
+        monkeypatch.delenv("PERMON_B200_NOFUSEDPOWER", raising=False)
+    else:
+        monkeypatch.setenv("PERMON_B200_NOFUSEDPOWER", "1")
+    n = 5000
+    L = sp.diags([-np.ones(n - 1), 2 * np.ones(n), -np.ones(n - 1)], [-1, 0, 1]).tolil()
+    L[0, 0] = 1.0
+    L[n - 1, n - 1] = 1.0
+    L = L.tocsr()
+    L.sort_indices()
+    A = P.MatCreateAIJ(L.indptr.astype(np.int32), L.indices.astype(np.int32), L.data)
+    lam = P.MatGetMaxEigenvalue(A, tol=1e-7, maxits=300)
+    lam_ref, _ = O.max_eigenvalue(O.Operator(L.indptr, L.indices, L.data), tol=1e-7, maxits=300)
+    P.MatDestroy(A)
+    assert np.isfinite(lam) and 3.0 < lam <= 4.0
+    assert lam == pytest.approx(lam_ref, rel=1e-11)

@@ -120,3 +120,28 @@ def test_survey_known_answers():
         assert abs(r["its"] - its) <= max(2, 0.02 * its)
         assert abs(r["nmv"] - nmv) <= max(2, 0.02 * nmv)
         assert r["maxeig"] == pytest.approx(7.757, rel=2e-2) or N != 256
+
+
+def test_power_method_restarts_from_the_null_space():
+    """MatGetMaxEigenvalue (permonmatutils.c:493-502): with the start vector v = 1 in the null space of a pure-Neumann Laplacian the
+    Rayleigh quotient is 0; the reference then replaces A v by a PETSCRAND48 vector and carries on.  The estimate must be finite and close
+    to the true largest eigenvalue (the omission of that branch gave NaN)."""
+    import scipy.sparse as sp
+    n = 200
+    L = sp.diags([-np.ones(n - 1), 2 * np.ones(n), -np.ones(n - 1)], [-1, 0, 1]).tolil()
+    L[0, 0] = 1.0
+    L[n - 1, n - 1] = 1.0
+    L = L.tocsr()
+    L.sort_indices()
+    lam, its = O.max_eigenvalue(O.Operator(L.indptr, L.indices, L.data), tol=1e-6, maxits=2000)
+    assert np.isfinite(lam) and its > 1
+    assert abs(lam - np.linalg.eigvalsh(L.toarray()).max()) <= 2e-3 * lam
+    # the restart vector is glibc's drand48 sequence seeded with PetscRandomCreate's 0x12345678 (rank 0)
+    lam1, _ = O.max_eigenvalue(O.Operator(L.indptr, L.indices, L.data), tol=1e-30, maxits=2)
+    X = (0x12345678 << 16) | 0x330E
+    r = np.empty(n)
+    for k in range(n):
+        X = (0x5DEECE66D * X + 0xB) & 0xFFFFFFFFFFFF
+        r[k] = X / 2.0 ** 48
+    v = r / np.sqrt(float(n))                      # v = Av / ||v_old||, v_old = 1
+    assert lam1 == pytest.approx(float(v @ (L @ v)) / float(v @ v), rel=1e-13)
