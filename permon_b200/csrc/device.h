@@ -245,6 +245,7 @@ struct TileOrder {
 int k_set(int n, double *x, double a);
 int k_copy(int n, const double *x, double *y);
 int k_scale(int n, double *x, double a);
+int k_filter(int n, double *x, double tol);                            // x_i = 0 where |x_i| < tol (VecFilter)
 int k_scale_to(int n, double *y, double a, const double *x);           // y = a x
 int k_axpy(int n, double *y, double a, const double *x);
 int k_aypx(int n, double *y, double a, const double *x);

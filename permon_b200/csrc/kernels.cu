@@ -2484,6 +2484,10 @@ int k_scale(int n, double *x, double a)
 {
   return launch_ew(n, [=] __device__(int i) { x[i] *= a; }, KF_VEC, 16.0 * n);
 }
+int k_filter(int n, double *x, double tol)
+{   // PETSc VecFilter: entries with |x_i| < tol become 0
+  return launch_ew(n, [=] __device__(int i) { const double v = x[i]; if (fabs(v) < tol) x[i] = 0.0; }, KF_VEC, 16.0 * n);
+}
 int k_scale_to(int n, double *y, double a, const double *x)
 {   // y = a x : VecCopy + VecScale in one pass (same products, same rounding)
   return launch_ew(n, [=] __device__(int i) { y[i] = x[i] * a; }, KF_VEC, 16.0 * n);

@@ -610,7 +610,16 @@ PetscErrorCode MpgpImpl::setup(QPS qps)
     PhaseTimer pt("MPGP set-up: work vectors");
     PB_CHK(set_work(qps, nw));
   }
-  if (bchop_tol) return err(PETSC_ERR_SUP, "-qps_mpgp_bound_chop_tol is not supported");
+  if (bchop_tol) {   // mpgp.c:379-382: VecFilter(lb / ub, bchop_tol) -- bounds closer to 0 than the tolerance become 0 (in the user's Vecs)
+    QPC qpc = qps->solQP->qpc;
+    for (Vec bnd : {qpc ? qpc->lb : (Vec) nullptr, qpc ? qpc->ub : (Vec) nullptr}) {
+      if (!bnd) continue;
+      double *d;
+      PB_CHK(vec_dev_rw(bnd, &d));
+      PB_CHK(k_filter(bnd->n, d, bchop_tol));
+    }
+    if (qpc) qpc->setupcalled = false;   // expanded (IS) copies of the bounds are rebuilt from the filtered vectors
+  }
   expproject = true;   // QPSCreate_MPGP :839 (re-evaluated at every set-up here)
   switch (exptype) {
   case QPS_MPGP_EXPANSION_STD:

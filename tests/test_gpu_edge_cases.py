@@ -228,3 +228,20 @@ def test_power_method_on_a_singular_hessian(P, fused, monkeypatch):
     P.MatDestroy(A)
     assert np.isfinite(lam) and 3.0 < lam <= 4.0
     assert lam == pytest.approx(lam_ref, rel=1e-11)
+
+
+def test_bound_chop_tol(P):
+    """-qps_mpgp_bound_chop_tol (mpgp.c:379-382): VecFilter zeroes the bound entries that are closer to 0 than the tolerance, in the user's
+    vectors, before the solve.  Oracle: the same filter applied to the bounds up front."""
+    pr = PR.obstacle2d(48, -100.0)
+    rng = np.random.default_rng(5)
+    pr.lb = np.where(rng.random(pr.n) < 0.5, -1e-4 * rng.random(pr.n), -0.02 - 0.01 * rng.random(pr.n))   # half of the bounds within 1e-3 of zero
+    tol = 1e-3
+    r = P.solve_problem(pr, "mpgp", f"-qps_rtol 1e-8 -qps_mpgp_bound_chop_tol {tol}")
+    lbf = np.where(np.abs(pr.lb) < tol, 0.0, pr.lb)
+    assert np.count_nonzero(lbf == 0.0) > pr.n // 3
+    xr, ro = O.mpgp_solve(O.Operator(pr.ia, pr.ja, pr.a), pr.b, O.BoxC(pr.n, lbf, None), pr.x0, O.mpgp_opts(rtol=1e-8))
+    assert r.reason == ro["reason"] == 2
+    assert abs(r.its - ro["its"]) <= max(2, 0.02 * ro["its"])
+    assert np.linalg.norm(r.x - xr) <= 1e-7 * np.linalg.norm(xr)
+    assert np.all(r.x >= lbf - 1e-12)
