@@ -132,6 +132,11 @@ struct StencilHost {   // host side of the all-stencil form, filled by pk_build
   int                        nwin = 0;
 };
 
+struct OffDiagEntries {   // ghost-column entries of a row block, in row order (storage order within a row)
+  std::vector<int>    row, gcol;
+  std::vector<double> val;
+};
+
 struct CsrDev {
   int           n      = 0;        // rows
   int           ncols  = 0;

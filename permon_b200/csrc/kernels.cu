@@ -26,6 +26,7 @@
 #include <string.h>
 #include <time.h>
 
+#include <algorithm>
 #include <string>
 #include <type_traits>
 #include <utility>
@@ -227,12 +228,27 @@ int prof_end()
     g_prof_n[f]++;
     if (ms[i] > mx[f]) mx[f] = ms[i];
   }
-  // "working" launches: a device-driven kernel that has nothing to do (K_A' outside expansion steps, anything enqueued behind
-  // the stopping iteration) exits within a few microseconds; launches above a quarter of the family's longest one did the work
-  for (size_t i = 0; i < g_prof_used; i++) {
-    const int f = g_prof[i].fam;
-    if (ms[i] > 0.25f * mx[f]) {
-      g_prof_work_ms[f] += ms[i];
+  // "working" launches: a device-driven kernel that has nothing to do (K_A' outside expansion steps, anything enqueued behind the
+  // stopping iteration) exits within a few microseconds.  Per family: when the 95th percentile of the durations is more than 8x the
+  // shortest launch the family has early exits, and everything above the geometric mean of the two did the work; otherwise every launch
+  // did.  A rare launch that takes several times the median of the working ones (host hiccup between the two events) is left out of
+  // the working time but still counted in the total.
+  for (int f = 0; f < KF_COUNT; f++) {
+    std::vector<float> d;
+    for (size_t i = 0; i < g_prof_used; i++)
+      if (g_prof[i].fam == f) d.push_back(ms[i]);
+    if (d.empty()) continue;
+    std::sort(d.begin(), d.end());
+    const float lo = d.front(), p95 = d[(size_t)(0.95 * (d.size() - 1))];
+    const float thr = (p95 > 8.f * lo) ? sqrtf(fmaxf(lo, 1e-4f) * p95) : 0.f;
+    std::vector<float> w;
+    for (float v : d)
+      if (v > thr) w.push_back(v);
+    if (w.empty()) continue;
+    const float med = w[w.size() / 2];
+    for (float v : w) {
+      if (v > 4.f * med) continue;
+      g_prof_work_ms[f] += v;
       g_prof_work_n[f]++;
     }
   }
@@ -1314,6 +1330,92 @@ __global__ void __launch_bounds__(PK_CT + 32, 4) k_spmv_st(CsrDev A, const doubl
   epi.finalize(acc);
 }
 
+
+// ---- all-stencil matrices, direct form: no staging at all.  With a uniform pattern the gather x[r + d] of the 32 rows of a warp is ONE
+// coalesced 256-byte load per pattern entry (served by L1 / L2 for the shifted copies), the presence byte only predicates it, and the
+// epilogue operands are plain coalesced loads: the kernel has the memory behaviour of the streaming kernels K_B / K_C (one round of
+// independent loads per row, thousands of threads in flight) instead of a producer / consumer ring.
+template <int L, class G>
+__device__ __forceinline__ double sd_row_fixed(uint32_t m, const StPattern &P, const G &gx, int r)
+{
+  constexpr uint32_t FULL = (1u << L) - 1u;
+  double             xv[L];
+  const double      *xr = gx.x + r;
+  if (__all_sync(0xffffffffu, m == FULL)) {
+#pragma unroll
+    for (int j = 0; j < L; j++) xv[j] = gx.ld(xr + P.d[j]);
+    double s = 0.0;
+#pragma unroll
+    for (int j = 0; j < L; j++) s += P.v[j] * xv[j];
+    return s;
+  }
+#pragma unroll
+  for (int j = 0; j < L; j++) xv[j] = ((m >> j) & 1u) ? gx.ld(xr + P.d[j]) : 0.0;
+  double s = 0.0;
+#pragma unroll
+  for (int j = 0; j < L; j++)
+    if ((m >> j) & 1u) s += P.v[j] * xv[j];
+  return s;
+}
+template <class G>
+__device__ __forceinline__ double sd_row_dispatch(int L, uint32_t m, const StPattern &P, const G &gx, int r)
+{
+  switch (L) {
+  case 1: return sd_row_fixed<1>(m, P, gx, r);
+  case 2: return sd_row_fixed<2>(m, P, gx, r);
+  case 3: return sd_row_fixed<3>(m, P, gx, r);
+  case 4: return sd_row_fixed<4>(m, P, gx, r);
+  case 5: return sd_row_fixed<5>(m, P, gx, r);
+  case 6: return sd_row_fixed<6>(m, P, gx, r);
+  case 7: return sd_row_fixed<7>(m, P, gx, r);
+  default: return sd_row_fixed<8>(m, P, gx, r);
+  }
+}
+
+template <class Epi, int MINB>
+__global__ void __launch_bounds__(NT, MINB) k_spmv_sd(CsrDev A, const double *__restrict__ x, Epi epi, TileOrder ord)
+{
+  pdl_enter();
+  if (!epi.active()) return;
+  __shared__ StPattern s_pats[PB_ST_MAXPAT];
+  {
+    const int  nw = A.st_npat * (int)(sizeof(StPattern) / 4);
+    const int *src = reinterpret_cast<const int *>(A.st_pats);
+    int       *dst = reinterpret_cast<int *>(s_pats);
+    for (int k = threadIdx.x; k < nw; k += NT) dst[k] = __ldg(src + k);
+  }
+  __syncthreads();
+  const int  ntiles = (A.n + TR - 1) / TR;
+  const bool rev = epi.reverse();
+  const typename Epi::Gather gx = epi.gather(x);
+  typename Epi::Acc acc;
+  epi.init(acc);
+  // presence byte and pattern id of the next tile are loaded one iteration ahead: the gathers of a row never wait for them
+  uint32_t m_next = 0;
+  int      pid_next = 0;
+  if ((int)blockIdx.x < ntiles) {
+    const int t0 = tile_at(blockIdx.x, ord.ta, ord.tb, rev);
+    pid_next = __ldg(A.st_pid + t0);
+    m_next   = __ldg(A.st_masks + (size_t)t0 * TR + threadIdx.x);   // the mask array is padded to whole tiles
+  }
+  for (int i = blockIdx.x; i < ntiles; i += gridDim.x) {
+    const int      tile = tile_at(i, ord.ta, ord.tb, rev);
+    const uint32_t m = m_next;
+    const int      pid = pid_next;
+    const int      ni = i + gridDim.x;
+    if (ni < ntiles) {
+      const int tn = tile_at(ni, ord.ta, ord.tb, rev);
+      pid_next = __ldg(A.st_pid + tn);
+      m_next   = __ldg(A.st_masks + (size_t)tn * TR + threadIdx.x);
+    }
+    const StPattern &P = s_pats[pid];
+    const int        r = tile * TR + threadIdx.x;
+    const double     sum = sd_row_dispatch(P.L, m, P, gx, r);   // rows beyond the end carry an empty mask: nothing is loaded
+    if (r < A.n) epi.row(r, sum, acc);
+  }
+  epi.finalize(acc);
+}
+
 template <class K>
 static int occ_blocks(K kernel, size_t smem)
 {
@@ -1491,6 +1593,34 @@ static int launch_st(const CsrDev &A, const double *x, const Epi &epi, TileOrder
   }
 }
 
+
+template <class Epi>
+static int launch_sd(const CsrDev &A, const double *x, const Epi &epi, TileOrder ord)
+{
+  static int minb = 0;
+  if (!minb) {
+    const char *e = getenv("PERMON_B200_SD_OCC");
+    minb = e ? atoi(e) : 5;
+    if (minb != 4 && minb != 6) minb = 5;
+  }
+  auto kern = (minb == 4) ? k_spmv_sd<Epi, 4> : (minb == 6 ? k_spmv_sd<Epi, 6> : k_spmv_sd<Epi, 5>);
+  static int occ = 0;
+  if (!occ) {
+    int nb = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, NT, 0) != cudaSuccess || nb < 1) nb = 1;
+    occ = nb;
+  }
+  int ntiles = (A.n + TR - 1) / TR, grid = g_ctx.sm_count * occ;
+  if (grid > ntiles) grid = ntiles;
+  if (grid > max_red_blocks()) grid = max_red_blocks();
+  if (ord.tb <= ord.ta || ord.tb > ntiles) {
+    ord.ta = 0;
+    ord.tb = ntiles;
+  }
+  launch_k(kern, grid, NT, 0, A, x, epi, ord);
+  return 0;
+}
+
 template <class Epi>
 static int launch_spmv(const CsrDev &A, const double *x, const Epi &epi, int family, double bytes, TileOrder ord = TileOrder())
 {
@@ -1499,7 +1629,13 @@ static int launch_spmv(const CsrDev &A, const double *x, const Epi &epi, int fam
     // still run one CTA so that reductions publish their (identity) record
     k_spmv_vector<Epi, 32><<<1, NT, 0, g_ctx.stream>>>(A, x, epi);
   } else if (A.kind == 4) {
-    PB_CHK(launch_st(A, x, epi, ord));
+    static int direct = -1;
+    if (direct < 0) {
+      const char *e = getenv("PERMON_B200_ST_KERNEL");   // "direct" (default) | "windows"
+      direct = (e && !strcmp(e, "windows")) ? 0 : 1;
+    }
+    if (direct) PB_CHK(launch_sd(A, x, epi, ord));
+    else PB_CHK(launch_st(A, x, epi, ord));
   } else if (A.kind == 3) {
     PB_CHK(launch_pk(A, x, epi, ord));
   } else if (A.kind == 2) {
@@ -1671,12 +1807,21 @@ struct EpiAT {
   {
     ax    = ghost_apply(gm, r, ax, a.halo_ok);
     Ap[r] = ax;
-    const double pr = p[r];
+    const double pr = __ldg(p + r);
     a.v[RA_PAP] += pr * ax;
+    if constexpr (MODE != 0) {
+      BoxVal b;
+      b.has_lb = true;
+      b.has_ub = (MODE == 2);
+      b.lb     = __ldg(bx.lb + r);
+      b.ub     = (MODE == 2) ? __ldg(bx.ub + r) : 0.0;
+      a.v[RA_FEAS] = box_feas_lazy(__ldg(x + r), pr, b, a.v[RA_FEAS]);
+    } else {
 #pragma unroll
-    for (int j = 0; j < PB_MAXEQ; j++)
-      if (j < m) a.v[RA_BP + j] += B[(size_t)j * n + r] * pr;
-    a.v[RA_FEAS] = box_feas_lazy(x[r], pr, load_box(bx, r), a.v[RA_FEAS]);
+      for (int j = 0; j < PB_MAXEQ; j++)
+        if (j < m) a.v[RA_BP + j] += B[(size_t)j * n + r] * pr;
+      a.v[RA_FEAS] = box_feas_lazy(x[r], pr, load_box(bx, r), a.v[RA_FEAS]);
+    }
   }
   __device__ void finalize(Acc &a) const { grid_reduce8<(1 << RA_FEAS)>(a.v, rb, nullptr); }
   // staged row vectors for the TMA kernels: p, x, [lb], [ub], [B_0..B_{m-1}]
@@ -1754,14 +1899,23 @@ struct EpiA2T {
   __device__ void row(int r, double ax, Acc &a) const
   {
     double gr = ghost_apply(gm, r, ax, a.halo_ok);
-    if (m > 0) {
-      double t = 0.0;
-      for (int j = 0; j < m; j++) t += B[(size_t)j * n + r] * S->Bu[j];
-      gr += S->rho * t;
+    BoxVal bv;
+    if constexpr (MODE != 0) {
+      bv.has_lb = true;
+      bv.has_ub = (MODE == 2);
+      bv.lb     = __ldg(bx.lb + r);
+      bv.ub     = (MODE == 2) ? __ldg(bx.ub + r) : 0.0;
+    } else {
+      bv = load_box(bx, r);
+      if (m > 0) {
+        double t = 0.0;
+        for (int j = 0; j < m; j++) t += B[(size_t)j * n + r] * S->Bu[j];
+        gr += S->rho * t;
+      }
     }
-    gr -= b[r];
+    gr -= __ldg(b + r);
     double gf, gc;
-    box_split(x[r], gr, load_box(bx, r), bx.astol, gf, gc);
+    box_split(x[r], gr, bv, bx.astol, gf, gc);
     g[r] = gr;
     p[r] = gf;
     const double gP = gf + gc;

@@ -113,6 +113,13 @@ struct HaloPlan {
     std::vector<double>        oa;
     UVec<double>               da;
     std::vector<unsigned char> skip;
+    // fast path (constant-coefficient stencils): the all-stencil form of the diagonal block, built straight from the caller's arrays;
+    // dia / dja / da stay empty unless MatB200GetHostSplit asks for them while those arrays are still alive
+    pb::StencilHost    st;
+    int64_t            nnz_diag = 0;
+    const PetscInt    *ui = nullptr, *uj = nullptr;
+    const PetscScalar *ua = nullptr;
+    PetscInt           c0 = 0;
   } *host = nullptr;
 };
 

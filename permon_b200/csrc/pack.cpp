@@ -47,6 +47,23 @@ size_t pk_raw_bytes(int nrows, int nnz)
 }
 
 namespace {
+// windows of a pattern: consecutive deltas within PB_ST_SPAN of the window's first delta share one; returns the last window index
+int pattern_windows(StPattern &P)
+{
+  int w = -1, first = 0;
+  for (int j = 0; j < P.L; j++) {
+    if (w < 0 || P.d[j] - first > PB_ST_SPAN) {
+      w++;
+      first    = P.d[j];
+      P.wlo[w] = (first & 1) ? first - 1 : first;   // even: 16-byte aligned copies (floor for negative odd values too)
+    }
+    int hi = P.d[j] + TR;
+    if (hi & 1) hi++;
+    P.wlen[w] = hi - P.wlo[w];
+    P.erel[j] = w * PB_ST_WCAP + (P.d[j] - P.wlo[w]) * 8;
+  }
+  return w;
+}
 struct TileDict {
   // open addressing over (delta, value bits); 1024 slots for at most 256 entries
   static constexpr int SLOTS = 1024;
@@ -274,19 +291,7 @@ int pk_build(int n, const int *ia, const int *ja, const double *a, RawBuf &blob,
           P.L = L;
           memcpy(P.d, pd, sizeof(int) * L);
           memcpy(P.v, pb, sizeof(double) * L);
-          // windows: consecutive deltas within PB_ST_SPAN of the window's first delta share it
-          int w = -1, first = 0;
-          for (int j = 0; j < L; j++) {
-            if (w < 0 || P.d[j] - first > PB_ST_SPAN) {
-              w++;
-              first    = P.d[j];
-              P.wlo[w] = (first & 1) ? first - 1 : first;   // even: 16-byte aligned copies (floor for negative odd values too)
-            }
-            int hi = P.d[j] + TR;
-            if (hi & 1) hi++;
-            P.wlen[w] = hi - P.wlo[w];
-            P.erel[j] = w * PB_ST_WCAP + (P.d[j] - P.wlo[w]) * 8;
-          }
+          int w = pattern_windows(P);
           P.nwin = w + 1;
           id     = (int)st->pats.size();
           st->pats.push_back(P);
@@ -385,6 +390,143 @@ int pk_build(int n, const int *ia, const int *ja, const double *a, RawBuf &blob,
   free(codes_tmp);
   ncoded = coded;
   packed = true;
+  return 0;
+}
+
+// All-stencil form of the DIAGONAL BLOCK of a row-partitioned matrix, straight from the caller's CSR with GLOBAL column indices: an
+// entry belongs to the block when coff <= col < coff + ncols (its local column is col - coff), every other entry is a ghost entry and
+// is appended to `off` (row, global column, value; storage order kept per row).  One pass over the arrays -- no intermediate copy of the
+// diagonal block is made.  Returns with st.valid == false when some tile is not a stencil tile or there are too many patterns (the
+// caller then splits the matrix the general way).  nnz_diag: entries of the block.
+int pk_stencil_windowed(int n, const int *ia, const int *ja, const double *a, int coff, int ncols, StencilHost &st, OffDiagEntries &off, int64_t &nnz_diag)
+{
+  const int ntiles = (n + TR - 1) / TR;
+  st.valid  = false;
+  nnz_diag  = 0;
+  off.row.clear();
+  off.gcol.clear();
+  off.val.clear();
+  if (ntiles == 0) return 0;
+  if (!st.masks.alloc((size_t)ntiles * TR)) return 55;
+  std::vector<StPattern> tpat((size_t)ntiles);
+  const int nthr = omp_get_max_threads();
+  std::vector<OffDiagEntries> toff((size_t)nthr);
+  bool    ok = true;
+  int64_t nd = 0;
+#pragma omp parallel reduction(&& : ok) reduction(+ : nd)
+  {
+    OffDiagEntries &mine = toff[(size_t)omp_get_thread_num()];
+#pragma omp for schedule(static)
+    for (int t = 0; t < ntiles; t++) {
+      if (!ok) continue;
+      const int r0 = t * TR, r1 = std::min(r0 + TR, n);
+      int       L = 0, pd[8];
+      uint64_t  pb[8];
+      bool      st_ok = true;
+      unsigned char *mk = st.masks.data() + (size_t)t * TR;
+      for (int r = r0; r < r1 && st_ok; r++) {
+        int  j = 0, prev_d = 0;
+        bool first = true;
+        for (int k = ia[r]; k < ia[r + 1]; k++) {
+          const int c = ja[k] - coff;
+          if (c < 0 || c >= ncols) {   // ghost column
+            mine.row.push_back(r);
+            mine.gcol.push_back(ja[k]);
+            mine.val.push_back(a[k]);
+            continue;
+          }
+          uint64_t b;
+          memcpy(&b, &a[k], 8);
+          const int d = c - r;
+          if (!first && d <= prev_d) {
+            st_ok = false;
+            break;
+          }
+          first  = false;
+          prev_d = d;
+          while (j < L && pd[j] < d) j++;
+          if (j < L && pd[j] == d) {
+            if (pb[j] != b) {
+              st_ok = false;
+              break;
+            }
+          } else {
+            if (L == 8) {
+              st_ok = false;
+              break;
+            }
+            for (int q = L; q > j; q--) {
+              pd[q] = pd[q - 1];
+              pb[q] = pb[q - 1];
+            }
+            pd[j] = d;
+            pb[j] = b;
+            L++;
+          }
+          j++;
+          nd++;
+        }
+      }
+      if (!st_ok || L == 0) {
+        ok = false;
+        continue;
+      }
+      for (int r = r0; r < r1; r++) {   // presence bytes against the final pattern of the tile
+        int      j = 0;
+        unsigned m = 0;
+        for (int k = ia[r]; k < ia[r + 1]; k++) {
+          const int c = ja[k] - coff;
+          if (c < 0 || c >= ncols) continue;
+          const int d = c - r;
+          while (pd[j] != d) j++;
+          m |= 1u << j;
+          j++;
+        }
+        mk[r - r0] = (unsigned char)m;
+      }
+      for (int r = r1; r < r0 + TR; r++) mk[r - r0] = 0;
+      StPattern &P = tpat[(size_t)t];
+      memset(&P, 0, sizeof P);
+      P.L = L;
+      memcpy(P.d, pd, sizeof(int) * L);
+      memcpy(P.v, pb, sizeof(double) * L);
+    }
+  }
+  if (!ok) return 0;
+  // dedupe the tiles' patterns
+  st.pats.clear();
+  st.pid.assign((size_t)ntiles, 0);
+  for (int t = 0; t < ntiles; t++) {
+    const StPattern &T = tpat[(size_t)t];
+    int              id = -1;
+    const int        prev = t > 0 ? st.pid[(size_t)t - 1] : 0;
+    if (!st.pats.empty()) {
+      const StPattern &Q = st.pats[(size_t)prev];
+      if (Q.L == T.L && !memcmp(Q.d, T.d, sizeof(int) * T.L) && !memcmp(Q.v, T.v, sizeof(double) * T.L)) id = prev;
+    }
+    for (int c = 0; c < (int)st.pats.size() && id < 0; c++) {
+      const StPattern &Q = st.pats[(size_t)c];
+      if (Q.L == T.L && !memcmp(Q.d, T.d, sizeof(int) * T.L) && !memcmp(Q.v, T.v, sizeof(double) * T.L)) id = c;
+    }
+    if (id < 0) {
+      if ((int)st.pats.size() == PB_ST_MAXPAT) return 0;
+      StPattern P = T;
+      P.nwin = pattern_windows(P) + 1;
+      id     = (int)st.pats.size();
+      st.pats.push_back(P);
+    }
+    st.pid[(size_t)t] = (unsigned char)id;
+  }
+  st.nwin = 0;
+  for (const StPattern &P : st.pats) st.nwin = std::max(st.nwin, P.nwin);
+  // ghost entries: static schedule => thread k owns a contiguous, ascending range of tiles: concatenation is already sorted by row
+  for (const OffDiagEntries &e : toff) {
+    off.row.insert(off.row.end(), e.row.begin(), e.row.end());
+    off.gcol.insert(off.gcol.end(), e.gcol.begin(), e.gcol.end());
+    off.val.insert(off.val.end(), e.val.begin(), e.val.end());
+  }
+  nnz_diag = nd;
+  st.valid = true;
   return 0;
 }
 

@@ -972,6 +972,7 @@ _p_Mat::~_p_Mat()
 namespace pb {
 int pk_build(int n, const int *ia, const int *ja, const double *a, RawBuf &blob, std::vector<unsigned> &h_off, int &max_tile_bytes,
              int64_t &ncoded, bool &packed, StencilHost *st, bool want_blob);
+int pk_stencil_windowed(int n, const int *ia, const int *ja, const double *a, int coff, int ncols, StencilHost &st, OffDiagEntries &off, int64_t &nnz_diag);
 }
 
 static double wall_now()
@@ -981,6 +982,36 @@ static double wall_now()
   return ts.tv_sec + 1e-9 * ts.tv_nsec;
 }
 static bool verbose_timing() { return getenv("PERMON_B200_VERBOSE") != nullptr; }
+
+// all-stencil form (device.h): presence bytes + pattern ids + pattern table
+static int upload_stencil(pb::CsrDev &C, pb::StencilHost &st, int64_t nnz, double t_build)
+{
+  cudaStream_t   s = ctx().stream;
+  const double   t0 = wall_now();
+  unsigned char *dm, *dp;
+  pb::StPattern *dt;
+  PB_CHK(dmalloc(&dm, st.masks.size()));
+  PB_CHK(dmalloc(&dp, st.pid.size()));
+  PB_CHK(dmalloc(&dt, st.pats.size()));
+  PB_CUDA(cudaMemcpyAsync(dm, st.masks.data(), st.masks.size(), cudaMemcpyHostToDevice, s));
+  PB_CUDA(cudaMemcpyAsync(dp, st.pid.data(), st.pid.size(), cudaMemcpyHostToDevice, s));
+  PB_CUDA(cudaMemcpyAsync(dt, st.pats.data(), sizeof(pb::StPattern) * st.pats.size(), cudaMemcpyHostToDevice, s));
+  PB_CUDA(cudaStreamSynchronize(s));   // st may be a local
+  if (verbose_timing())
+    fprintf(stderr, "[permon_b200] matrix %d rows, %lld nnz: all-stencil form (%d patterns, %d windows) built in %.1f ms, %.1f MB uploaded in %.1f ms\n", C.n,
+            (long long)nnz, (int)st.pats.size(), st.nwin, 1e3 * t_build, (st.masks.size() + st.pid.size()) / 1e6, 1e3 * (wall_now() - t0));
+  C.st_masks = dm;
+  C.st_pid   = dp;
+  C.st_pats  = dt;
+  C.st_npat  = (int)st.pats.size();
+  C.st_nwin  = st.nwin;
+  C.pk_bytes = (int64_t)st.masks.size() + (int64_t)st.pid.size() + (int64_t)(sizeof(pb::StPattern) * st.pats.size());
+  C.pk_coded = (int64_t)st.pid.size();
+  C.kind     = 4;
+  const char *stg = getenv("PERMON_B200_STAGES");
+  C.stages = stg ? atoi(stg) : 0;   // 0: as many as fit
+  return 0;
+}
 
 static int upload_csr(pb::CsrDev &C, int nrows, int ncols, const int *ia, const int *ja, const double *a, const int *rows)
 {
@@ -1011,29 +1042,8 @@ static int upload_csr(pb::CsrDev &C, int nrows, int ncols, const int *ia, const 
     PB_CHK(pb::pk_build(nrows, ia, ja, a, blob, off, max_tile, ncoded, packed, want_st ? &st : nullptr, false));
     const double t_pk1 = wall_now();
     if (packed && st.valid) {
-      // all-stencil form: presence bytes + pattern ids + pattern table
-      unsigned char *dm, *dp;
-      pb::StPattern *dt;
-      PB_CHK(dmalloc(&dm, st.masks.size()));
-      PB_CHK(dmalloc(&dp, st.pid.size()));
-      PB_CHK(dmalloc(&dt, st.pats.size()));
-      PB_CUDA(cudaMemcpyAsync(dm, st.masks.data(), st.masks.size(), cudaMemcpyHostToDevice, s));
-      PB_CUDA(cudaMemcpyAsync(dp, st.pid.data(), st.pid.size(), cudaMemcpyHostToDevice, s));
-      PB_CUDA(cudaMemcpyAsync(dt, st.pats.data(), sizeof(pb::StPattern) * st.pats.size(), cudaMemcpyHostToDevice, s));
-      PB_CUDA(cudaStreamSynchronize(s));   // st is a local
-      if (verbose_timing())
-        fprintf(stderr, "[permon_b200] matrix %d rows, %lld nnz: all-stencil form (%d patterns, %d windows) built in %.1f ms, %.1f MB uploaded in %.1f ms\n", nrows,
-                (long long)nnz, (int)st.pats.size(), st.nwin, 1e3 * (t_pk1 - t_pk0), (st.masks.size() + st.pid.size()) / 1e6, 1e3 * (wall_now() - t_pk1));
-      C.st_masks = dm;
-      C.st_pid   = dp;
-      C.st_pats  = dt;
-      C.st_npat  = (int)st.pats.size();
-      C.st_nwin  = st.nwin;
-      C.pk_bytes = (int64_t)st.masks.size() + (int64_t)st.pid.size() + (int64_t)(sizeof(pb::StPattern) * st.pats.size());
+      PB_CHK(upload_stencil(C, st, nnz, t_pk1 - t_pk0));
       C.pk_coded = ncoded;
-      C.kind     = 4;
-      const char *stg = getenv("PERMON_B200_STAGES");
-      C.stages = stg ? atoi(stg) : 0;   // 0: as many as fit
       return 0;
     }
     if (packed) {
@@ -1169,10 +1179,49 @@ PetscErrorCode MatCreateMPIAIJWithArrays(MPI_Comm comm, PetscInt m, PetscInt n, 
   HaloPlan::UVec<int>    &dja = H->host->dja;
   HaloPlan::UVec<double> &da = H->host->da;
   std::vector<unsigned char> &skip = H->host->skip;
+  std::vector<PetscInt>       gh;
+  double t_s1 = t_s0;
+  // Fast path: the diagonal block of a constant-coefficient stencil goes straight from the caller's arrays (global columns) into the
+  // all-stencil form -- one pass, no intermediate copy of the block; the ghost entries fall out of the same pass.
+  bool fast = false;
+  {
+    const char *e1 = getenv("PERMON_B200_ST_WINDOWS"), *e2 = getenv("PERMON_B200_PACK_STENCIL");
+    if (m == n && m >= 64 && !getenv("PERMON_B200_EAGER_SPLIT") && !getenv("PERMON_B200_SPMV") && !(e1 && e1[0] == '0') && !(e2 && e2[0] == '0')) {
+      pb::OffDiagEntries off;
+      int64_t            nd = 0;
+      PB_CHK(pb::pk_stencil_windowed((int)m, i, j, a, (int)c0, (int)n, H->host->st, off, nd));
+      if (H->host->st.valid) {
+        fast = true;
+        t_s1 = wall_now();
+        H->host->nnz_diag = nd;
+        H->host->ui = i;
+        H->host->uj = j;
+        H->host->ua = a;
+        H->host->c0 = c0;
+        skip.assign(std::max<PetscInt>(m, 1), 0);
+        gh.assign(off.gcol.begin(), off.gcol.end());
+        std::sort(gh.begin(), gh.end());
+        gh.erase(std::unique(gh.begin(), gh.end()), gh.end());
+        H->garray = gh;
+        oja.resize(off.row.size());
+        oa.assign(off.val.begin(), off.val.end());
+        oia.assign(1, 0);
+        for (size_t k = 0; k < off.row.size(); k++) {
+          if (orow.empty() || orow.back() != off.row[k]) {
+            if (!orow.empty()) oia.push_back((int)k);
+            orow.push_back(off.row[k]);
+            skip[off.row[k]] = 1;
+          }
+          oja[k] = (int)(std::lower_bound(gh.begin(), gh.end(), (PetscInt)off.gcol[k]) - gh.begin());
+        }
+        if (!orow.empty()) oia.push_back((int)off.row.size());
+      }
+    }
+  }
+  if (!fast) {
   dia.assign(m + 1, 0);
   skip.assign(std::max<PetscInt>(m, 1), 0);
   std::vector<int>      ocnt(m + 1, 0);
-  std::vector<PetscInt> gh;
   {
     std::vector<std::vector<PetscInt>> part;
 #pragma omp parallel
@@ -1203,7 +1252,7 @@ PetscErrorCode MatCreateMPIAIJWithArrays(MPI_Comm comm, PetscInt m, PetscInt n, 
   std::sort(gh.begin(), gh.end());
   gh.erase(std::unique(gh.begin(), gh.end()), gh.end());
   H->garray = gh;
-  const double t_s1 = wall_now();
+  t_s1 = wall_now();
   // prefix sums, then pass 2 fills both blocks
   for (PetscInt r = 0; r < m; r++) {
     dia[r + 1] += dia[r];
@@ -1229,6 +1278,7 @@ PetscErrorCode MatCreateMPIAIJWithArrays(MPI_Comm comm, PetscInt m, PetscInt n, 
         oa[po++] = a[k];
       }
     }
+  }
   }
   H->nboundary = (PetscInt)orow.size();
   const double t_s2 = wall_now();
@@ -1290,7 +1340,7 @@ PetscErrorCode MatCreateMPIAIJWithArrays(MPI_Comm comm, PetscInt m, PetscInt n, 
             (long long)nnz, 1e3 * (t_s1 - t_s0), 1e3 * (t_s2 - t_s1), 1e3 * (wall_now() - t_s2));
   A->Ad.n = m;   // sizes are known; the arrays reach the device on first use (mat_ensure_device)
   A->Ad.ncols = n;
-  A->Ad.nnz = (int64_t)dja.size();
+  A->Ad.nnz = fast ? H->host->nnz_diag : (int64_t)dja.size();
   *mat = A;
   return 0;
 }
@@ -1423,7 +1473,14 @@ int mat_ensure_device(Mat A)
   PB_CHK(dev_init());
   PhaseTimer pt("mat_ensure_device (pack + upload + halo set-up)");
   const PetscInt m = A->m;
-  PB_CHK(upload_csr(A->Ad, m, A->n, S->dia.data(), S->dja.data(), S->da.data(), nullptr));
+  if (S->st.valid) {
+    A->Ad.n     = m;
+    A->Ad.ncols = A->n;
+    A->Ad.nnz   = S->nnz_diag;
+    PB_CHK(upload_stencil(A->Ad, S->st, S->nnz_diag, 0.0));
+  } else {
+    PB_CHK(upload_csr(A->Ad, m, A->n, S->dia.data(), S->dja.data(), S->da.data(), nullptr));
+  }
   PB_CHK(upload_csr(A->Ao, (int)S->orow.size(), (int)H->garray.size(), S->oia.data(), S->oja.data(), S->oa.data(), S->orow.data()));
   PB_CHK(dmalloc(&H->d_send_idx, std::max<size_t>(H->send_idx.size(), 1)));
   PB_CHK(dmalloc(&H->d_send, std::max<size_t>(H->send_idx.size(), 1)));
@@ -1469,6 +1526,25 @@ PetscErrorCode MatB200GetHostSplit(Mat A, const PetscInt **dia, const PetscInt *
 {
   if (!A || A->kind != MK_AIJ || !A->halo || !A->halo->host) return err(PETSC_ERR_ARG_WRONGSTATE, "no host split (sequential matrix, or already on the device)");
   HaloPlan::HostSplit *S = A->halo->host;
+  if (S->st.valid && S->dia.empty()) {
+    // fast path: the diagonal-block copy was never made; rebuild it from the arrays the matrix was created from (this accessor is a
+    // test hook: it must be called while those arrays are still alive)
+    const PetscInt m = A->m, c0 = S->c0, c1 = S->c0 + A->n;
+    S->dia.assign((size_t)m + 1, 0);
+    for (PetscInt r = 0; r < m; r++) {
+      int nd = 0;
+      for (PetscInt k = S->ui[r]; k < S->ui[r + 1]; k++) nd += (S->uj[k] >= c0 && S->uj[k] < c1);
+      S->dia[(size_t)r + 1] = S->dia[(size_t)r] + nd;
+    }
+    S->dja.resize((size_t)S->dia[(size_t)m]);
+    S->da.resize((size_t)S->dia[(size_t)m]);
+    for (PetscInt r = 0, p = 0; r < m; r++)
+      for (PetscInt k = S->ui[r]; k < S->ui[r + 1]; k++)
+        if (S->uj[k] >= c0 && S->uj[k] < c1) {
+          S->dja[(size_t)p] = S->uj[k] - c0;
+          S->da[(size_t)p++] = S->ua[k];
+        }
+  }
   if (dia) *dia = S->dia.data();
   if (dja) *dja = S->dja.data();
   if (da) *da = S->da.data();
