@@ -159,7 +159,7 @@ struct CsrDev {
   const unsigned char *st_masks = nullptr;   // [n] presence byte per row
   const unsigned char *st_pid = nullptr;     // [ntiles] pattern of each tile
   const StPattern     *st_pats = nullptr;
-  int                  st_npat = 0, st_nwin = 0;   // patterns; largest number of windows of a pattern
+  int                  st_npat = 0, st_nwin = 0, st_lmax = 0;   // patterns; largest number of windows of a pattern; longest pattern
   int           W      = 32;
   int           tile_cap = 0;      // max nnz of a 256-row tile (stream kind)
   int           grid   = 0;        // persistent grid size (fixed => reproducible reductions)

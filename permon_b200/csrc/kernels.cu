@@ -1333,46 +1333,36 @@ __global__ void __launch_bounds__(PK_CT + 32, 4) k_spmv_st(CsrDev A, const doubl
 
 // ---- all-stencil matrices, direct form: no staging at all.  With a uniform pattern the gather x[r + d] of the 32 rows of a warp is ONE
 // coalesced 256-byte load per pattern entry (served by L1 / L2 for the shifted copies), the presence byte only predicates it, and the
-// epilogue operands are plain coalesced loads: the kernel has the memory behaviour of the streaming kernels K_B / K_C (one round of
-// independent loads per row, thousands of threads in flight) instead of a producer / consumer ring.
-template <int L, class G>
-__device__ __forceinline__ double sd_row_fixed(uint32_t m, const StPattern &P, const G &gx, int r)
+// epilogue operands are plain coalesced loads issued together with the gathers: a row costs ONE memory round trip, like the streaming
+// kernels K_B / K_C, and thousands of threads keep the loads in flight -- no producer / consumer ring, no shared-memory traffic.
+// LMAX = longest pattern of the matrix (5 / 7 for the Laplacians): tiles with that pattern and no missing entry take the unrolled path.
+template <int LMAX, class G>
+__device__ __forceinline__ double sd_row(int L, uint32_t m, const StPattern &P, const G &gx, int r)
 {
-  constexpr uint32_t FULL = (1u << L) - 1u;
-  double             xv[L];
-  const double      *xr = gx.x + r;
-  if (__all_sync(0xffffffffu, m == FULL)) {
+  constexpr uint32_t FULL = (1u << LMAX) - 1u;
+  const char        *xr = reinterpret_cast<const char *>(gx.x + r);
+  if (__all_sync(0xffffffffu, L == LMAX && m == FULL)) {
+    double xv[LMAX];
+    int    db[LMAX];
 #pragma unroll
-    for (int j = 0; j < L; j++) xv[j] = gx.ld(xr + P.d[j]);
+    for (int j = 0; j < LMAX; j++) db[j] = P.d[j] * 8;
+#pragma unroll
+    for (int j = 0; j < LMAX; j++) xv[j] = gx.ld(reinterpret_cast<const double *>(xr + (long long)db[j]));
+    __syncwarp();   // scheduling fence (the warp is converged here): every gather is issued before the first multiply-add
     double s = 0.0;
 #pragma unroll
-    for (int j = 0; j < L; j++) s += P.v[j] * xv[j];
+    for (int j = 0; j < LMAX; j++) s += P.v[j] * xv[j];
     return s;
   }
-#pragma unroll
-  for (int j = 0; j < L; j++) xv[j] = ((m >> j) & 1u) ? gx.ld(xr + P.d[j]) : 0.0;
+  // boundary tiles / rows with missing entries: same order, predicated
   double s = 0.0;
-#pragma unroll
+#pragma unroll 1
   for (int j = 0; j < L; j++)
-    if ((m >> j) & 1u) s += P.v[j] * xv[j];
+    if ((m >> j) & 1u) s += P.v[j] * gx.ld(reinterpret_cast<const double *>(xr + (long long)(P.d[j] * 8)));
   return s;
 }
-template <class G>
-__device__ __forceinline__ double sd_row_dispatch(int L, uint32_t m, const StPattern &P, const G &gx, int r)
-{
-  switch (L) {
-  case 1: return sd_row_fixed<1>(m, P, gx, r);
-  case 2: return sd_row_fixed<2>(m, P, gx, r);
-  case 3: return sd_row_fixed<3>(m, P, gx, r);
-  case 4: return sd_row_fixed<4>(m, P, gx, r);
-  case 5: return sd_row_fixed<5>(m, P, gx, r);
-  case 6: return sd_row_fixed<6>(m, P, gx, r);
-  case 7: return sd_row_fixed<7>(m, P, gx, r);
-  default: return sd_row_fixed<8>(m, P, gx, r);
-  }
-}
 
-template <class Epi, int MINB>
+template <class Epi, int LMAX, int MINB>
 __global__ void __launch_bounds__(NT, MINB) k_spmv_sd(CsrDev A, const double *__restrict__ x, Epi epi, TileOrder ord)
 {
   pdl_enter();
@@ -1403,15 +1393,17 @@ __global__ void __launch_bounds__(NT, MINB) k_spmv_sd(CsrDev A, const double *__
     const uint32_t m = m_next;
     const int      pid = pid_next;
     const int      ni = i + gridDim.x;
+    const int      r = tile * TR + threadIdx.x;
+    const bool     live = r < A.n;
+    const typename Epi::Pre pre = epi.preload(live ? r : 0);   // epilogue operands: in flight together with the gathers
     if (ni < ntiles) {
       const int tn = tile_at(ni, ord.ta, ord.tb, rev);
       pid_next = __ldg(A.st_pid + tn);
       m_next   = __ldg(A.st_masks + (size_t)tn * TR + threadIdx.x);
     }
     const StPattern &P = s_pats[pid];
-    const int        r = tile * TR + threadIdx.x;
-    const double     sum = sd_row_dispatch(P.L, m, P, gx, r);   // rows beyond the end carry an empty mask: nothing is loaded
-    if (r < A.n) epi.row(r, sum, acc);
+    const double     sum = sd_row<LMAX>(P.L, m, P, gx, r);   // rows beyond the end carry an empty mask: nothing is loaded
+    if (live) epi.row_p(r, sum, pre, acc);
   }
   epi.finalize(acc);
 }
@@ -1594,8 +1586,8 @@ static int launch_st(const CsrDev &A, const double *x, const Epi &epi, TileOrder
 }
 
 
-template <class Epi>
-static int launch_sd(const CsrDev &A, const double *x, const Epi &epi, TileOrder ord)
+template <class Epi, int LMAX>
+static int launch_sd_l(const CsrDev &A, const double *x, const Epi &epi, TileOrder ord)
 {
   static int minb = 0;
   if (!minb) {
@@ -1603,7 +1595,7 @@ static int launch_sd(const CsrDev &A, const double *x, const Epi &epi, TileOrder
     minb = e ? atoi(e) : 5;
     if (minb != 4 && minb != 6) minb = 5;
   }
-  auto kern = (minb == 4) ? k_spmv_sd<Epi, 4> : (minb == 6 ? k_spmv_sd<Epi, 6> : k_spmv_sd<Epi, 5>);
+  auto kern = (minb == 4) ? k_spmv_sd<Epi, LMAX, 4> : (minb == 5 ? k_spmv_sd<Epi, LMAX, 5> : k_spmv_sd<Epi, LMAX, 6>);
   static int occ = 0;
   if (!occ) {
     int nb = 0;
@@ -1619,6 +1611,18 @@ static int launch_sd(const CsrDev &A, const double *x, const Epi &epi, TileOrder
   }
   launch_k(kern, grid, NT, 0, A, x, epi, ord);
   return 0;
+}
+template <class Epi>
+static int launch_sd(const CsrDev &A, const double *x, const Epi &epi, TileOrder ord)
+{
+  // the unrolled path is compiled for the pattern lengths of the common stencils; other lengths run the predicated loop (LMAX = 8 never
+  // matches a shorter pattern, so every row takes the generic path)
+  switch (A.st_lmax) {
+  case 3: return launch_sd_l<Epi, 3>(A, x, epi, ord);
+  case 5: return launch_sd_l<Epi, 5>(A, x, epi, ord);
+  case 7: return launch_sd_l<Epi, 7>(A, x, epi, ord);
+  default: return launch_sd_l<Epi, 8>(A, x, epi, ord);
+  }
 }
 
 template <class Epi>
@@ -1722,6 +1726,9 @@ struct EpiPlain {
   __device__ bool reverse() const { return false; }
   __device__ void init(Acc &) const {}
   __device__ void row(int r, double ax, Acc &) const { y[r] = accumulate ? y[r] + ax : ax; }
+  struct Pre {};
+  __device__ Pre preload(int) const { return Pre{}; }
+  __device__ void row_p(int r, double ax, const Pre &, Acc &a) const { row(r, ax, a); }
   __device__ void finalize(Acc &) const {}
   __host__ __device__ int  nvec() const { return 0; }
   __host__ __device__ const double *vsrc(int) const { return nullptr; }
@@ -1745,6 +1752,9 @@ struct EpiGated {
   __device__ bool reverse() const { return false; }
   __device__ void init(Acc &) const {}
   __device__ void row(int r, double ax, Acc &) const { y[r] = ax; }
+  struct Pre {};
+  __device__ Pre preload(int) const { return Pre{}; }
+  __device__ void row_p(int r, double ax, const Pre &, Acc &a) const { row(r, ax, a); }
   __device__ void finalize(Acc &) const {}
   __host__ __device__ int  nvec() const { return 0; }
   __host__ __device__ const double *vsrc(int) const { return nullptr; }
@@ -1760,28 +1770,35 @@ struct AccRed {
 
 // off-diagonal part of row r (multi-GPU): MatMultAdd order, the ghost products are added one by one to the diagonal-block sum.
 // Out of line: it runs for the few rows next to a partition boundary only and must not cost the streaming loop any registers.
-__device__ __noinline__ double ghost_slow(const GhostMerge &gm, int r, double ax, int &halo_ok)
+struct GhostRet {
+  double ax;
+  int    ok;
+};
+__device__ __noinline__ GhostRet ghost_slow(const GhostMerge &gm, int r, double ax, int halo_ok)
 {
+  GhostRet  out{ax, halo_ok};
   const int k = __ldg(gm.row_map + (r < gm.lo ? r : r - gm.hi + gm.lo));
-  if (k < 0) return ax;
+  if (k < 0) return out;
   if (!halo_ok) {
     for (int q = 0; q < gm.nflags; q++) wait_flag(gm.flags + (size_t)q * PB_FLAG_STRIDE, gm.seq);
-    halo_ok = 1;
+    out.ok = 1;
   }
   const int e0 = __ldg(gm.oia + k), e1 = __ldg(gm.oia + k + 1);
-  for (int e = e0; e < e1; e++) ax += __ldg(gm.oa + e) * __ldcg(gm.ghost + __ldg(gm.oja + e));
-  return ax;
+  for (int e = e0; e < e1; e++) out.ax += __ldg(gm.oa + e) * __ldcg(gm.ghost + __ldg(gm.oja + e));
+  return out;
 }
 __device__ __forceinline__ double ghost_apply(const GhostMerge &gm, int r, double ax, int &halo_ok)
 {
   if (gm.row_map == nullptr || (r >= gm.lo && r < gm.hi)) return ax;
-  return ghost_slow(gm, r, ax, halo_ok);
+  const GhostRet g = ghost_slow(gm, r, ax, halo_ok);   // by value: the accumulators stay in registers
+  halo_ok = g.ok;
+  return g.ax;
 }
 
 // K_A epilogue: Ap_r = (A p)_r ; p.Ap ; B p ; max feasible step (QPCFeas).  (g.p comes from the kernel that wrote p, see mpgp_ctl.h.)
 // MODE 1: lower bound only, no equality rows (the obstacle problems); MODE 2: lower and upper bound arrays, no equality rows
 // (two-sided boxes, C5); MODE 0: anything.  In modes 1 and 2 the staged path sheds every run-time flag.
-template <int MODE>
+template <int MODE, bool GHOST>
 struct EpiAT {
   typedef GatherPlain Gather;
   __device__ Gather gather(const double *x) const { return Gather{x}; }
@@ -1805,7 +1822,7 @@ struct EpiAT {
   }
   __device__ void row(int r, double ax, Acc &a) const
   {
-    ax    = ghost_apply(gm, r, ax, a.halo_ok);
+    if constexpr (GHOST) ax = ghost_apply(gm, r, ax, a.halo_ok);
     Ap[r] = ax;
     const double pr = __ldg(p + r);
     a.v[RA_PAP] += pr * ax;
@@ -1822,6 +1839,36 @@ struct EpiAT {
         if (j < m) a.v[RA_BP + j] += B[(size_t)j * n + r] * pr;
       a.v[RA_FEAS] = box_feas_lazy(x[r], pr, load_box(bx, r), a.v[RA_FEAS]);
     }
+  }
+  // direct kernels: the row's epilogue operands are loaded BEFORE the gathers are consumed, so that a row costs one memory round trip
+  struct Pre {
+    double p, x, lb, ub;
+  };
+  __device__ Pre preload(int r) const
+  {
+    Pre q;
+    q.p  = __ldg(p + r);
+    q.x  = __ldg(x + r);
+    q.lb = (MODE != 0 || bx.lb) ? __ldg(bx.lb + r) : 0.0;
+    q.ub = (MODE == 2 || (MODE == 0 && bx.ub)) ? __ldg(bx.ub + r) : 0.0;
+    return q;
+  }
+  __device__ void row_p(int r, double ax, const Pre &q, Acc &a) const
+  {
+    if constexpr (GHOST) ax = ghost_apply(gm, r, ax, a.halo_ok);
+    Ap[r] = ax;
+    a.v[RA_PAP] += q.p * ax;
+    BoxVal b;
+    b.has_lb = (MODE != 0) || bx.lb != nullptr;
+    b.has_ub = (MODE == 2) || (MODE == 0 && bx.ub != nullptr);
+    b.lb     = q.lb;
+    b.ub     = q.ub;
+    if constexpr (MODE == 0) {
+#pragma unroll
+      for (int j = 0; j < PB_MAXEQ; j++)
+        if (j < m) a.v[RA_BP + j] += B[(size_t)j * n + r] * q.p;
+    }
+    a.v[RA_FEAS] = box_feas_lazy(q.x, q.p, b, a.v[RA_FEAS]);
   }
   __device__ void finalize(Acc &a) const { grid_reduce8<(1 << RA_FEAS)>(a.v, rb, nullptr); }
   // staged row vectors for the TMA kernels: p, x, [lb], [ub], [B_0..B_{m-1}]
@@ -1846,7 +1893,7 @@ struct EpiAT {
   // va: shared-memory address of this row's slot in the first staged vector; vector k sits k * TR * 8 bytes further
   __device__ void row_s(int r, uint32_t va, double ax, Acc &a) const
   {
-    ax    = ghost_apply(gm, r, ax, a.halo_ok);
+    if constexpr (GHOST) ax = ghost_apply(gm, r, ax, a.halo_ok);
     Ap[r] = ax;
     const double pr = lds_f64(va);
     a.v[RA_PAP] += pr * ax;
@@ -1872,10 +1919,9 @@ struct EpiAT {
     }
   }
 };
-typedef EpiAT<0> EpiA;
 
 // K_A' epilogue: g_r = (A x)_r + rho (B^T Bu)_r - b_r ; split ; p = gf ; |gP|^2 |gc|^2 |gf|^2
-template <int MODE>
+template <int MODE, bool GHOST>
 struct EpiA2T {
   typedef GatherPlain Gather;
   __device__ Gather gather(const double *x) const { return Gather{x}; }
@@ -1898,7 +1944,8 @@ struct EpiA2T {
   }
   __device__ void row(int r, double ax, Acc &a) const
   {
-    double gr = ghost_apply(gm, r, ax, a.halo_ok);
+    double gr = ax;
+    if constexpr (GHOST) gr = ghost_apply(gm, r, ax, a.halo_ok);
     BoxVal bv;
     if constexpr (MODE != 0) {
       bv.has_lb = true;
@@ -1916,6 +1963,44 @@ struct EpiA2T {
     gr -= __ldg(b + r);
     double gf, gc;
     box_split(x[r], gr, bv, bx.astol, gf, gc);
+    g[r] = gr;
+    p[r] = gf;
+    const double gP = gf + gc;
+    a.v[RB_GP2] += gP * gP;
+    a.v[RB_GC2] += gc * gc;
+    a.v[RB_GF2] += gf * gf;
+  }
+  struct Pre {
+    double x, b, lb, ub;
+  };
+  __device__ Pre preload(int r) const
+  {
+    Pre q;
+    q.x  = __ldg(x + r);
+    q.b  = __ldg(b + r);
+    q.lb = (MODE != 0 || bx.lb) ? __ldg(bx.lb + r) : 0.0;
+    q.ub = (MODE == 2 || (MODE == 0 && bx.ub)) ? __ldg(bx.ub + r) : 0.0;
+    return q;
+  }
+  __device__ void row_p(int r, double ax, const Pre &q, Acc &a) const
+  {
+    double gr = ax;
+    if constexpr (GHOST) gr = ghost_apply(gm, r, ax, a.halo_ok);
+    BoxVal bv;
+    bv.has_lb = (MODE != 0) || bx.lb != nullptr;
+    bv.has_ub = (MODE == 2) || (MODE == 0 && bx.ub != nullptr);
+    bv.lb     = q.lb;
+    bv.ub     = q.ub;
+    if constexpr (MODE == 0) {
+      if (m > 0) {
+        double t = 0.0;
+        for (int j = 0; j < m; j++) t += B[(size_t)j * n + r] * S->Bu[j];
+        gr += S->rho * t;
+      }
+    }
+    gr -= q.b;
+    double gf, gc;
+    box_split(q.x, gr, bv, bx.astol, gf, gc);
     g[r] = gr;
     p[r] = gf;
     const double gP = gf + gc;
@@ -1946,7 +2031,8 @@ struct EpiA2T {
   __device__ void row_s(int r, uint32_t va, double ax, Acc &a) const
   {
     BoxVal bv;
-    double gr = ghost_apply(gm, r, ax, a.halo_ok);
+    double gr = ax;
+    if constexpr (GHOST) gr = ghost_apply(gm, r, ax, a.halo_ok);
     if constexpr (MODE != 0) {
       bv.has_lb = true;
       bv.has_ub = (MODE == 2);
@@ -1977,7 +2063,6 @@ struct EpiA2T {
     a.v[RB_GF2] += gf * gf;
   }
 };
-typedef EpiA2T<0> EpiA2;
 
 // power-method step (MatGetMaxEigenvalue, permonmatutils.c:484-511) in ONE pass: the normalised iterate v = s * w is formed on the
 // fly (the same product VecScale would have stored), y = A v, and the two dot products of VecMDot(v, {Av, v}) ride in the epilogue
@@ -2001,6 +2086,17 @@ struct EpiPower {
   {
     y[r] = ax;
     const double vr = w[r] * s;
+    a.v[0] += ax * vr;
+    a.v[1] += vr * vr;
+  }
+  struct Pre {
+    double w;
+  };
+  __device__ Pre preload(int r) const { return Pre{__ldg(w + r)}; }
+  __device__ void row_p(int r, double ax, const Pre &q, Acc &a) const
+  {
+    y[r] = ax;
+    const double vr = q.w * s;
     a.v[0] += ax * vr;
     a.v[1] += vr * vr;
   }
@@ -2064,34 +2160,47 @@ static TileOrder tile_order(const CsrDev &A, const GhostMerge &gm)
   return o;
 }
 
+template <int MODE, bool GHOST>
+static int fused_A_t(const CsrDev &A, const double *xin, const MpgpVecs &v, const MpgpCtl *S, RedBuf rb, const GhostMerge &gm, TileOrder ord)
+{
+  EpiAT<MODE, GHOST> e{v.p, v.x, v.Ap, v.bx, v.B, v.m, v.n, S, rb, gm};
+  return launch_spmv(A, xin, e, KF_SPMV_A, bytes_A(A, v), ord);
+}
+template <int MODE, bool GHOST>
+static int fused_A2_t(const CsrDev &A, const double *xin, const MpgpVecs &v, const MpgpCtl *S, RedBuf rb, const GhostMerge &gm, TileOrder ord)
+{
+  EpiA2T<MODE, GHOST> e{v.x, v.b, v.g, v.p, v.bx, v.B, v.m, v.n, S, rb, gm};
+  return launch_spmv(A, xin, e, KF_SPMV_A2, bytes_A2(A, v), ord);
+}
+// MODE: 1 lower bound only, 2 both bounds (no equality rows), 0 anything; the ghost-column code exists only in the multi-GPU instantiations
+static int box_mode(const MpgpVecs &v) { return (v.m == 0 && v.bx.lb) ? (v.bx.ub ? 2 : 1) : 0; }
+
 int k_fused_A(const CsrDev &A, const double *xin, const MpgpVecs &v, const MpgpCtl *S, RedBuf rb, const GhostMerge &gm)
 {
   const TileOrder ord = tile_order(A, gm);
-  if (v.bx.lb && !v.bx.ub && v.m == 0) {
-    EpiAT<1> e{v.p, v.x, v.Ap, v.bx, v.B, v.m, v.n, S, rb, gm};
-    return launch_spmv(A, xin, e, KF_SPMV_A, bytes_A(A, v), ord);
+  const int       mode = box_mode(v);
+  if (gm.row_map) {
+    if (mode == 1) return fused_A_t<1, true>(A, xin, v, S, rb, gm, ord);
+    if (mode == 2) return fused_A_t<2, true>(A, xin, v, S, rb, gm, ord);
+    return fused_A_t<0, true>(A, xin, v, S, rb, gm, ord);
   }
-  if (v.bx.lb && v.bx.ub && v.m == 0) {
-    EpiAT<2> e{v.p, v.x, v.Ap, v.bx, v.B, v.m, v.n, S, rb, gm};
-    return launch_spmv(A, xin, e, KF_SPMV_A, bytes_A(A, v), ord);
-  }
-  EpiA e{v.p, v.x, v.Ap, v.bx, v.B, v.m, v.n, S, rb, gm};
-  return launch_spmv(A, xin, e, KF_SPMV_A, bytes_A(A, v), ord);
+  if (mode == 1) return fused_A_t<1, false>(A, xin, v, S, rb, gm, ord);
+  if (mode == 2) return fused_A_t<2, false>(A, xin, v, S, rb, gm, ord);
+  return fused_A_t<0, false>(A, xin, v, S, rb, gm, ord);
 }
 
 int k_fused_A2(const CsrDev &A, const double *xin, const MpgpVecs &v, const MpgpCtl *S, RedBuf rb, const GhostMerge &gm)
 {
   const TileOrder ord = tile_order(A, gm);
-  if (v.bx.lb && !v.bx.ub && v.m == 0) {
-    EpiA2T<1> e{v.x, v.b, v.g, v.p, v.bx, v.B, v.m, v.n, S, rb, gm};
-    return launch_spmv(A, xin, e, KF_SPMV_A2, bytes_A2(A, v), ord);
+  const int       mode = box_mode(v);
+  if (gm.row_map) {
+    if (mode == 1) return fused_A2_t<1, true>(A, xin, v, S, rb, gm, ord);
+    if (mode == 2) return fused_A2_t<2, true>(A, xin, v, S, rb, gm, ord);
+    return fused_A2_t<0, true>(A, xin, v, S, rb, gm, ord);
   }
-  if (v.bx.lb && v.bx.ub && v.m == 0) {
-    EpiA2T<2> e{v.x, v.b, v.g, v.p, v.bx, v.B, v.m, v.n, S, rb, gm};
-    return launch_spmv(A, xin, e, KF_SPMV_A2, bytes_A2(A, v), ord);
-  }
-  EpiA2 e{v.x, v.b, v.g, v.p, v.bx, v.B, v.m, v.n, S, rb, gm};
-  return launch_spmv(A, xin, e, KF_SPMV_A2, bytes_A2(A, v), ord);
+  if (mode == 1) return fused_A2_t<1, false>(A, xin, v, S, rb, gm, ord);
+  if (mode == 2) return fused_A2_t<2, false>(A, xin, v, S, rb, gm, ord);
+  return fused_A2_t<0, false>(A, xin, v, S, rb, gm, ord);
 }
 
 // peer-memory halo push: dst_q[k] = vec[send_idx[k]] written straight into the neighbours' ghost buffers, then a

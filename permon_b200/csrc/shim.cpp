@@ -1005,6 +1005,8 @@ static int upload_stencil(pb::CsrDev &C, pb::StencilHost &st, int64_t nnz, doubl
   C.st_pats  = dt;
   C.st_npat  = (int)st.pats.size();
   C.st_nwin  = st.nwin;
+  C.st_lmax  = 0;
+  for (const pb::StPattern &P : st.pats) C.st_lmax = std::max(C.st_lmax, P.L);
   C.pk_bytes = (int64_t)st.masks.size() + (int64_t)st.pid.size() + (int64_t)(sizeof(pb::StPattern) * st.pats.size());
   C.pk_coded = (int64_t)st.pid.size();
   C.kind     = 4;
