@@ -1354,11 +1354,21 @@ __device__ __forceinline__ double sd_row(int L, uint32_t m, const StPattern &P, 
     for (int j = 0; j < LMAX; j++) s += P.v[j] * xv[j];
     return s;
   }
-  // boundary tiles / rows with missing entries: same order, predicated
+  // rows with missing entries (next to a grid boundary) and tiles with a shorter pattern: same order, every load predicated and still
+  // issued before the first multiply-add -- the warps that own the boundary rows of a structured grid take this path in every tile
+  double xv[LMAX], vv[LMAX];
+#pragma unroll
+  for (int j = 0; j < LMAX; j++) {
+    const bool on = (j < L) && ((m >> j) & 1u);
+    xv[j]         = on ? gx.ld(reinterpret_cast<const double *>(xr + (long long)(P.d[j] * 8))) : 0.0;
+  }
+  __syncwarp();
+#pragma unroll
+  for (int j = 0; j < LMAX; j++) vv[j] = P.v[j];
   double s = 0.0;
-#pragma unroll 1
-  for (int j = 0; j < L; j++)
-    if ((m >> j) & 1u) s += P.v[j] * gx.ld(reinterpret_cast<const double *>(xr + (long long)(P.d[j] * 8)));
+#pragma unroll
+  for (int j = 0; j < LMAX; j++)
+    if ((j < L) && ((m >> j) & 1u)) s += vv[j] * xv[j];
   return s;
 }
 
@@ -1404,6 +1414,102 @@ __global__ void __launch_bounds__(NT, MINB) k_spmv_sd(CsrDev A, const double *__
     const StPattern &P = s_pats[pid];
     const double     sum = sd_row<LMAX>(P.L, m, P, gx, r);   // rows beyond the end carry an empty mask: nothing is loaded
     if (live) epi.row_p(r, sum, pre, acc);
+  }
+  epi.finalize(acc);
+}
+
+
+// Two ADJACENT rows per thread (r even): the epilogue operands and results travel as 16-byte accesses, the two gathers of a pattern entry
+// share one address computation, and the per-row share of the loop overhead (pattern operands, tile bookkeeping) is halved.  A CTA walks
+// "super tiles" of 512 rows = two 256-row tiles (threads 0..127 the first, 128..255 the second: the pattern is still warp-uniform).
+// Needs an even row count and 16-byte aligned vectors; k_spmv_sd is the fallback.
+template <int LMAX, class G>
+__device__ __forceinline__ void sd_row2(int L, uint32_t m0, uint32_t m1, const StPattern &P, const G &gx, int r, double &s0, double &s1)
+{
+  constexpr uint32_t FULL = (1u << LMAX) - 1u;
+  const char        *xr = reinterpret_cast<const char *>(gx.x + r);
+  double             x0[LMAX], x1[LMAX], vv[LMAX];
+  if (__all_sync(0xffffffffu, L == LMAX && m0 == FULL && m1 == FULL)) {
+#pragma unroll
+    for (int j = 0; j < LMAX; j++) {
+      const double *a = reinterpret_cast<const double *>(xr + (long long)(P.d[j] * 8));
+      x0[j]           = gx.ld(a);
+      x1[j]           = gx.ld(a + 1);
+    }
+    __syncwarp();   // scheduling fence: every gather is issued before the first multiply-add
+#pragma unroll
+    for (int j = 0; j < LMAX; j++) vv[j] = P.v[j];
+    s0 = 0.0;
+    s1 = 0.0;
+#pragma unroll
+    for (int j = 0; j < LMAX; j++) s0 += vv[j] * x0[j];
+#pragma unroll
+    for (int j = 0; j < LMAX; j++) s1 += vv[j] * x1[j];
+    return;
+  }
+#pragma unroll
+  for (int j = 0; j < LMAX; j++) {
+    const double *a = reinterpret_cast<const double *>(xr + (long long)(P.d[j] * 8));
+    const bool    on0 = (j < L) && ((m0 >> j) & 1u), on1 = (j < L) && ((m1 >> j) & 1u);
+    x0[j]             = on0 ? gx.ld(a) : 0.0;
+    x1[j]             = on1 ? gx.ld(a + 1) : 0.0;
+  }
+  __syncwarp();
+#pragma unroll
+  for (int j = 0; j < LMAX; j++) vv[j] = P.v[j];
+  s0 = 0.0;
+  s1 = 0.0;
+#pragma unroll
+  for (int j = 0; j < LMAX; j++)
+    if ((j < L) && ((m0 >> j) & 1u)) s0 += vv[j] * x0[j];
+#pragma unroll
+  for (int j = 0; j < LMAX; j++)
+    if ((j < L) && ((m1 >> j) & 1u)) s1 += vv[j] * x1[j];
+}
+
+template <class Epi, int LMAX, int MINB>
+__global__ void __launch_bounds__(NT, MINB) k_spmv_sd2(CsrDev A, const double *__restrict__ x, Epi epi, TileOrder ord)
+{
+  pdl_enter();
+  if (!epi.active()) return;
+  __shared__ StPattern s_pats[PB_ST_MAXPAT];
+  {
+    const int  nw = A.st_npat * (int)(sizeof(StPattern) / 4);
+    const int *src = reinterpret_cast<const int *>(A.st_pats);
+    int       *dst = reinterpret_cast<int *>(s_pats);
+    for (int k = threadIdx.x; k < nw; k += NT) dst[k] = __ldg(src + k);
+  }
+  __syncthreads();
+  const int  nst = (A.n + 2 * TR - 1) / (2 * TR);   // super tiles (the mask / pattern-id arrays are padded to an even number of tiles)
+  const int  half = threadIdx.x >> 7;
+  const bool rev = epi.reverse();
+  const typename Epi::Gather gx = epi.gather(x);
+  typename Epi::Acc acc;
+  epi.init(acc);
+  uchar2 m_next = make_uchar2(0, 0);
+  int    pid_next = 0;
+  if ((int)blockIdx.x < nst) {
+    const int t0 = tile_at(blockIdx.x, ord.ta, ord.tb, rev);
+    pid_next = __ldg(A.st_pid + 2 * t0 + half);
+    m_next   = __ldg(reinterpret_cast<const uchar2 *>(A.st_masks + (size_t)t0 * (2 * TR)) + threadIdx.x);
+  }
+  for (int i = blockIdx.x; i < nst; i += gridDim.x) {
+    const int    st = tile_at(i, ord.ta, ord.tb, rev);
+    const uchar2 m = m_next;
+    const int    pid = pid_next;
+    const int    ni = i + gridDim.x;
+    const int    r = st * (2 * TR) + 2 * (int)threadIdx.x;
+    const bool   live = r < A.n;   // n is even: r + 1 < n as well
+    const typename Epi::Pre2 pre = epi.preload2(live ? r : 0);
+    if (ni < nst) {
+      const int tn = tile_at(ni, ord.ta, ord.tb, rev);
+      pid_next = __ldg(A.st_pid + 2 * tn + half);
+      m_next   = __ldg(reinterpret_cast<const uchar2 *>(A.st_masks + (size_t)tn * (2 * TR)) + threadIdx.x);
+    }
+    const StPattern &P = s_pats[pid];
+    double           s0, s1;
+    sd_row2<LMAX>(P.L, m.x, m.y, P, gx, r, s0, s1);
+    if (live) epi.row2_p(r, s0, s1, pre, acc);
   }
   epi.finalize(acc);
 }
@@ -1595,6 +1701,40 @@ static int launch_sd_l(const CsrDev &A, const double *x, const Epi &epi, TileOrd
     minb = e ? atoi(e) : 5;
     if (minb != 4 && minb != 6) minb = 5;
   }
+  static int pairs = -1;
+  if (pairs < 0) {
+    const char *e = getenv("PERMON_B200_SD_PAIRS");
+    pairs = (e && e[0] == '0') ? 0 : 1;
+  }
+  if (pairs && (A.n % 2 == 0) && aligned16(x) && epi.pair_ok()) {
+    // two adjacent rows per thread, 16-byte accesses
+    static int minb2 = 0;
+    if (!minb2) {
+      const char *e = getenv("PERMON_B200_SD2_OCC");
+      minb2 = e ? atoi(e) : 4;
+      if (minb2 != 3 && minb2 != 5) minb2 = 4;
+    }
+    auto       k2 = (minb2 == 3) ? k_spmv_sd2<Epi, LMAX, 3> : (minb2 == 5 ? k_spmv_sd2<Epi, LMAX, 5> : k_spmv_sd2<Epi, LMAX, 4>);
+    static int occ2 = 0;
+    if (!occ2) {
+      int nb = 0;
+      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k2, NT, 0) != cudaSuccess || nb < 1) nb = 1;
+      occ2 = nb;
+    }
+    const int ntiles = (A.n + TR - 1) / TR, nst = (ntiles + 1) / 2;
+    int       grid = g_ctx.sm_count * occ2;
+    if (grid > nst) grid = nst;
+    if (grid > max_red_blocks()) grid = max_red_blocks();
+    TileOrder o2;
+    o2.ta = (ord.ta + 1) / 2;
+    o2.tb = ord.tb / 2;
+    if (o2.tb <= o2.ta || o2.tb > nst || ord.tb <= ord.ta || ord.tb > ntiles || (ord.ta == 0 && ord.tb == ntiles)) {
+      o2.ta = 0;
+      o2.tb = nst;
+    }
+    launch_k(k2, grid, NT, 0, A, x, epi, o2);
+    return 0;
+  }
   auto kern = (minb == 4) ? k_spmv_sd<Epi, LMAX, 4> : (minb == 5 ? k_spmv_sd<Epi, LMAX, 5> : k_spmv_sd<Epi, LMAX, 6>);
   static int occ = 0;
   if (!occ) {
@@ -1735,6 +1875,15 @@ struct EpiPlain {
   int nvec_host() const { return nvec(); }
   const double *vsrc_host(int i) const { return vsrc(i); }
   __device__ void row_s(int r, uint32_t, double ax, Acc &a) const { row(r, ax, a); }
+
+  struct Pre2 {};
+  __device__ Pre2 preload2(int) const { return Pre2{}; }
+  __device__ void row2_p(int r, double a0, double a1, const Pre2 &, Acc &a) const
+  {
+    row(r, a0, a);
+    row(r + 1, a1, a);
+  }
+  bool pair_ok() const { return true; }
 };
 
 struct EpiGated {
@@ -1755,6 +1904,14 @@ struct EpiGated {
   struct Pre {};
   __device__ Pre preload(int) const { return Pre{}; }
   __device__ void row_p(int r, double ax, const Pre &, Acc &a) const { row(r, ax, a); }
+  struct Pre2 {};
+  __device__ Pre2 preload2(int) const { return Pre2{}; }
+  __device__ void row2_p(int r, double a0, double a1, const Pre2 &, Acc &a) const
+  {
+    row(r, a0, a);
+    row(r + 1, a1, a);
+  }
+  bool pair_ok() const { return true; }
   __device__ void finalize(Acc &) const {}
   __host__ __device__ int  nvec() const { return 0; }
   __host__ __device__ const double *vsrc(int) const { return nullptr; }
@@ -1870,6 +2027,44 @@ struct EpiAT {
     }
     a.v[RA_FEAS] = box_feas_lazy(q.x, q.p, b, a.v[RA_FEAS]);
   }
+  struct Pre2 {
+    double2 p, x, lb, ub;
+  };
+  __device__ Pre2 preload2(int r) const
+  {
+    Pre2 q;
+    q.p  = __ldg(reinterpret_cast<const double2 *>(p + r));
+    q.x  = __ldg(reinterpret_cast<const double2 *>(x + r));
+    q.lb = (MODE != 0 || bx.lb) ? __ldg(reinterpret_cast<const double2 *>(bx.lb + r)) : make_double2(0.0, 0.0);
+    q.ub = (MODE == 2 || (MODE == 0 && bx.ub)) ? __ldg(reinterpret_cast<const double2 *>(bx.ub + r)) : make_double2(0.0, 0.0);
+    return q;
+  }
+  __device__ void row2_p(int r, double a0, double a1, const Pre2 &q, Acc &a) const
+  {
+    if constexpr (GHOST) {
+      a0 = ghost_apply(gm, r, a0, a.halo_ok);
+      a1 = ghost_apply(gm, r + 1, a1, a.halo_ok);
+    }
+    *reinterpret_cast<double2 *>(Ap + r) = make_double2(a0, a1);
+    a.v[RA_PAP] += q.p.x * a0;
+    a.v[RA_PAP] += q.p.y * a1;
+    BoxVal b0, b1;
+    b0.has_lb = b1.has_lb = (MODE != 0) || bx.lb != nullptr;
+    b0.has_ub = b1.has_ub = (MODE == 2) || (MODE == 0 && bx.ub != nullptr);
+    b0.lb = q.lb.x; b1.lb = q.lb.y;
+    b0.ub = q.ub.x; b1.ub = q.ub.y;
+    if constexpr (MODE == 0) {
+#pragma unroll
+      for (int j = 0; j < PB_MAXEQ; j++)
+        if (j < m) {
+          a.v[RA_BP + j] += B[(size_t)j * n + r] * q.p.x;
+          a.v[RA_BP + j] += B[(size_t)j * n + r + 1] * q.p.y;
+        }
+    }
+    a.v[RA_FEAS] = box_feas_lazy(q.x.x, q.p.x, b0, a.v[RA_FEAS]);
+    a.v[RA_FEAS] = box_feas_lazy(q.x.y, q.p.y, b1, a.v[RA_FEAS]);
+  }
+  bool pair_ok() const { return aligned16(p) && aligned16(x) && aligned16(Ap) && aligned16(bx.lb) && aligned16(bx.ub); }
   __device__ void finalize(Acc &a) const { grid_reduce8<(1 << RA_FEAS)>(a.v, rb, nullptr); }
   // staged row vectors for the TMA kernels: p, x, [lb], [ub], [B_0..B_{m-1}]
   __host__ __device__ int nvec() const { return 2 + (bx.lb ? 1 : 0) + (bx.ub ? 1 : 0) + m; }
@@ -2008,6 +2203,57 @@ struct EpiA2T {
     a.v[RB_GC2] += gc * gc;
     a.v[RB_GF2] += gf * gf;
   }
+  struct Pre2 {
+    double2 x, b, lb, ub;
+  };
+  __device__ Pre2 preload2(int r) const
+  {
+    Pre2 q;
+    q.x  = __ldg(reinterpret_cast<const double2 *>(x + r));
+    q.b  = __ldg(reinterpret_cast<const double2 *>(b + r));
+    q.lb = (MODE != 0 || bx.lb) ? __ldg(reinterpret_cast<const double2 *>(bx.lb + r)) : make_double2(0.0, 0.0);
+    q.ub = (MODE == 2 || (MODE == 0 && bx.ub)) ? __ldg(reinterpret_cast<const double2 *>(bx.ub + r)) : make_double2(0.0, 0.0);
+    return q;
+  }
+  __device__ void row2_p(int r, double a0, double a1, const Pre2 &q, Acc &a) const
+  {
+    double gr0 = a0, gr1 = a1;
+    if constexpr (GHOST) {
+      gr0 = ghost_apply(gm, r, a0, a.halo_ok);
+      gr1 = ghost_apply(gm, r + 1, a1, a.halo_ok);
+    }
+    BoxVal b0, b1;
+    b0.has_lb = b1.has_lb = (MODE != 0) || bx.lb != nullptr;
+    b0.has_ub = b1.has_ub = (MODE == 2) || (MODE == 0 && bx.ub != nullptr);
+    b0.lb = q.lb.x; b1.lb = q.lb.y;
+    b0.ub = q.ub.x; b1.ub = q.ub.y;
+    if constexpr (MODE == 0) {
+      if (m > 0) {
+        double t0 = 0.0, t1 = 0.0;
+        for (int j = 0; j < m; j++) {
+          t0 += B[(size_t)j * n + r] * S->Bu[j];
+          t1 += B[(size_t)j * n + r + 1] * S->Bu[j];
+        }
+        gr0 += S->rho * t0;
+        gr1 += S->rho * t1;
+      }
+    }
+    gr0 -= q.b.x;
+    gr1 -= q.b.y;
+    double gf0, gc0, gf1, gc1;
+    box_split(q.x.x, gr0, b0, bx.astol, gf0, gc0);
+    box_split(q.x.y, gr1, b1, bx.astol, gf1, gc1);
+    *reinterpret_cast<double2 *>(g + r) = make_double2(gr0, gr1);
+    *reinterpret_cast<double2 *>(p + r) = make_double2(gf0, gf1);
+    const double gP0 = gf0 + gc0, gP1 = gf1 + gc1;
+    a.v[RB_GP2] += gP0 * gP0;
+    a.v[RB_GC2] += gc0 * gc0;
+    a.v[RB_GF2] += gf0 * gf0;
+    a.v[RB_GP2] += gP1 * gP1;
+    a.v[RB_GC2] += gc1 * gc1;
+    a.v[RB_GF2] += gf1 * gf1;
+  }
+  bool pair_ok() const { return aligned16(x) && aligned16(b) && aligned16(g) && aligned16(p) && aligned16(bx.lb) && aligned16(bx.ub); }
   __device__ void finalize(Acc &a) const { grid_reduce8<0>(a.v, rb, nullptr); }
   // staged row vectors for the TMA kernels: x, b, [lb], [ub], [B_0..B_{m-1}]
   __host__ __device__ int nvec() const { return 2 + (bx.lb ? 1 : 0) + (bx.ub ? 1 : 0) + m; }
@@ -2100,6 +2346,20 @@ struct EpiPower {
     a.v[0] += ax * vr;
     a.v[1] += vr * vr;
   }
+  struct Pre2 {
+    double2 w;
+  };
+  __device__ Pre2 preload2(int r) const { return Pre2{__ldg(reinterpret_cast<const double2 *>(w + r))}; }
+  __device__ void row2_p(int r, double a0, double a1, const Pre2 &q, Acc &a) const
+  {
+    *reinterpret_cast<double2 *>(y + r) = make_double2(a0, a1);
+    const double v0 = q.w.x * s, v1 = q.w.y * s;
+    a.v[0] += a0 * v0;
+    a.v[1] += v0 * v0;
+    a.v[0] += a1 * v1;
+    a.v[1] += v1 * v1;
+  }
+  bool pair_ok() const { return aligned16(w) && aligned16(y); }
   __device__ void finalize(Acc &a) const { grid_reduce8<0>(a.v, rb, nullptr); }
   __host__ __device__ int nvec() const { return 1; }
   __host__ __device__ const double *vsrc(int) const { return w; }

@@ -16,7 +16,8 @@
 #define PB_HD __host__ __device__
 #endif
 
-#define PB_MAXEQ 4   // equality rows handled by the fused rank-m update
+#define PB_MAXEQ 4       // equality rows handled by the fused rank-m update (accumulators in registers)
+#define PB_MAXEQ_ALL 64  // equality rows handled at all: beyond PB_MAXEQ the un-fused route runs (dense rows, 8 per reduction launch)
 #define PB_NRED 8    // doubles per reduction record
 #define PB_MAXRANKS 16
 

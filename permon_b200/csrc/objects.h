@@ -279,6 +279,10 @@ struct Reducer {
 Reducer &reducer(MPI_Comm comm);           // shared scratch reducer of the communicator
 
 int  vec_prefetch(Vec v);                                    // start the H2D copy of a host-valid vector on the copy stream (pinned buffers: truly asynchronous)
+// dense equality rows B (m x n, row-major on the device), any m <= PB_MAXEQ_ALL: t = B x (host values, summed over ranks) and
+// y (+)= scale * B^T t, in chunks of PB_NRED rows per launch
+int  dense_rows_mult_host(MPI_Comm comm, int n, int m, const double *Bd, const double *x, double *t);
+int  dense_rows_multT_host(MPI_Comm comm, int n, int m, const double *Bd, const double *t, double scale, double *y, int accumulate);
 int  vec_dot(Vec x, Vec y, double *val);
 int  vec_norm2(Vec x, double *val);
 int  vec_mdot2(Vec x, Vec y0, Vec y1, double *v0, double *v1);

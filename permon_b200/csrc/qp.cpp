@@ -368,7 +368,7 @@ PetscErrorCode QPPFSetUp(QPPF cp)
   PB_CHK(dev_init());
   cp->m = G->M;
   cp->n = G->n;
-  if (cp->m > PB_MAXEQ) return err(PETSC_ERR_SUP, "the B200 SMALXE path handles at most %d equality rows (got %d)", PB_MAXEQ, (int)cp->m);
+  if (cp->m > PB_MAXEQ_ALL) return err(PETSC_ERR_SUP, "at most %d equality rows are handled (got %d)", PB_MAXEQ_ALL, (int)cp->m);
   if (G->kind == MK_ONEROW) {
     const double *d;
     PB_CHK(vec_dev_read(G->row, &d));
@@ -396,13 +396,7 @@ PetscErrorCode QPPFSetUp(QPPF cp)
   // G G^T (m x m) on the device, factor on the host (replicated on every rank: PCREDUNDANT, matinv.c:565-569)
   const int m = cp->m;
   cp->GGt.assign((size_t)m * m, 0.0);
-  Reducer &R = reducer(cp->comm);
-  for (int i = 0; i < m; i++) {
-    PB_CHK(k_dense_rows_mult(cp->n, m, cp->Bd, cp->Bd + (size_t)i * cp->n, R.rb));
-    PB_CHK(R.gather());
-    PB_CHK(R.fetch());
-    for (int j = 0; j < m; j++) cp->GGt[(size_t)i * m + j] = R.sum(j);
-  }
+  for (int i = 0; i < m; i++) PB_CHK(dense_rows_mult_host(cp->comm, cp->n, m, cp->Bd, cp->Bd + (size_t)i * cp->n, &cp->GGt[(size_t)i * m]));
   // MatHasOrthonormalRows(G, PETSC_SMALL, 3) (qppf.c:394, permonmatorth.c:551): the reference tests
   // G G^T v = v on 3 random vectors; m is tiny here so G G^T is compared with I entry by entry.
   cp->orth = true;
@@ -451,20 +445,13 @@ static int qppf_G_mult(QPPF cp, Vec v, double *t)
   const double *dv;
   PB_CHK(vec_dev_read(v, &dv));
   if (v->n != cp->n) return err(PETSC_ERR_ARG_SIZ, "QPPF: vector has local size %d, G has %d columns", (int)v->n, (int)cp->n);
-  Reducer &R = reducer(cp->comm);
-  PB_CHK(k_dense_rows_mult(cp->n, cp->m, cp->Bd, dv, R.rb));
-  PB_CHK(R.gather());
-  PB_CHK(R.fetch());
-  for (int j = 0; j < cp->m; j++) t[j] = R.sum(j);
-  return 0;
+  return dense_rows_mult_host(cp->comm, cp->n, cp->m, cp->Bd, dv, t);
 }
 static int qppf_Gt_mult(QPPF cp, const double *t, Vec y)
 {   // y = G^T t
-  double  *dy;
-  Reducer &R = reducer(cp->comm);
+  double *dy;
   PB_CHK(vec_dev_write(y, &dy));
-  PB_CUDA(cudaMemcpyAsync(R.d_all, t, sizeof(double) * cp->m, cudaMemcpyHostToDevice, ctx().stream));
-  return k_dense_rows_multT_add(cp->n, cp->m, cp->Bd, R.d_all, 1.0, dy, 0);
+  return dense_rows_multT_host(cp->comm, cp->n, cp->m, cp->Bd, t, 1.0, dy, 0);
 }
 static int mvec_get(Vec x, int m, double *t)
 {   // m-vector on the host.  In the reference's layout rank 0 owns the m entries (MatCreateOneRow, onerow.c:97-113);
@@ -508,7 +495,7 @@ static int mvec_put(Vec y, int m, const double *t)
 PetscErrorCode QPPFApplyCP(QPPF cp, Vec x, Vec y)
 {   // qppf.c:610-645
   PB_CHK(QPPFSetUp(cp));
-  double r[PB_MAXEQ], s[PB_MAXEQ];
+  double r[PB_MAXEQ_ALL], s[PB_MAXEQ_ALL];
   PB_CHK(mvec_get(x, cp->m, r));
   PB_CHK(qppf_solve(cp, r, s));
   return mvec_put(y, cp->m, s);
@@ -516,17 +503,17 @@ PetscErrorCode QPPFApplyCP(QPPF cp, Vec x, Vec y)
 PetscErrorCode QPPFApplyGtG(QPPF cp, Vec v, Vec GtGv)
 {   // qppf.c:580-605 (with orthonormal rows the reference routes through ApplyQ = G^T (G v) as well)
   PB_CHK(QPPFSetUp(cp));
-  double t[PB_MAXEQ];
+  double t[PB_MAXEQ_ALL];
   PB_CHK(qppf_G_mult(cp, v, t));
   return qppf_Gt_mult(cp, t, GtGv);
 }
 PetscErrorCode QPPFApplyQ(QPPF cp, Vec v, Vec Qv)
 {   // qppf.c:454-502
   PB_CHK(QPPFSetUp(cp));
-  double t[PB_MAXEQ], s[PB_MAXEQ];
+  double t[PB_MAXEQ_ALL], s[PB_MAXEQ_ALL];
   PB_CHK(qppf_G_mult(cp, v, t));
   if (!cp->orth) PB_CHK(qppf_solve(cp, t, s));
-  else memcpy(s, t, sizeof s);
+  else memcpy(s, t, sizeof(double) * cp->m);
   return qppf_Gt_mult(cp, s, Qv);
 }
 PetscErrorCode QPPFApplyP(QPPF cp, Vec v, Vec Pv)
@@ -538,16 +525,11 @@ namespace pb {
 int qppf_apply_P_dev(QPPF cp, const double *x, double *y)
 {   // QPPFMatMult_P -> QPPFApplyP (qppf.c:560-575): y = x - G^T (G G^T)^{-1} G x
   PB_CHK(QPPFSetUp(cp));
-  double   t[PB_MAXEQ], s[PB_MAXEQ];
-  Reducer &R = reducer(cp->comm);
-  PB_CHK(k_dense_rows_mult(cp->n, cp->m, cp->Bd, x, R.rb));
-  PB_CHK(R.gather());
-  PB_CHK(R.fetch());
-  for (int j = 0; j < cp->m; j++) t[j] = R.sum(j);
+  double t[PB_MAXEQ_ALL], s[PB_MAXEQ_ALL];
+  PB_CHK(dense_rows_mult_host(cp->comm, cp->n, cp->m, cp->Bd, x, t));
   if (!cp->orth) PB_CHK(qppf_solve(cp, t, s));
-  else memcpy(s, t, sizeof s);
-  PB_CUDA(cudaMemcpyAsync(R.d_all, s, sizeof(double) * cp->m, cudaMemcpyHostToDevice, ctx().stream));
-  PB_CHK(k_dense_rows_multT_add(cp->n, cp->m, cp->Bd, R.d_all, 1.0, y, 0));   // y = Q x
+  else memcpy(s, t, sizeof(double) * cp->m);
+  PB_CHK(dense_rows_multT_host(cp->comm, cp->n, cp->m, cp->Bd, s, 1.0, y, 0));   // y = Q x
   return k_aypx(cp->n, y, -1.0, x);                                            // VecAYPX(Pv, -1, v)
 }
 }   // namespace pb
@@ -569,7 +551,7 @@ PetscErrorCode QPPFCreateP(QPPF cp, Mat *newP)
 PetscErrorCode QPPFApplyHalfQ(QPPF cp, Vec x, Vec y)
 {   // qppf.c:507-530: y = (G G^T)^{-1} G x
   PB_CHK(QPPFSetUp(cp));
-  double t[PB_MAXEQ], s[PB_MAXEQ];
+  double t[PB_MAXEQ_ALL], s[PB_MAXEQ_ALL];
   PB_CHK(qppf_G_mult(cp, x, t));
   PB_CHK(qppf_solve(cp, t, s));
   return mvec_put(y, cp->m, s);
@@ -577,10 +559,10 @@ PetscErrorCode QPPFApplyHalfQ(QPPF cp, Vec x, Vec y)
 PetscErrorCode QPPFApplyHalfQTranspose(QPPF cp, Vec x, Vec y)
 {   // qppf.c:535-568: y = G^T (G G^T)^{-1} x
   PB_CHK(QPPFSetUp(cp));
-  double r[PB_MAXEQ], s[PB_MAXEQ];
+  double r[PB_MAXEQ_ALL], s[PB_MAXEQ_ALL];
   PB_CHK(mvec_get(x, cp->m, r));
   if (!cp->orth) PB_CHK(qppf_solve(cp, r, s));
-  else memcpy(s, r, sizeof s);
+  else memcpy(s, r, sizeof(double) * cp->m);
   return qppf_Gt_mult(cp, s, y);
 }
 
@@ -901,7 +883,7 @@ static int lagrangian_gradient(QP qp, Vec x, Vec r, bool with_box, bool with_eq,
     } else if (qp->lambda_E && !qp->lambda_E->invalidated && qp->pf) {
       Vec t;
       PB_CHK(VecDuplicate(r, &t));
-      double lam[PB_MAXEQ];
+      double lam[PB_MAXEQ_ALL];
       PB_CHK(mvec_get(qp->lambda_E, qp->pf->m, lam));
       PB_CHK(QPPFSetUp(qp->pf));
       PB_CHK(qppf_Gt_mult(qp->pf, lam, t));
@@ -1002,11 +984,11 @@ PetscErrorCode QPViewKKT(QP qp, PetscViewer v)
   }
   pb::unref(r);
   if (qp->BE && qp->pf) {
-    double t[PB_MAXEQ], s = 0.0;
+    double t[PB_MAXEQ_ALL], s = 0.0;
     PB_CHK(QPPFSetUp(qp->pf));
     PB_CHK(qppf_G_mult(qp->pf, qp->x, t));
     if (qp->cE) {
-      double c[PB_MAXEQ];
+      double c[PB_MAXEQ_ALL];
       PB_CHK(mvec_get(qp->cE, qp->pf->m, c));
       for (int j = 0; j < qp->pf->m; j++) t[j] -= c[j];
     }
@@ -1176,6 +1158,7 @@ PetscErrorCode QPTOrthonormalizeEq(QP qp, MatOrthType type, MatOrthForm form)
   if (type == MAT_ORTH_NONE) return 0;
   if (type != MAT_ORTH_GS && type != MAT_ORTH_CHOLESKY) return err(PETSC_ERR_SUP, "QPTOrthonormalizeEq: the B200 path provides MAT_ORTH_GS and MAT_ORTH_CHOLESKY");
   if (qp->comm->size > 1) return err(PETSC_ERR_SUP, "QPTOrthonormalizeEq is single-GPU in this round");
+  if (qp->BE && qp->BE->M > PB_MAXEQ) return err(PETSC_ERR_SUP, "QPTOrthonormalizeEq handles at most %d equality rows (got %d)", PB_MAXEQ, (int)qp->BE->M);
   QPPF pf;
   PB_CHK(QPGetQPPF(qp, &pf));
   PB_CHK(QPPFSetUp(pf));
@@ -1219,7 +1202,7 @@ PetscErrorCode QPTOrthonormalizeEq(QP qp, MatOrthType type, MatOrthForm form)
     };
     for (int i = 0; i < m; i++) {
       double *q = TB->rows_d + (size_t)i * n;
-      double  d, norm, norm_last, dots[PB_MAXEQ];
+      double  d, norm, norm_last, dots[PB_MAXEQ_ALL];
       PB_CHK(dot(q, q, &d));
       norm = sqrt(d);
       do {
@@ -1247,7 +1230,7 @@ PetscErrorCode QPTOrthonormalizeEq(QP qp, MatOrthType type, MatOrthForm form)
   }
   Vec TcE = nullptr;
   if (qp->cE) {   // TcE = T*cE (:610-613)
-    double c[PB_MAXEQ], tc[PB_MAXEQ];
+    double c[PB_MAXEQ_ALL], tc[PB_MAXEQ_ALL];
     PB_CHK(mvec_get(qp->cE, m, c));
     for (int i = 0; i < m; i++) {
       double s2 = 0.0;
@@ -1340,7 +1323,7 @@ PetscErrorCode QPTEnforceEqByPenalty(QP qp, PetscReal rho_user, PetscBool rho_di
   if (qp->cE) {   // newb = b + rho BE' c  (:396-401)
     Vec newb;
     PB_CHK(VecDuplicate(qp->b, &newb));
-    double c[PB_MAXEQ];
+    double c[PB_MAXEQ_ALL];
     PB_CHK(QPPFSetUp(qp->pf));
     PB_CHK(mvec_get(qp->cE, qp->pf->m, c));
     PB_CHK(qppf_Gt_mult(qp->pf, c, newb));

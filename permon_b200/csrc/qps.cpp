@@ -544,7 +544,10 @@ struct MpgpImpl : QPSImpl {   // QPS_MPGP mpgpimpl.h:5-38
     if (exptype != QPS_MPGP_EXPANSION_STD || explengthtype != QPS_MPGP_EXPANSION_LENGTH_FIXED) return false;
     if (fallback || fallback2) return false;
     Mat A = qps->solQP->A;
-    if (A->kind == MK_PENALIZED) A = A->A;
+    if (A->kind == MK_PENALIZED) {
+      if (A->pf && A->pf->G && A->pf->G->M > PB_MAXEQ) return false;   // the rank-m fusion keeps PB_MAXEQ accumulators; more rows: un-fused route
+      A = A->A;
+    }
     if (A->kind == MK_PROD) return A->M1->kind == MK_AIJ && A->M2->kind == MK_AIJ && A->comm->size == 1;
     return A->kind == MK_AIJ;
   }
@@ -1330,12 +1333,9 @@ int SmalxeImpl::update_normBu(QPS qps, Vec u, double *nBu, double *en)
   int           m;
   PB_CHK(qppf_dense_rows(pf, &Bd, &m));
   PB_CHK(vec_dev_read(u, &du));
-  Reducer &R = reducer(qps->comm);
-  PB_CHK(k_dense_rows_mult(u->n, m, Bd, du, R.rb));
-  PB_CHK(R.gather());
-  PB_CHK(R.fetch());
-  double s = 0.0;
-  for (int j = 0; j < m; j++) s += R.sum(j) * R.sum(j);
+  double t[PB_MAXEQ_ALL], s = 0.0;
+  PB_CHK(dense_rows_mult_host(qps->comm, u->n, m, Bd, du, t));
+  for (int j = 0; j < m; j++) s += t[j] * t[j];
   *nBu = sqrt(s);
   *en  = *nBu / rtol_E;
   return 0;

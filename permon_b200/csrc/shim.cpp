@@ -324,6 +324,30 @@ int vec_host_rw(Vec v, double **h)
   return 0;
 }
 
+int dense_rows_mult_host(MPI_Comm comm, int n, int m, const double *Bd, const double *x, double *t)
+{
+  Reducer &R = reducer(comm);
+  for (int c = 0; c < m; c += PB_NRED) {
+    const int mc = std::min(PB_NRED, m - c);
+    PB_CHK(k_dense_rows_mult(n, mc, Bd + (size_t)c * n, x, R.rb));
+    PB_CHK(R.gather());
+    PB_CHK(R.fetch());
+    for (int j = 0; j < mc; j++) t[c + j] = R.sum(j);
+  }
+  return 0;
+}
+int dense_rows_multT_host(MPI_Comm comm, int n, int m, const double *Bd, const double *t, double scale, double *y, int accumulate)
+{
+  Reducer &R = reducer(comm);
+  if (m == 0 && !accumulate) return k_set(n, y, 0.0);
+  for (int c = 0; c < m; c += PB_NRED) {
+    const int mc = std::min(PB_NRED, m - c);
+    // t is pageable host memory: the copy is staged before the call returns, the chunk buffer can be reused right away on the stream
+    PB_CUDA(cudaMemcpyAsync(R.d_all, t + c, sizeof(double) * mc, cudaMemcpyHostToDevice, ctx().stream));
+    PB_CHK(k_dense_rows_multT_add(n, mc, Bd + (size_t)c * n, R.d_all, scale, y, (accumulate || c > 0) ? 1 : 0));
+  }
+  return 0;
+}
 int vec_dot(Vec x, Vec y, double *val)
 {
   if (x->n != y->n) return err(PETSC_ERR_ARG_INCOMP, "VecDot: local sizes differ (%d vs %d)", (int)x->n, (int)y->n);
@@ -990,8 +1014,11 @@ static int upload_stencil(pb::CsrDev &C, pb::StencilHost &st, int64_t nnz, doubl
   const double   t0 = wall_now();
   unsigned char *dm, *dp;
   pb::StPattern *dt;
-  PB_CHK(dmalloc(&dm, st.masks.size()));
-  PB_CHK(dmalloc(&dp, st.pid.size()));
+  // one spare (zero) tile behind both arrays: the two-rows-per-thread kernel walks pairs of tiles
+  PB_CHK(dmalloc(&dm, st.masks.size() + TR));
+  PB_CHK(dmalloc(&dp, st.pid.size() + 16));
+  PB_CUDA(cudaMemsetAsync(dm + st.masks.size(), 0, TR, s));
+  PB_CUDA(cudaMemsetAsync(dp + st.pid.size(), 0, 16, s));
   PB_CHK(dmalloc(&dt, st.pats.size()));
   PB_CUDA(cudaMemcpyAsync(dm, st.masks.data(), st.masks.size(), cudaMemcpyHostToDevice, s));
   PB_CUDA(cudaMemcpyAsync(dp, st.pid.data(), st.pid.size(), cudaMemcpyHostToDevice, s));
@@ -1743,16 +1770,9 @@ int mat_mult_dev(Mat A, const double *x, double *y)
     int           m;
     PB_CHK(qppf_dense_rows(A->pf, &Bd, &m));
     PB_CHK(mat_mult_dev(A->A, x, y));
-    Reducer &R = reducer(A->comm);
-    PB_CHK(k_dense_rows_mult(A->n, m, Bd, x, R.rb));
-    PB_CHK(R.gather());
-    // rank-ordered sum of the gathered records on the device is what the fused path does; here: host
-    PB_CHK(R.fetch());
-    double t[PB_MAXEQ];
-    for (int j = 0; j < m; j++) t[j] = R.sum(j);
-    double *dt = R.d_all;   // reuse as device scratch for the m coefficients
-    PB_CUDA(cudaMemcpyAsync(dt, t, sizeof(double) * m, cudaMemcpyHostToDevice, ctx().stream));
-    return k_dense_rows_multT_add(A->n, m, Bd, dt, A->rho, y, 1);
+    double t[PB_MAXEQ_ALL];
+    PB_CHK(dense_rows_mult_host(A->comm, A->n, m, Bd, x, t));                 // t = B x, rank-ordered sums
+    return dense_rows_multT_host(A->comm, A->n, m, Bd, t, A->rho, y, 1);      // y += rho B^T t
   }
   default: return err(PETSC_ERR_SUP, "MatMult: unsupported matrix kind for device vectors");
   }

@@ -15,20 +15,25 @@ def _ngpu():
     return api.device_count()
 
 
-@pytest.mark.parametrize("nproc,p2p", [(2, "1"), (2, "0"), (4, "1")])
+@pytest.mark.parametrize("nproc,p2p", [(2, "1"), (2, "0"), (4, "1"), (8, "1")])
 def test_row_partitioned_solves_match_oracle(nproc, p2p):
     """p2p=1: reduction records and halos are pushed through CUDA-IPC peer memory inside the kernels;
     p2p=0: NCCL all-gather / send-recv path"""
     if _ngpu() < nproc:
         pytest.skip(f"needs {nproc} GPUs")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nproc}", "--master-addr", "127.0.0.1", "--master-port", "29613",
-           os.path.join(ROOT, "tests", "mgpu_worker.py"), "obstacle2d,obstacle3d,varcoef3d,smalxe"]
+           os.path.join(ROOT, "tests", "mgpu_worker.py"), "obstacle2d,obstacle3d,varcoef3d,varcoef3d64t,smalxe"]
     p = subprocess.run(cmd, capture_output=True, text=True, timeout=900, env={**os.environ, "PERMON_B200_P2P": p2p})
     assert p.returncode == 0, p.stdout[-3000:] + p.stderr[-3000:]
     line = [l for l in p.stdout.splitlines() if l.startswith("MGPU_RESULT ")][-1]
     res = json.loads(line[len("MGPU_RESULT "):])
+    print("MGPU_RESULT", nproc, "ranks, p2p", p2p, json.dumps(res))
     for kind, r in res.items():
         assert r["reason"] == r["reason_ref"], (kind, r)
+        if kind == "varcoef3d64t":                    # truncated run: identical step kinds, tolerances at the cut
+            assert r["its"] == r["its_ref"] == 300 and r["counts"] == r["counts_ref"], (kind, r)
+            assert r["relx"] <= 1e-7 and r["relf"] <= 1e-10, (kind, r)
+            continue
         band = r["band"] or [r["its_ref"]]
         assert min(band) * 0.97 - 3 <= r["its"] <= max(band) * 1.03 + 3, (kind, r)
         assert r["relx"] <= (1e-7 if kind != "varcoef3d" else 1e-5), (kind, r)
