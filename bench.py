@@ -527,6 +527,143 @@ def measure(env, spec, K, W, want_e2e=True, want_cpu=True, want_parity=True, cpu
     return out
 
 
+# ----------------------------------------------------------------------------------------------------------
+# C4: SVM dual through SMALXE + MPGP, Hessian applied as two long-row SpMVs (BASELINE.json configs[3])
+# ----------------------------------------------------------------------------------------------------------
+def measure_c4(env, n, K, W, want_cpu=True, want_parity=True):
+    """min 1/2 a'(Z Z')a - 1'a, 0 <= a <= 1, y'a = 0; Z = diag(y) X, X n x n with n/1000 (at most 1000) non-zeros per row.  A step is one
+    INNER MPGP iteration of a bounded SMALXE window (1 outer iteration, K inner iterations; at n = d the dual is too ill-conditioned to
+    converge inside any bench window, in the oracle as well).  The dominant kernel is the long-row SpMV pair of the Hessian."""
+    P, torch, dev, stream = env.P, env.torch, env.dev, env.stream
+    from permon_b200 import problems as PR
+    t0 = time.time()
+    k = max(1, min(1000, n // 100))
+    pr = PR.svm_dual_fast(n, n, nnz_per_row=k)
+    t_gen = time.time() - t0
+    nnz = len(pr.a)
+    peak, peak_src = peaks()
+
+    def build(host_side):
+        h = {}
+        h["A1"] = P.MatCreateAIJ(pr.ia, pr.ja, pr.a, ncols_local=n)
+        h["A2"] = P.MatCreateAIJ(pr.second[0], pr.second[1], pr.second[2], ncols_local=n)
+        h["A"] = P.MatCreateProd([h["A2"], h["A1"]])
+        h["xh"] = np.zeros(n)
+        h["b"], h["x"] = P.VecFromArray(np.ones(n)), P.VecFromArray(h["xh"])
+        h["lb"], h["ub"] = P.VecFromArray(np.zeros(n)), P.VecFromArray(np.full(n, 1.0))
+        h["brow"] = P.VecFromArray(pr.B[0].copy())
+        h["BE"] = P.MatCreateOneRow(h["brow"])
+        qp = P.QPCreate()
+        P.QPSetOperator(qp, h["A"]); P.QPSetRhs(qp, h["b"]); P.QPSetInitialVector(qp, h["x"]); P.QPSetBox(qp, None, h["lb"], h["ub"]); P.QPSetEq(qp, h["BE"], None)
+        qps = P.QPSCreate()
+        P.QPSSetType(qps, "smalxe"); P.QPSSetQP(qps, qp); P.QPSSetAutoPostSolve(qps, False)
+        h["qp"], h["qps"] = qp, qps
+        return h
+
+    def destroy(h):
+        P.QPSDestroy(h["qps"]); P.QPDestroy(h["qp"])
+        for kk in ("b", "x", "lb", "ub", "brow"):
+            P.VecDestroy(h[kk])
+        for kk in ("BE", "A", "A2", "A1"):
+            P.MatDestroy(h[kk])
+
+    def window(h, iters):
+        P.options_clear()
+        P.call("PetscOptionsInsertString", None, f"-qps_max_it 1 -smalxe_qps_max_it {iters - 1} -qps_rtol 1e-30 -smalxe_qps_rtol 1e-30".encode())
+        P.QPSSetFromOptions(h["qps"])
+
+    # ---- Hessian application alone (the two long-row SpMVs)
+    h = build(False)
+    storage = [P.MatStorageInfo(h["A1"]), P.MatStorageInfo(h["A2"])]
+    vx, vy = P.VecFromArray(np.random.default_rng(0).standard_normal(n)), P.VecCreate(n)
+    for _ in range(3):
+        P.MatMult(h["A"], vx, vy)
+    reps = 20
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record(stream)
+    for _ in range(reps):
+        P.MatMult(h["A"], vx, vy)
+    e1.record(stream)
+    torch.cuda.synchronize()
+    ms_mult = e0.elapsed_time(e1) / reps
+    bytes_mult = sum(st["stream_bytes"] for st in storage) + 8 * n * 4       # two matrix streams, x, t (written + read), y
+    P.VecDestroy(vx); P.VecDestroy(vy)
+    # ---- device-resident window: set-up outside, K inner iterations timed
+    window(h, W)
+    P.QPSSetUp(h["qps"])
+    P.QPSSolve(h["qps"])                                                       # warm-up window
+    inner = P.QPSSMALXEGetInnerQPS(h["qps"])
+    maxeig_inner = P.QPSMPGPGetOperatorMaxEigenvalue(inner)
+    P.VecSetArray(h["x"], np.zeros(n))
+    window(h, K)
+    st0 = P.QPSSMALXEGetStatistics(h["qps"])["inner_iter_accu"]
+    launches0 = P.launch_count()
+    torch.cuda.synchronize()
+    e0.record(stream)
+    P.QPSSolve(h["qps"])
+    e1.record(stream)
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    launches = P.launch_count() - launches0
+    its = P.QPSSMALXEGetStatistics(h["qps"])["inner_iter_accu"]
+    counts = P.QPSMPGPGetStepCounts(inner)
+    value = its / (ms * 1e-3)
+    destroy(h)
+    torch.cuda.empty_cache()
+    # ---- e2e: host arrays -> upload (+ tile-ELL re-layout on the device) -> set-up (two power methods) -> K inner iterations -> download
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    h2 = build(True)
+    window(h2, K)
+    P.QPSSolve(h2["qps"])
+    P.VecSyncToHost(h2["x"])
+    torch.cuda.synchronize()
+    te = time.perf_counter() - t0
+    its2 = P.QPSSMALXEGetStatistics(h2["qps"])["inner_iter_accu"]
+    host_in = 2 * (12 * nnz + 4 * (n + 1)) + 8 * n * 5
+    e2e = dict(value=its2 / te, unit=UNIT, h2d_bytes_per_step=host_in / max(its2, 1), d2h_bytes_per_step=8 * n / max(its2, 1), seconds=round(te, 3),
+               note="host CSR of both factors + vectors -> upload, tile-ELL re-layout on the device, SMALXE set-up (two power methods), K inner iterations, download of x")
+    # ---- oracle: bounded sample + parity at the cut
+    cpu, parity = None, None
+    if want_cpu or want_parity:
+        from oracle import oracle_py as O
+        threads = os.cpu_count() or 1
+        Kc = max(3, min(K, int(25.0 / max(1e-9, 6.0e-10 * 2 * nnz * 16.0 / max(threads, 1)))))
+        P.VecSetArray(h2["x"], np.zeros(n))
+        window(h2, Kc)
+        P.QPSSolve(h2["qps"])
+        P.VecSyncToHost(h2["x"])
+        torch.cuda.synchronize()
+        x_gpu = h2["xh"].copy()
+        c_gpu = P.QPSMPGPGetStepCounts(P.QPSSMALXEGetInnerQPS(h2["qps"]))
+        op = O.Operator(pr.ia, pr.ja, pr.a, second=pr.second)
+        bx = O.BoxC(n, pr.lb, pr.ub)
+        maxeig = P.MatGetMaxEigenvalue(h2["A"])
+        xr, ro = O.smalxe_solve(op, pr.b, bx, pr.B, None, pr.x0,
+                                O.smalxe_opts(inner=dict(nthreads=threads, max_it=Kc - 1, rtol=1e-30, maxeig=maxeig_inner), max_it=1, rtol=1e-30, maxeig=maxeig))
+        if want_cpu:
+            cpu = dict(value=round(ro["inner_its_accu"] / ro["seconds"], 3), unit=UNIT, cores=threads, kind="port", seconds=round(ro["seconds"], 2),
+                       sample=f"{ro['inner_its_accu']} inner MPGP iterations of one SMALXE outer iteration on the full-size problem ({n} x {n}, {nnz} non-zeros per factor), "
+                              f"{threads} OpenMP threads; eigenvalue estimates handed over from the GPU run (the two power methods alone would take minutes on the CPU)")
+        if want_parity:
+            nx = float(np.linalg.norm(xr))
+            parity = dict(iterations=int(ro["inner_its_accu"]), relx=float(np.linalg.norm(x_gpu - xr) / max(nx, 1e-300)),
+                          step_mix_gpu={kk: int(c_gpu[kk]) for kk in ("ncg", "nexp", "nprop", "nmv")},
+                          step_mix_cpu={kk: int(ro[kk]) for kk in ("ncg", "nexp", "nprop", "nmv")}, tolerances=dict(relx=1e-7))
+            parity["step_mix_equal"] = parity["step_mix_gpu"] == parity["step_mix_cpu"]
+            parity["ok"] = bool(parity["relx"] <= 1e-7 and parity["step_mix_equal"])
+    destroy(h2)
+    gbs = bytes_mult / (ms_mult * 1e-3) / 1e9
+    roofline = dict(bound="hbm", kernel="long-row SpMV pair (Hessian Z Z^T)", achieved=round(gbs, 1), peak=peak, unit="GB/s", frac=round(gbs / peak, 4), traffic=None,
+                    peak_source=peak_src, launches=reps, avg_launch_ms=round(ms_mult, 4), algorithmic_bytes_per_launch=int(bytes_mult), matrix_storage=storage)
+    return dict(value=round(value, 2), unit=UNIT, ms_per_step=round(ms / max(its, 1), 5), steps=int(its), warmup=W,
+                config=dict(workload=f"C4 SVM dual {n} x {n}, {k} non-zeros per row ({nnz / 1e6:.0f}M per factor), SMALXE + MPGP, Hessian = two long-row SpMVs", n=n, nnz=2 * nnz,
+                            l2="inputs larger than L2 (each factor streams 12 B per non-zero)"),
+                details=dict(step_mix=counts, inner_iterations=int(its), maxeig_inner=maxeig_inner, generate_s=round(t_gen, 1)),
+                e2e=e2e, gpu_launches=int(launches), roofline=roofline, cpu_baseline=cpu, parity=parity)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -539,12 +676,13 @@ def main():
     ap.add_argument("--no-parity", action="store_true")
     ap.add_argument("--no-c2", action="store_true", help="N = 1, workload auto: skip the nested C2 object")
     ap.add_argument("--cpu-budget", type=float, default=20.0)
+    ap.add_argument("--c4-n", type=int, default=1_000_000, help="--workload c4: rows = columns of X (BASELINE config 4: 1M)")
     args = ap.parse_args()
     K, W = max(1, args.steps), max(3, args.warmup)
     rank = int(os.environ.get("RANK", "0"))
     size = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    spec = workload_spec(args.workload)
+    spec = workload_spec(args.workload if args.workload != "c4" else "c3")
 
     if args.impl == "reference":
         # the reference's own CPU implementation cannot be built here (PETSc/MPI absent): time the oracle port on all host cores.
@@ -597,6 +735,14 @@ def main():
 
     sampler = ClockSampler(local_rank)
     sampler.start()
+    if args.workload == "c4":
+        assert size == 1, "the C4 product operator is single-GPU"
+        res = measure_c4(env, args.c4_n, K, W, want_cpu=not args.no_cpu_baseline, want_parity=not args.no_parity)
+        line = dict(metric=METRIC, value=res["value"], unit=UNIT, n_gpus=1, steps=res["steps"], warmup=W, ms_per_step=res["ms_per_step"], higher_is_better=True,
+                    scaling="strong", vs_baseline=None, dtype="f64", data="synthetic", config=res["config"], details=res["details"], clocks=sampler.stop(),
+                    e2e=res["e2e"], gpu_launches=res["gpu_launches"], roofline=res["roofline"], cpu_baseline=res["cpu_baseline"], parity=res["parity"])
+        print(json.dumps(line), flush=True)
+        return
     res = measure(env, spec, K, W, want_e2e=not args.no_e2e, want_cpu=not args.no_cpu_baseline, want_parity=not args.no_parity,
                   cpu_budget=args.cpu_budget, sampler=sampler)
     clocks = sampler.stop()

@@ -160,6 +160,14 @@ struct CsrDev {
   const unsigned char *st_pid = nullptr;     // [ntiles] pattern of each tile
   const StPattern     *st_pats = nullptr;
   int                  st_npat = 0, st_nwin = 0, st_lmax = 0;   // patterns; largest number of windows of a pattern; longest pattern
+  // long-row matrices in tile-ELL form (kind 5): 256-row tiles stored COLUMN-major (entry t of all rows of the tile is contiguous), one
+  // thread per row -- unit-stride matrix stream, products added in storage order
+  const double *ell_val = nullptr;
+  const int    *ell_col = nullptr;
+  const int    *ell_len = nullptr;     // [n] row lengths
+  const int    *ell_lt  = nullptr;     // [ntiles] longest row of each tile
+  const int64_t *ell_off = nullptr;    // [ntiles] first element of each tile in ell_val / ell_col
+  int64_t       ell_elems = 0;         // elements stored (padding included)
   int           W      = 32;
   int           tile_cap = 0;      // max nnz of a 256-row tile (stream kind)
   int           grid   = 0;        // persistent grid size (fixed => reproducible reductions)
@@ -313,6 +321,7 @@ int k_pack(int n, const int *idx, const double *x, double *buf);
 
 double csr_stream_bytes(const CsrDev &A);   // bytes one SpMV must read for the matrix itself (CSR: 12 nnz + 4(n+1); packed: blob + directory)
 int  spmv_config(CsrDev &A, const int *h_ia);   // picks kind / W / grid from the host row pointer
+int  csr_to_tile_ell(CsrDev &A, const int *h_ia);   // long-row matrices: re-lay the uploaded CSR out as tile-ELL (kind 5) on the device
 int  elementwise_grid();
 int  fused_C_grid(int n);   // CTAs of K_C for n local rows (K_A adds that many partial sums of g.p)
 int  max_red_blocks();

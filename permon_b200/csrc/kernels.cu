@@ -1536,6 +1536,119 @@ static void launch_vector(const CsrDev &A, const double *x, const Epi &epi)
 }
 
 
+
+// ---- long rows (SVM factors: ~1000 non-zeros per row): tile-ELL -----------------------------------------------------------------
+// The lanes-per-row kernel reads a row with unit stride but gathers x with one 32-byte sector per non-zero from L2 (2.7x the matrix
+// stream at C4).  Here a tile of 256 rows is stored column-major, one thread owns a row: entry t of 32 rows is one 256-byte line of values
+// and one 128-byte line of columns, the gathers of a warp at step t fall into the same column neighbourhood when the rows are similar
+// (sorted columns: the t-th entry of every row sits near t/len of the column range), and the products are added in storage order.
+static constexpr int ELL_U = 8;
+template <class Epi>
+__global__ void __launch_bounds__(NT, 3) k_spmv_ell(CsrDev A, const double *__restrict__ x, Epi epi)
+{
+  pdl_enter();
+  if (!epi.active()) return;
+  typename Epi::Acc acc;
+  epi.init(acc);
+  const int ntiles = (A.n + TR - 1) / TR;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int     r = tile * TR + threadIdx.x;
+    const int     len = (r < A.n) ? __ldg(A.ell_len + r) : 0;
+    const int     lt = __ldg(A.ell_lt + tile);
+    const double *val = A.ell_val + __ldg(A.ell_off + tile) + threadIdx.x;
+    const int    *col = A.ell_col + __ldg(A.ell_off + tile) + threadIdx.x;
+    double        s = 0.0;
+    for (int t = 0; t < lt; t += ELL_U) {
+      int    c[ELL_U];
+      double v[ELL_U], xv[ELL_U];
+#pragma unroll
+      for (int j = 0; j < ELL_U; j++) {
+        const bool on = t + j < len;
+        c[j]          = on ? __ldcs(col + (size_t)(t + j) * TR) : 0;
+        v[j]          = on ? __ldcs(val + (size_t)(t + j) * TR) : 0.0;
+      }
+#pragma unroll
+      for (int j = 0; j < ELL_U; j++) xv[j] = (t + j < len) ? __ldg(x + c[j]) : 0.0;
+#pragma unroll
+      for (int j = 0; j < ELL_U; j++)
+        if (t + j < len) s += v[j] * xv[j];
+    }
+    if (r < A.n) epi.row(r, s, acc);
+  }
+  epi.finalize(acc);
+}
+
+template <class Epi>
+static void launch_ell(const CsrDev &A, const double *x, const Epi &epi)
+{
+  static int occ = 0;
+  if (!occ) occ = occ_blocks(k_spmv_ell<Epi>, 0);
+  int ntiles = (A.n + TR - 1) / TR, grid = g_ctx.sm_count * occ;
+  if (grid > ntiles) grid = ntiles;
+  if (grid > max_red_blocks()) grid = max_red_blocks();
+  if (grid < 1) grid = 1;
+  launch_k(k_spmv_ell<Epi>, grid, NT, 0, A, x, epi);
+}
+
+// CSR -> tile-ELL on the device: one CTA per tile, thread r walks its row and scatters it into the column-major tile
+__global__ void __launch_bounds__(NT) k_csr_to_ell(int n, const int *__restrict__ ia, const int *__restrict__ ja, const double *__restrict__ a, const int64_t *__restrict__ off,
+                                                   const int *__restrict__ lt, double *__restrict__ ev, int *__restrict__ ec, int *__restrict__ elen)
+{
+  const int tile = blockIdx.x, r = tile * TR + threadIdx.x;
+  const int L = lt[tile];
+  const int k0 = (r < n) ? ia[r] : 0, len = (r < n) ? ia[r + 1] - k0 : 0;
+  if (r < n) elen[r] = len;
+  double *v = ev + off[tile] + threadIdx.x;
+  int    *c = ec + off[tile] + threadIdx.x;
+  for (int t = 0; t < L; t++) {
+    v[(size_t)t * TR] = (t < len) ? a[k0 + t] : 0.0;
+    c[(size_t)t * TR] = (t < len) ? ja[k0 + t] : 0;
+  }
+}
+int csr_to_tile_ell(CsrDev &A, const int *h_ia)
+{
+  const int ntiles = (A.n + TR - 1) / TR;
+  if (ntiles == 0 || !A.ia || !A.ja || !A.a) return 0;
+  std::vector<int64_t> off((size_t)ntiles);
+  std::vector<int>     lt((size_t)ntiles);
+  int64_t              tot = 0;
+  for (int t = 0; t < ntiles; t++) {
+    int L = 0;
+    for (int r = t * TR; r < std::min(A.n, (t + 1) * TR); r++) L = std::max(L, h_ia[r + 1] - h_ia[r]);
+    L      = (L + ELL_U - 1) / ELL_U * ELL_U;
+    lt[t]  = L;
+    off[t] = tot;
+    tot += (int64_t)L * TR;
+  }
+  if (tot > (int64_t)(1.3 * (double)A.nnz) + 65536) return 0;   // ragged rows: the padding would cost more than it saves
+  double  *ev;
+  int     *ec, *el, *dlt;
+  int64_t *doff;
+  PB_CHK(dmalloc(&ev, (size_t)tot));
+  PB_CHK(dmalloc(&ec, (size_t)tot));
+  PB_CHK(dmalloc(&el, (size_t)std::max(A.n, 1)));
+  PB_CHK(dmalloc(&dlt, (size_t)ntiles));
+  PB_CHK(dmalloc(&doff, (size_t)ntiles));
+  PB_CUDA(cudaMemcpyAsync(dlt, lt.data(), sizeof(int) * (size_t)ntiles, cudaMemcpyHostToDevice, g_ctx.stream));
+  PB_CUDA(cudaMemcpyAsync(doff, off.data(), sizeof(int64_t) * (size_t)ntiles, cudaMemcpyHostToDevice, g_ctx.stream));
+  k_csr_to_ell<<<ntiles, NT, 0, g_ctx.stream>>>(A.n, A.ia, A.ja, A.a, doff, dlt, ev, ec, el);
+  LAUNCH_CHECK();
+  PB_CUDA(cudaStreamSynchronize(g_ctx.stream));   // lt / off are locals
+  dfree(A.ia);
+  dfree(A.ja);
+  dfree(A.a);
+  A.ia = A.ja = nullptr;
+  A.a  = nullptr;
+  A.ell_val   = ev;
+  A.ell_col   = ec;
+  A.ell_len   = el;
+  A.ell_lt    = dlt;
+  A.ell_off   = doff;
+  A.ell_elems = tot;
+  A.kind      = 5;
+  return 0;
+}
+
 template <class Epi, class = void>
 struct EpiHasStaged : std::false_type {};
 template <class Epi>
@@ -1703,8 +1816,8 @@ static int launch_sd_l(const CsrDev &A, const double *x, const Epi &epi, TileOrd
   }
   static int pairs = -1;
   if (pairs < 0) {
-    const char *e = getenv("PERMON_B200_SD_PAIRS");
-    pairs = (e && e[0] == '0') ? 0 : 1;
+    const char *e = getenv("PERMON_B200_SD_PAIRS");   // measured on C2 / C3: one row per thread is 2-10 % faster (more warps in flight); pairs stay selectable
+    pairs = (e && e[0] == '1') ? 1 : 0;
   }
   if (pairs && (A.n % 2 == 0) && aligned16(x) && epi.pair_ok()) {
     // two adjacent rows per thread, 16-byte accesses
@@ -1772,6 +1885,8 @@ static int launch_spmv(const CsrDev &A, const double *x, const Epi &epi, int fam
   if (A.n == 0) {
     // still run one CTA so that reductions publish their (identity) record
     k_spmv_vector<Epi, 32><<<1, NT, 0, g_ctx.stream>>>(A, x, epi);
+  } else if (A.kind == 5) {
+    launch_ell(A, x, epi);
   } else if (A.kind == 4) {
     static int direct = -1;
     if (direct < 0) {
@@ -1814,6 +1929,7 @@ static int launch_spmv(const CsrDev &A, const double *x, const Epi &epi, int fam
 double csr_stream_bytes(const CsrDev &A)
 {
   if (A.kind == 3 || A.kind == 4) return (double)A.pk_bytes;
+  if (A.kind == 5) return 12.0 * (double)A.ell_elems + 4.0 * A.n;
   return 12.0 * (double)A.nnz + 4.0 * (A.n + 1);
 }
 

@@ -961,6 +961,11 @@ _p_Mat::~_p_Mat()
     pb::dfree(Ad.st_masks);
     pb::dfree(Ad.st_pid);
     pb::dfree(Ad.st_pats);
+    pb::dfree(Ad.ell_val);
+    pb::dfree(Ad.ell_col);
+    pb::dfree(Ad.ell_len);
+    pb::dfree(Ad.ell_lt);
+    pb::dfree(Ad.ell_off);
   }
   if (kind == MK_DENSEROWS) pb::dfree(rows_d);
   if (kind == MK_AIJ) {
@@ -1114,6 +1119,8 @@ static int upload_csr(pb::CsrDev &C, int nrows, int ncols, const int *ia, const 
   C.ia = dia;
   C.ja = dja;
   C.a  = da;
+  // long rows (vector kind): tile-ELL when the rows of a tile are of similar length; PERMON_B200_SPMV=vector keeps the lanes-per-row kernel
+  if (C.kind == 1 && !rows && nnz >= (1 << 20) && !getenv("PERMON_B200_SPMV") && !getenv("PERMON_B200_NOELL")) PB_CHK(pb::csr_to_tile_ell(C, ia));
   return 0;
 }
 

@@ -129,7 +129,7 @@ def test_vec_and_qpc_kernels(P):
         P.QPCDestroy(q)
 
 
-@pytest.mark.parametrize("kind", ["stencil5", "stencil7", "longrows", "empty_rows"])
+@pytest.mark.parametrize("kind", ["stencil5", "stencil7", "longrows", "longrows_ell", "longrows_ell_ragged", "empty_rows"])
 def test_spmv_against_oracle(P, kind):
     import scipy.sparse as sp
     rng = np.random.default_rng(2)
@@ -143,6 +143,16 @@ def test_spmv_against_oracle(P, kind):
         S = sp.random(2000, 3000, density=0.1, random_state=3, format="csr")
         S.sort_indices()
         ia, ja, a, n, m = S.indptr, S.indices, S.data, 3000, 2000
+    elif kind.startswith("longrows_ell"):
+        # > 1M non-zeros in long rows: re-laid out as tile-ELL on the device (kind 5); products are added in storage order there, so the
+        # result equals the oracle's running sum bit for bit up to FMA contraction.  "ragged": row lengths 300..500, a partial last tile
+        nrow = 3000 if kind == "longrows_ell" else 3100
+        S = sp.random(nrow, 4000, density=0.1, random_state=5, format="csr")
+        if kind == "longrows_ell_ragged":
+            keep = rng.random(S.nnz) < np.repeat(0.75 + 0.25 * rng.random(nrow), np.diff(S.indptr))
+            S = sp.csr_matrix((S.data[keep], S.indices[keep], np.concatenate([[0], np.cumsum(np.add.reduceat(keep, S.indptr[:-1]))])), shape=S.shape)
+        S.sort_indices()
+        ia, ja, a, n, m = S.indptr, S.indices, S.data, 4000, nrow
     else:
         S = sp.random(5000, 5000, density=0.0004, random_state=4, format="csr")   # many empty rows
         S.sort_indices()
