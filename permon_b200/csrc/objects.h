@@ -59,6 +59,7 @@ struct _p_Vec : PObj {
   bool     invalidated = false;
   int64_t  state = 0;
   cudaEvent_t up_ev = nullptr;   // a prefetch (H2D on the copy stream) is in flight: settled by the next access
+  bool        h2d_inflight = false;   // an asynchronous upload FROM the host buffer was enqueued on the compute stream: a host writer must wait for it
   ~_p_Vec() override;
 };
 

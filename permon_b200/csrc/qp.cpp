@@ -1301,10 +1301,21 @@ PetscErrorCode QPTEnforceEqByPenalty(QP qp, PetscReal rho_user, PetscBool rho_di
     pb::unref(qp->cE);
     return 0;
   }
-  double rho;
+  if (qp->cE) {   // qptransform.c:352-360
+    bool flg = false;
+    options_bool("", "-qpt_homogenize_eq_always", &flg);
+    if (flg) {
+      PB_CHK(QPTHomogenizeEq(qp));
+      PB_CHK(QPChainGetLast(qp, &qp));
+    }
+  }
+  double   rho, maxeig_tol = PETSC_DECIDE;
+  PetscInt maxeig_iter = PETSC_DECIDE;
+  options_real("", "-qpt_penalize_maxeig_tol", &maxeig_tol);    // :362-363
+  options_int("", "-qpt_penalize_maxeig_iter", &maxeig_iter);
   if (!rho_direct) {
     double maxeig;
-    PB_CHK(MatGetMaxEigenvalue(qp->A, NULL, &maxeig, PETSC_DECIDE, PETSC_DECIDE));
+    PB_CHK(MatGetMaxEigenvalue(qp->A, NULL, &maxeig, maxeig_tol, maxeig_iter));
     rho = rho_user * maxeig;
   } else {
     rho = rho_user;

@@ -241,7 +241,8 @@ PetscErrorCode QPSSetTolerances(QPS qps, PetscReal rtol, PetscReal atol, PetscRe
     if (maxits < 0) return err(PETSC_ERR_ARG_OUTOFRANGE, "Maximum number of iterations %d must be non-negative", (int)maxits);
     qps->max_it = maxits;
   }
-  if (qps->convergencetest == QPSConvergedDefault && qps->cnvctx) ((QPSConvergedDefaultCtx *)qps->cnvctx)->setup_called = false;
+  // as in the reference (qps.c:793-830) the cached ttol / norm_rhs_div of QPSConvergedDefaultCtx are NOT invalidated here: they are
+  // computed once, at the first convergence test after QPSConvergedDefaultCreate (qps.c:686,723-728)
   return 0;
 }
 PetscErrorCode QPSGetTolerances(QPS qps, PetscReal *rtol, PetscReal *atol, PetscReal *dtol, PetscInt *maxits)

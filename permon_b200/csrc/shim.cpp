@@ -260,8 +260,12 @@ int vec_dev_read(Vec v, const double **d)
   PB_CHK(vec_settle(v, false));
   PB_CHK(vec_alloc_dev(v));
   if (!v->d_valid) {
-    if (v->h_valid) PB_CUDA(cudaMemcpyAsync(v->d, v->h, sizeof(double) * (size_t)v->n, cudaMemcpyHostToDevice, ctx().stream));
-    else PB_CUDA(cudaMemsetAsync(v->d, 0, sizeof(double) * (size_t)v->n, ctx().stream));
+    if (v->h_valid) {
+      PB_CUDA(cudaMemcpyAsync(v->d, v->h, sizeof(double) * (size_t)v->n, cudaMemcpyHostToDevice, ctx().stream));
+      v->h2d_inflight = true;   // pinned host buffers: the DMA really is asynchronous
+    } else {
+      PB_CUDA(cudaMemsetAsync(v->d, 0, sizeof(double) * (size_t)v->n, ctx().stream));
+    }
     v->d_valid = true;
   }
   *d = v->d;
@@ -307,7 +311,8 @@ int vec_host_write(Vec v, double **h)
 {
   PB_CHK(vec_settle(v, true));
   PB_CHK(vec_alloc_host(v));
-  if (v->d_valid && ctx().ready) PB_CUDA(cudaStreamSynchronize(ctx().stream));   // pending device readers of the old contents
+  if ((v->d_valid || v->h2d_inflight) && ctx().ready) PB_CUDA(cudaStreamSynchronize(ctx().stream));   // pending device readers / an upload still reading the host buffer
+  v->h2d_inflight = false;
   v->h_valid = true;
   v->d_valid = false;
   v->state++;
@@ -318,6 +323,10 @@ int vec_host_rw(Vec v, double **h)
 {
   const double *c;
   PB_CHK(vec_host_read(v, &c));
+  if (v->h2d_inflight && ctx().ready) {   // the caller is about to WRITE the buffer an asynchronous upload may still be reading
+    PB_CUDA(cudaStreamSynchronize(ctx().stream));
+    v->h2d_inflight = false;
+  }
   v->d_valid = false;
   v->state++;
   *h = v->h;
@@ -1363,10 +1372,16 @@ PetscErrorCode MatCreateMPIAIJWithArrays(MPI_Comm comm, PetscInt m, PetscInt n, 
       }
       off += cnt;
     }
-    // symmetric sparsity is assumed (Hessians are symmetric): the ranks I receive from are the ranks I send to
-    if (sneigh != H->neigh) {
-      delete A;
-      return err(PETSC_ERR_SUP, "non-symmetric halo pattern (send and receive neighbour sets differ)");
+    // symmetric sparsity is assumed (Hessians are symmetric); every rank must take the same exit, or the others would hang in the next
+    // collective: agree on the flag first, then free the object through the normal destructor (halo plan and host split included)
+    std::vector<int64_t> oks(size);
+    if (comm->agi(comm->agctx, (int64_t)(sneigh == H->neigh), oks.data())) return err(PETSC_ERR_LIB, "host all-gather failed");
+    bool all_ok = true;
+    for (int r = 0; r < size; r++) all_ok = all_ok && oks[r];
+    if (!all_ok) {
+      Mat tmp = A;
+      MatDestroy(&tmp);
+      return err(PETSC_ERR_SUP, "non-symmetric halo pattern (send and receive neighbour sets differ on some rank)");
     }
     H->send_off = soff;
     H->send_idx = sidx;

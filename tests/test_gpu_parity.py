@@ -166,6 +166,8 @@ def test_spmv_against_oracle(P, kind):
     y = P.VecGetArray(vy)
     scale = np.abs(sp.csr_matrix((np.abs(a), ja, ia), shape=(m, n)) @ np.abs(x)) + 1e-300
     assert np.max(np.abs(y - y_ref) / scale) <= 1e-15
+    if kind.startswith("longrows_ell"):
+        assert P.MatStorageInfo(A)["kind"] == 5
     P.VecDestroy(vx), P.VecDestroy(vy), P.MatDestroy(A)
 
 
