@@ -20,6 +20,7 @@
 //   MPGP step formulas  src/qps/impls/mpgp/mpgp.c:299-323 (expansion), :553-560 (CG), :623-638 (proportioning)
 #include <climits>
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>
 #include <stdarg.h>
 #include <stddef.h>
 #include <stdio.h>
@@ -155,6 +156,7 @@ static double phase_now()
 }
 PhaseTimer::PhaseTimer(const char *nm) : name(nm), t0(0.0), on(false)
 {
+  nvtxRangePushA(nm);   // NVTX range of every phase (header-only NVTX3: a no-op unless a profiler injects itself)
   static const bool enabled = getenv("PERMON_B200_TIMING") != nullptr;
   on = enabled;
   if (on) {
@@ -164,6 +166,7 @@ PhaseTimer::PhaseTimer(const char *nm) : name(nm), t0(0.0), on(false)
 }
 PhaseTimer::~PhaseTimer()
 {
+  nvtxRangePop();
   if (!on) return;
   if (g_ctx.ready) cudaDeviceSynchronize();
   fprintf(stderr, "[permon_b200 timing] %-44s %9.2f ms\n", name, 1e3 * (phase_now() - t0));
