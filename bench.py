@@ -32,6 +32,12 @@ import sys
 import threading
 import time
 
+# torchrun exports OMP_NUM_THREADS=1 to every rank "to avoid overloading the system" and asks the application to tune it: the host side
+# of the e2e leg (diagonal / off-diagonal split and re-coding of this rank's rows) is an OpenMP region, so the ranks of one node share
+# the host cores evenly.  Must happen before the OpenMP runtime starts (numpy / torch / the library).
+if int(os.environ.get("WORLD_SIZE", "1")) > 1 and os.environ.get("OMP_NUM_THREADS", "1") == "1" and not os.environ.get("PERMON_B200_KEEP_OMP"):
+    os.environ["OMP_NUM_THREADS"] = str(max(1, (os.cpu_count() or 1) // int(os.environ.get("LOCAL_WORLD_SIZE", os.environ["WORLD_SIZE"]))))
+
 import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -321,7 +327,7 @@ def measure(env, spec, K, W, want_e2e=True, want_cpu=True, want_parity=True, cpu
                 h[k] = P.VecFromDevicePointer(d[k].data_ptr(), n_loc)
             h["dev"] = d
         else:
-            h["xh"] = torch.zeros(n_loc, dtype=torch.float64).pin_memory()
+            h["xh"] = xh_pinned                       # the caller's x buffer (x0 in, solution out): pinned host memory that exists before the timed region
             h["A"] = P.MatCreateAIJ(host["ia"].numpy(), host["ja"].numpy(), host["a"].numpy(), ncols_local=n_loc)
             for k in vec_keys:
                 h[k] = P.VecFromArray(host[k].numpy())
@@ -437,6 +443,7 @@ def measure(env, spec, K, W, want_e2e=True, want_cpu=True, want_parity=True, cpu
     if want_e2e or want_parity:
         host_in = sum(host[k].numel() * host[k].element_size() for k in host) + n_loc * 8      # CSR + b, bounds, x0 handed over in host memory
         d2h = n_loc * 8
+        xh_pinned = torch.zeros(n_loc, dtype=torch.float64).pin_memory()      # host input like ia / ja / a / b / lb (page-locking 1 GB takes ~0.4 s)
         barrier()
         t0 = time.perf_counter()
         h2 = make_solver(False)
@@ -730,8 +737,11 @@ def main():
             dist.all_reduce(t)
             return t.cpu().tolist()
         env.all_gather_int = all_gather_int
-    env.stream = torch.cuda.current_stream()
-    P.set_stream(env.stream.cuda_stream)
+    # CUDA events must be recorded on the stream the kernels are launched on: torch's current stream becomes the library's stream
+    # (a null stream handed to PermonB200SetStream would select the library's own non-blocking stream, which events on torch's
+    # default stream do not see)
+    env.stream = torch.cuda.ExternalStream(P.get_stream(), device=dev)
+    torch.cuda.set_stream(env.stream)
 
     sampler = ClockSampler(local_rank)
     sampler.start()

@@ -127,6 +127,13 @@ def set_stream(ptr):
     call("PermonB200SetStream", C.c_void_p(ptr))
 
 
+def get_stream() -> int:
+    """the CUDA stream the library launches on (its own non-blocking stream unless PermonB200SetStream handed it another)"""
+    s = C.c_void_p()
+    call("PermonB200GetStream", C.byref(s))
+    return int(s.value or 0)
+
+
 def synchronize():
     call("PermonB200Synchronize")
 

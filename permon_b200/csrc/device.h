@@ -160,6 +160,7 @@ struct CsrDev {
   const unsigned char *st_pid = nullptr;     // [ntiles] pattern of each tile
   const StPattern     *st_pats = nullptr;
   int                  st_npat = 0, st_nwin = 0, st_lmax = 0;   // patterns; largest number of windows of a pattern; longest pattern
+  int                  st_dlo = 0, st_dhi = 0;                  // smallest / largest col - row over all patterns
   // long-row matrices in tile-ELL form (kind 5): 256-row tiles stored COLUMN-major (entry t of all rows of the tile is contiguous), one
   // thread per row -- unit-stride matrix stream, products added in storage order
   const double *ell_val = nullptr;
@@ -252,6 +253,8 @@ struct GhostMerge {
 // sweep direction of the iteration says so), then the tiles outside that range
 struct TileOrder {
   int ta = 0, tb = 0;
+  int pf = 0;        // direct stencil kernels: L2 prefetch distance in grid sweeps (0: off)
+  int dlo = 0, dhi = 0;   // smallest / largest col - row of the stencil patterns (the gather that touches a line first, per sweep direction)
 };
 
 // ---- kernels: generic vector ops (deterministic) -----------------------------------------------------

@@ -1375,6 +1375,33 @@ __device__ __forceinline__ double sd_row(int L, uint32_t m, const StPattern &P, 
   return s;
 }
 
+// L2 prefetch of what a future tile of this CTA will read from DRAM: the 2 KB slices of the epilogue vectors and the one gather window
+// no earlier row has touched (largest offset on an ascending sweep, smallest on a descending one) -- bulk prefetches issued by one warp
+// (cp.async.bulk.prefetch.L2 -> UBLKPF), no registers and no shared memory held while the lines travel.  The loads of the row loop then
+// find their lines in L2 (~0.3 us) instead of HBM (~1 us under load), which is what bounds a one-round-trip-per-row kernel.
+__device__ __forceinline__ void l2_prefetch_bulk(const double *p, long long e0, long long e1, long long n)
+{   // elements [e0, e1) of p, clipped to [0, n) and widened to 16-byte granules inside the array
+  if (e0 < 0) e0 = 0;
+  if (e1 > n) e1 = n;
+  uintptr_t a0 = (uintptr_t)(p + e0), a1 = (uintptr_t)(p + e1);
+  a0 = (a0 + 15) & ~(uintptr_t)15;
+  a1 &= ~(uintptr_t)15;
+  if (a1 > a0) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a0), "r"((uint32_t)(a1 - a0)) : "memory");
+}
+template <class Epi>
+__device__ __forceinline__ void sd_prefetch_tile(const Epi &epi, const double *gx, int tile, int rows, int n, int ncols, bool rev, const TileOrder &ord, int lane)
+{
+  const long long r0 = (long long)tile * rows;
+  const int       nv = epi.nvec();
+  if (lane == 0) {
+    const int d = rev ? ord.dlo : ord.dhi;
+    l2_prefetch_bulk(gx, r0 + d, r0 + d + rows, ncols);
+  } else if (lane <= nv) {
+    const double *v = epi.vsrc(lane - 1);
+    if (v != gx) l2_prefetch_bulk(v, r0, r0 + rows, n);
+  }
+}
+
 template <class Epi, int LMAX, int MINB>
 __global__ void __launch_bounds__(NT, MINB) k_spmv_sd(CsrDev A, const double *__restrict__ x, Epi epi, TileOrder ord)
 {
@@ -1408,6 +1435,10 @@ __global__ void __launch_bounds__(NT, MINB) k_spmv_sd(CsrDev A, const double *__
     const int      ni = i + gridDim.x;
     const int      r = tile * TR + threadIdx.x;
     const bool     live = r < A.n;
+    if (ord.pf > 0 && threadIdx.x < 32) {
+      const long long pi = (long long)i + (long long)ord.pf * gridDim.x;
+      if (pi < ntiles) sd_prefetch_tile(epi, gx.x, tile_at((int)pi, ord.ta, ord.tb, rev), TR, A.n, A.ncols, rev, ord, (int)threadIdx.x);
+    }
     const typename Epi::Pre pre = epi.preload(live ? r : 0);   // epilogue operands: in flight together with the gathers
     if (ni < ntiles) {
       const int tn = tile_at(ni, ord.ta, ord.tb, rev);
@@ -1852,6 +1883,17 @@ static int launch_sd_l(const CsrDev &A, const double *x, const Epi &epi, TileOrd
     return 0;
   }
   auto kern = (minb == 4) ? k_spmv_sd<Epi, LMAX, 4> : (minb == 5 ? k_spmv_sd<Epi, LMAX, 5> : k_spmv_sd<Epi, LMAX, 6>);
+  static int pf = -1;
+  if (pf < 0) {
+    // L2 prefetch distance in grid sweeps.  OFF by default: measured on C2 / C3 (profiles/README.md, r2k) the bulk prefetches make K_A
+    // 28-40 % SLOWER at every distance tried (1, 2, 4) -- kept as a switch for the record
+    const char *e = getenv("PERMON_B200_SD_PF");
+    pf = e ? atoi(e) : 0;
+    if (pf < 0 || pf > 64) pf = 0;
+  }
+  ord.pf  = pf;
+  ord.dlo = A.st_dlo;
+  ord.dhi = A.st_dhi;
   static int occ = 0;
   if (!occ) {
     int nb = 0;

@@ -1048,6 +1048,12 @@ static int upload_stencil(pb::CsrDev &C, pb::StencilHost &st, int64_t nnz, doubl
   C.st_nwin  = st.nwin;
   C.st_lmax  = 0;
   for (const pb::StPattern &P : st.pats) C.st_lmax = std::max(C.st_lmax, P.L);
+  C.st_dlo = C.st_dhi = 0;
+  for (const pb::StPattern &P : st.pats)
+    for (int j = 0; j < P.L; j++) {
+      C.st_dlo = std::min(C.st_dlo, P.d[j]);
+      C.st_dhi = std::max(C.st_dhi, P.d[j]);
+    }
   C.pk_bytes = (int64_t)st.masks.size() + (int64_t)st.pid.size() + (int64_t)(sizeof(pb::StPattern) * st.pats.size());
   C.pk_coded = (int64_t)st.pid.size();
   C.kind     = 4;
