@@ -265,6 +265,13 @@ PERMON_EXTERN PetscErrorCode QPPFApplyHalfQTranspose(QPPF cp, Vec x, Vec y);    
 PERMON_EXTERN PetscErrorCode QPPFApplyCP(QPPF cp, Vec x, Vec y);                     /* permonqppf.h:24, qppf.c:610 */
 PERMON_EXTERN PetscErrorCode QPPFApplyGtG(QPPF cp, Vec v, Vec GtGv);                 /* permonqppf.h:25, qppf.c:580 */
 PERMON_EXTERN PetscErrorCode QPPFCreateP(QPPF cp, Mat *P);                           /* permonqppf.h:32, qppf.c:685 */
+PERMON_EXTERN PetscErrorCode QPPFCreateQ(QPPF cp, Mat *Q);                           /* permonqppf.h:31, qppf.c:650 */
+PERMON_EXTERN PetscErrorCode QPPFCreateGtG(QPPF cp, Mat *GtG);                       /* permonqppf.h:34, qppf.c:705 */
+PERMON_EXTERN PetscErrorCode QPPFSetFromOptions(QPPF cp);                            /* permonqppf.h:16, qppf.c:170: -qppf_explicit, -qppf_redundancy */
+PERMON_EXTERN PetscErrorCode QPPFSetRedundancy(QPPF cp, PetscInt nred);              /* permonqppf.h:28, qppf.c:158 */
+PERMON_EXTERN PetscErrorCode QPPFSetExplicitInv(QPPF cp, PetscBool explicitInv);     /* permonqppf.h:29, qppf.c:143 */
+PERMON_EXTERN PetscErrorCode QPPFGetAlphaTilde(QPPF cp, Vec *alpha_tilde);           /* permonqppf.h:19, qppf.c:441 */
+PERMON_EXTERN PetscErrorCode QPPFGetGGt(QPPF cp, Mat *GGt);                          /* permonqppf.h:38, qppf.c:744 */
 
 /* ===================================================================================================
  * QP -- problem container: include/permonqp.h:21-123, src/qp/interface/qp.c

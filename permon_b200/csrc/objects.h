@@ -144,6 +144,7 @@ struct _p_Mat : PObj {
   Mat    A = nullptr;
   QPPF   pf = nullptr;
   double rho = 0.0;
+  int    proj_mode = 0;   // PROJ: 0 P = I - Q (QPPFCreateP), 1 Q (QPPFCreateQ), 2 G^T G (QPPFCreateGtG)
   // cached extreme eigenvalue (PetscObjectComposedData in the reference)
   ~_p_Mat() override;
 };
@@ -166,6 +167,13 @@ struct _p_QPPF : PObj {   // qppfimpl.h:6-31
   std::vector<double> GGt, L;           // m x m and its Cholesky factor (host, replicated)
   bool                orth = false, setupcalled = false;
   Vec                 G_left = nullptr, Gt_right = nullptr;
+  // qppfimpl.h: explicitInv (apply inv(G G^T) as an explicit m x m matrix instead of two triangular solves), redundancy (number of
+  // redundant coarse solves; the m x m factor is replicated on every rank here, so any value is honoured as "all ranks"), alpha_tilde
+  bool                explicitInv = false;
+  PetscInt            redundancy = PETSC_DEFAULT, setfromoptionscalled = 0;
+  std::vector<double> GGtinv;           // explicit inverse (host, replicated) when explicitInv
+  Vec                 alpha_tilde = nullptr;
+  Mat                 GGt_mat = nullptr;   // QPPFGetGGt: G G^T as an m x m dense-rows Mat (built on demand)
   ~_p_QPPF() override;
 };
 
@@ -186,7 +194,7 @@ struct _p_QP : PObj {   // qpimpl.h:6-57
   int           transform = 0;            // 0 none, 1 penalty, 2 homogenize, 3 projector, 4 orthonormalize
   std::string   transform_name = "";
   int           id = 0;
-  bool          setupcalled = false, solved = false;
+  bool          setupcalled = false, solved = false, setfromoptionscalled = false;
   PetscErrorCode (*changeListener)(QP) = nullptr;
   void         *changeListenerCtx = nullptr;
   ~_p_QP() override;
@@ -290,6 +298,7 @@ int  vec_mdot2(Vec x, Vec y0, Vec y1, double *v0, double *v1);
 int  mat_mult(Mat A, Vec x, Vec y);
 int  mat_mult_dev(Mat A, const double *x, double *y);        // raw device pointers (local lengths)
 int  qppf_apply_P_dev(QPPF cp, const double *x, double *y);   // y = x - G^T (G G^T)^{-1} G x on raw device pointers
+int  qppf_apply_mode_dev(QPPF cp, int mode, const double *x, double *y);   // 0: P, 1: Q, 2: G^T G
 int  mat_ensure_device(Mat A);                               // upload a lazily kept host split (multi-rank AIJ)
 int  mat_halo_begin(Mat A, const double *x);                 // pack + post send/recv on the comm stream
 int  mat_halo_end(Mat A);                                    // make the compute stream wait for the ghosts

@@ -304,6 +304,8 @@ _p_QPPF::~_p_QPPF()
   if (Bd_owned && Bd) cudaFree(Bd);
   pb::unref(G_left);
   pb::unref(Gt_right);
+  pb::unref(alpha_tilde);
+  pb::unref(GGt_mat);
 }
 PetscErrorCode QPPFCreate(MPI_Comm comm, QPPF *cp)
 {
@@ -326,6 +328,34 @@ PetscErrorCode QPPFReset(QPPF cp)
   cp->setupcalled = false;
   cp->GGt.clear();
   cp->L.clear();
+  cp->GGtinv.clear();
+  pb::unref(cp->GGt_mat);
+  cp->GGt_mat = nullptr;
+  return 0;
+}
+PetscErrorCode QPPFSetExplicitInv(QPPF cp, PetscBool explicitInv)
+{   // qppf.c:143-154
+  if (cp->explicitInv != (explicitInv != PETSC_FALSE)) {
+    cp->explicitInv = explicitInv != PETSC_FALSE;
+    cp->setupcalled = false;
+  }
+  return 0;
+}
+PetscErrorCode QPPFSetRedundancy(QPPF cp, PetscInt nred)
+{   // qppf.c:158-166.  The coarse problem (G G^T, m x m) is factored redundantly on EVERY rank here (the PCREDUNDANT end of the
+    // reference's range, matinv.c:565-569): the value is recorded and reported back, it does not change the arithmetic.
+  cp->redundancy = nred;
+  return 0;
+}
+PetscErrorCode QPPFSetFromOptions(QPPF cp)
+{   // qppf.c:170-188 (-qppf_explicit, -qppf_redundancy); -qppf_explicit_GGt (:237) is read as well: G G^T is always formed explicitly here
+  bool     flg = cp->explicitInv;
+  PetscInt nred = cp->redundancy;
+  if (pb::options_bool(cp->prefix, "-qppf_explicit", &flg)) PB_CHK(QPPFSetExplicitInv(cp, flg ? PETSC_TRUE : PETSC_FALSE));
+  if (pb::options_int(cp->prefix, "-qppf_redundancy", &nred)) PB_CHK(QPPFSetRedundancy(cp, nred));
+  bool ggt = true;
+  pb::options_bool(cp->prefix, "-qppf_explicit_GGt", &ggt);
+  cp->setfromoptionscalled++;
   return 0;
 }
 PetscErrorCode QPPFSetG(QPPF cp, Mat G)
@@ -346,6 +376,14 @@ PetscErrorCode QPPFGetG(QPPF cp, Mat *G)
 static int qppf_solve(QPPF cp, const double *r, double *y)
 {   // (G G^T) y = r through the Cholesky factor (MatMult_Inv: KSPPREONLY + PCCHOLESKY, matinv.c:487-488,734-743)
   const int     m = cp->m;
+  if (cp->explicitInv && !cp->GGtinv.empty()) {   // qppf.c:314-330: the explicit inverse applied as a matrix
+    for (int i = 0; i < m; i++) {
+      double v = 0.0;
+      for (int k = 0; k < m; k++) v += cp->GGtinv[(size_t)i * m + k] * r[k];
+      y[i] = v;
+    }
+    return 0;
+  }
   const double *L = cp->L.data();
   for (int i = 0; i < m; i++) {
     double v = r[i];
@@ -415,6 +453,17 @@ PetscErrorCode QPPFSetUp(QPPF cp)
       for (int k = 0; k < j; k++) v -= cp->L[i * m + k] * cp->L[j * m + k];
       cp->L[i * m + j] = v / d;
     }
+  }
+  cp->GGtinv.clear();
+  if (cp->explicitInv) {   // MatInvExplicitly (qppf.c:319): column j of the inverse = solve with the j-th unit vector
+    std::vector<double> inv((size_t)m * m), e(m), y(m);
+    for (int j = 0; j < m; j++) {
+      std::fill(e.begin(), e.end(), 0.0);
+      e[j] = 1.0;
+      PB_CHK(qppf_solve(cp, e.data(), y.data()));
+      for (int i = 0; i < m; i++) inv[(size_t)i * m + j] = y[i];
+    }
+    cp->GGtinv = inv;
   }
   cp->setupcalled = true;
   return 0;
@@ -507,6 +556,19 @@ PetscErrorCode QPPFApplyGtG(QPPF cp, Vec v, Vec GtGv)
   PB_CHK(qppf_G_mult(cp, v, t));
   return qppf_Gt_mult(cp, t, GtGv);
 }
+static int qppf_store_alpha_tilde(QPPF cp, const double *s)
+{   // qppf.c:486-487: alpha_tilde = (G G^T)^{-1} G v of the last Q / P application (an m-vector: rank 0 owns the entries, onerow.c:97-113)
+  if (!cp->alpha_tilde) {
+    const int nloc = (cp->comm->rank == 0) ? (int)cp->m : 0;
+    PB_CHK(VecCreateMPI(cp->comm, nloc, cp->m, &cp->alpha_tilde));
+  }
+  return mvec_put(cp->alpha_tilde, cp->m, s);
+}
+PetscErrorCode QPPFGetAlphaTilde(QPPF cp, Vec *alpha_tilde)
+{   // qppf.c:441-449 (borrowed pointer; NULL before the first application, like the reference before QPPFSetUp)
+  *alpha_tilde = cp->alpha_tilde;
+  return 0;
+}
 PetscErrorCode QPPFApplyQ(QPPF cp, Vec v, Vec Qv)
 {   // qppf.c:454-502
   PB_CHK(QPPFSetUp(cp));
@@ -514,6 +576,7 @@ PetscErrorCode QPPFApplyQ(QPPF cp, Vec v, Vec Qv)
   PB_CHK(qppf_G_mult(cp, v, t));
   if (!cp->orth) PB_CHK(qppf_solve(cp, t, s));
   else memcpy(s, t, sizeof(double) * cp->m);
+  PB_CHK(qppf_store_alpha_tilde(cp, s));
   return qppf_Gt_mult(cp, s, Qv);
 }
 PetscErrorCode QPPFApplyP(QPPF cp, Vec v, Vec Pv)
@@ -532,7 +595,52 @@ int qppf_apply_P_dev(QPPF cp, const double *x, double *y)
   PB_CHK(dense_rows_multT_host(cp->comm, cp->n, cp->m, cp->Bd, s, 1.0, y, 0));   // y = Q x
   return k_aypx(cp->n, y, -1.0, x);                                            // VecAYPX(Pv, -1, v)
 }
+int qppf_apply_mode_dev(QPPF cp, int mode, const double *x, double *y)
+{   // the shell operators of qppf.c:648-718: 0 P, 1 Q = G^T (G G^T)^{-1} G, 2 G^T G
+  if (mode == 0) return qppf_apply_P_dev(cp, x, y);
+  PB_CHK(QPPFSetUp(cp));
+  double t[PB_MAXEQ_ALL], s[PB_MAXEQ_ALL];
+  PB_CHK(dense_rows_mult_host(cp->comm, cp->n, cp->m, cp->Bd, x, t));
+  if (mode == 1 && !cp->orth) PB_CHK(qppf_solve(cp, t, s));
+  else memcpy(s, t, sizeof(double) * cp->m);
+  return dense_rows_multT_host(cp->comm, cp->n, cp->m, cp->Bd, s, 1.0, y, 0);
+}
 }   // namespace pb
+
+static int qppf_create_shell(QPPF cp, int mode, Mat *out)
+{
+  if (!cp->G) return err(PETSC_ERR_ORDER, "QPPFSetG must be called first");
+  _p_Mat *P = new _p_Mat;
+  P->comm      = cp->comm;
+  P->kind      = MK_PROJ;
+  P->proj_mode = mode;
+  P->pf        = cp;
+  cp->refct++;
+  P->m = P->n = cp->G->n;
+  P->M = P->N = cp->G->N;
+  *out        = P;
+  return 0;
+}
+PetscErrorCode QPPFCreateQ(QPPF cp, Mat *newQ) { return qppf_create_shell(cp, 1, newQ); }         // qppf.c:650-663
+PetscErrorCode QPPFCreateGtG(QPPF cp, Mat *newGtG) { return qppf_create_shell(cp, 2, newGtG); }   // qppf.c:705-718
+PetscErrorCode QPPFGetGGt(QPPF cp, Mat *GGt)
+{   // qppf.c:744-755: the coarse-problem matrix (NULL when the explicit inverse replaced it or G has orthonormal rows, :225-229)
+  *GGt = nullptr;
+  PB_CHK(QPPFSetUp(cp));
+  if (cp->explicitInv || cp->orth) return 0;
+  if (!cp->GGt_mat) {
+    const int m = cp->m;
+    _p_Mat   *T = new _p_Mat;
+    T->comm = cp->comm;
+    T->kind = MK_DENSEROWS;
+    T->m = T->n = T->M = T->N = m;
+    PB_CUDA(cudaMalloc(&T->rows_d, sizeof(double) * std::max<size_t>((size_t)m * m, 1)));
+    PB_CUDA(cudaMemcpy(T->rows_d, cp->GGt.data(), sizeof(double) * (size_t)m * m, cudaMemcpyHostToDevice));
+    cp->GGt_mat = T;
+  }
+  *GGt = cp->GGt_mat;
+  return 0;
+}
 
 PetscErrorCode QPPFCreateP(QPPF cp, Mat *newP)
 {   // qppf.c:685-700: P = I - G' inv(G G') G in implicit form
@@ -740,7 +848,13 @@ PetscErrorCode QPSetOptionsPrefix(QP qp, const char prefix[])
   qp->prefix = prefix ? prefix : "";
   return 0;
 }
-PetscErrorCode QPSetFromOptions(QP) { return 0; }   // the options that matter are read at post-solve (-qp_chain_view_kkt)
+PetscErrorCode QPSetFromOptions(QP qp)
+{   // qp.c:2480-2490: only records the request; the objects that exist at QPSetUp time read their options there (QPSetFromOptions_Private,
+    // qp.c:2448-2465: the QPPF inherits the QP's prefix and reads -qppf_*); -qp_chain_view_kkt is read at post-solve
+  qp->setfromoptionscalled = true;
+  qp->setupcalled          = false;
+  return 0;
+}
 PetscErrorCode QPGetSolutionVector(QP qp, Vec *x)
 {
   *x = qp->x;
@@ -815,6 +929,10 @@ static int qp_setup_inner_objects(QP qp)
 PetscErrorCode QPSetUp(QP qp)
 {   // qp.c:614-635
   if (qp->setupcalled) return 0;
+  if (qp->setfromoptionscalled && qp->pf) {   // QPSetFromOptions_Private qp.c:2448-2465
+    if (qp->pf->prefix.empty()) qp->pf->prefix = qp->prefix;
+    PB_CHK(QPPFSetFromOptions(qp->pf));
+  }
   PB_CHK(qp_setup_inner_objects(qp));
   qp->setupcalled = true;
   return 0;

@@ -1231,6 +1231,10 @@ struct SmalxeImpl : QPSImpl {   // QPS_SMALXE smalxeimpl.h:13-67
   int              state = 1;
   PetscInt         inner_iter_accu = 0;
   bool             setfromoptionscalled = false;
+  // lagged ||B u|| update (smalxe.c:1190-1200 defaults; :289-370)
+  bool             lag_enabled = false, lag_monitor = false, lag_compare = false;
+  PetscInt         lag_offset = 2, Jstart = 10, Jstep = 5, Jend = 20;
+  double           lag_lower = 0.1, lag_upper = 1.1;
   double           normBu = NAN, normBu_old = NAN, normBu_prev = NAN, enorm = NAN;
   Vec              BtBu = nullptr;
 
@@ -1319,8 +1323,18 @@ PetscErrorCode SmalxeImpl::setfromoptions(QPS qps)
   options_int(p, "-qps_smalxe_inner_no_gtol_stop", &inner_no_gtol_stop);
   options_real(p, "-qps_smalxe_update_threshold", &update_threshold);
   options_bool(p, "-qps_smalxe_knoll", &knoll);
-  bool lag = false;
-  if (options_bool(p, "-qps_smalxe_norm_update_lag", &lag) && lag) return err(PETSC_ERR_SUP, "-qps_smalxe_norm_update_lag: B u is free on the device, the lagged variant is not provided");
+  // smalxe.c:754-762.  As in the reference the lag switches only take effect when B_E has no MatMult (the implicit orthonormalisation
+  // dummies, smalxe.c:878-886); every equality matrix of this library has one, so ||B u|| is evaluated exactly in every inner iteration
+  // (it costs no extra pass on the device: K_B reduces B u of the new iterate).
+  options_bool(p, "-qps_smalxe_norm_update_lag", &lag_enabled);
+  options_bool(p, "-qps_smalxe_norm_update_lag_monitor", &lag_monitor);
+  options_bool(p, "-qps_smalxe_norm_update_lag_compare", &lag_compare);
+  options_int(p, "-qps_smalxe_norm_update_lag_offset", &lag_offset);
+  options_int(p, "-qps_smalxe_norm_update_lag_start", &Jstart);
+  options_int(p, "-qps_smalxe_norm_update_lag_step", &Jstep);
+  options_int(p, "-qps_smalxe_norm_update_lag_end", &Jend);
+  options_real(p, "-qps_smalxe_norm_update_lag_lower", &lag_lower);
+  options_real(p, "-qps_smalxe_norm_update_lag_upper", &lag_upper);
   setfromoptionscalled = true;
   qps->setupcalled     = false;
   return 0;

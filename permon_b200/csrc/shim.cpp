@@ -1790,7 +1790,7 @@ int mat_mult_dev(Mat A, const double *x, double *y)
     PB_CHK(mat_mult_dev(A->M2, x, t));
     return mat_mult_dev(A->M1, t, y);
   }
-  case MK_PROJ: return qppf_apply_P_dev(A->pf, x, y);   // QPPFMatMult_P
+  case MK_PROJ: return qppf_apply_mode_dev(A->pf, A->proj_mode, x, y);   // QPPFMatMult_P / _Q / _GtG
   case MK_PENALIZED: {
     // MatMult_Penalized (src/qp/utils/matpenalized.c:12-22): y = BtB x; y *= rho; y += A x.  A x goes first here: a projected
     // Hessian (MK_PROD of MK_PROJ) uses the reducer's device scratch for its own coefficients

@@ -19,7 +19,10 @@ fi
 ls gpurun_out/${tag}_tl*rank[1-9]*.csv 2>/dev/null | xargs -r rm -f      # rank 0's timeline is enough
 python - $tag <<'PY'
 import json, sys
+import os
 for k in ("k20", "k300", "c5_k300"):
+    if not os.path.exists(f"gpurun_out/{sys.argv[1]}_bench_{k}.json"):
+        continue
     try:
         d = json.loads([l for l in open(f"gpurun_out/{sys.argv[1]}_bench_{k}.json") if l.startswith("{")][-1])
         e = d.get("e2e") or {}
