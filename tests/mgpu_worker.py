@@ -5,6 +5,11 @@ import json
 import os
 import sys
 
+# torchrun exports OMP_NUM_THREADS=1; the host side of the set-up (split + re-coding of this rank's rows) is OpenMP-parallel: the ranks of
+# the node share the host cores (must happen before the OpenMP runtime starts)
+if os.environ.get("OMP_NUM_THREADS", "1") == "1" and not os.environ.get("PERMON_B200_KEEP_OMP"):
+    os.environ["OMP_NUM_THREADS"] = str(max(1, (os.cpu_count() or 1) // int(os.environ.get("LOCAL_WORLD_SIZE", os.environ.get("WORLD_SIZE", "1")))))
+
 import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
