@@ -1095,6 +1095,11 @@ static int upload_csr(pb::CsrDev &C, int nrows, int ncols, const int *ia, const 
       C.pk_coded = ncoded;
       return 0;
     }
+    // Incompressible matrices (every value distinct: FEM, scaled operators): a raw tile costs 12 B per non-zero in the blob format as
+    // well, and the CSR ring (k_spmv_tma: three unit-stride streams, 0.90 of the HBM roof on C2r) beats the blob kernel on raw tiles
+    // (0.64) -- measured 1942 vs 1349 it/s on C2r (profiles/README.md).  Break-even is about one third of the tiles coded.
+    const int64_t ntiles_pk = ((int64_t)nrows + TR - 1) / TR;
+    if (packed && !getenv("PERMON_B200_KEEP_RAW_TILES") && ncoded * 3 < ntiles_pk) packed = false;
     if (packed) {
       unsigned char *dblob;
       unsigned      *doff;

@@ -28,7 +28,8 @@ def main():
                 fam = "K_A' spmv+grad+split"
             elif "k_spmv" in name and "EpiAT" not in name:
                 continue
-            dur = float(d["gpu__time_duration.sum"])
+            tscale = {"s": 1e6, "ms": 1e3, "us": 1.0, "ns": 1e-3}[units[hdr.index("gpu__time_duration.sum")]]
+            dur = float(d["gpu__time_duration.sum"]) * tscale      # microseconds
             if dur < 20.0:          # early exits
                 continue
             scale = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}

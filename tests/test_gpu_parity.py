@@ -178,6 +178,8 @@ def test_packed_tiles_bit_identical_to_csr(P, kind, monkeypatch):
     stencils take the all-stencil form (x windows staged by bulk copies, kind 4); ":blob" keeps them as stencil tiles inside the general
     blob format (gathers), ":coded" as dictionary-coded tiles."""
     kind, _, form = kind.partition(":")
+    # incompressible matrices are routed to the CSR ring by default (shim.cpp: upload_csr); this test is about the blob format itself
+    monkeypatch.setenv("PERMON_B200_KEEP_RAW_TILES", "1")
     monkeypatch.setenv("PERMON_B200_ST_WINDOWS", "0" if form else "1")
     monkeypatch.setenv("PERMON_B200_PACK_STENCIL", "0" if form == "coded" else "1")
     import scipy.sparse as sp
@@ -343,8 +345,8 @@ def test_varcoef3d_both_bounds(P):
     assert np.array_equal(la, pr.meta["lower_active"])
 
 
-@pytest.mark.parametrize("kind", ["raw_tiles", "mixed_tiles"])
-def test_fused_solve_on_raw_and_mixed_tiles(P, kind):
+@pytest.mark.parametrize("kind", ["raw_tiles", "mixed_tiles", "raw_default"])
+def test_fused_solve_on_raw_and_mixed_tiles(P, kind, monkeypatch):
     """Hessians whose values do not repeat: every tile (or a band of tiles) overflows the 256-entry dictionary and is stored raw in
     the packed format; the fused MPGP iteration must not care.  A = D L D with a random positive diagonal scaling D; the load is
     large enough for CG, expansion and proportioning steps and a few hundred active dofs."""
@@ -353,6 +355,8 @@ def test_fused_solve_on_raw_and_mixed_tiles(P, kind):
     n = pr.n
     rng = np.random.default_rng(17)
     d = 1.0 + 0.5 * rng.random(n)
+    if kind != "raw_default":     # "raw_default": the library's own choice for an incompressible matrix = plain CSR through the TMA ring
+        monkeypatch.setenv("PERMON_B200_KEEP_RAW_TILES", "1")
     if kind == "mixed_tiles":
         d[: n // 3] = 1.0
         d[2 * n // 3:] = 1.0
@@ -363,8 +367,9 @@ def test_fused_solve_on_raw_and_mixed_tiles(P, kind):
     Am = P.MatCreateAIJ(pr.ia, pr.ja, pr.a)
     info = P.MatStorageInfo(Am)
     P.MatDestroy(Am)
-    assert info["kind"] == 3
-    assert (info["coded_tiles"] <= 1) if kind == "raw_tiles" else (0 < info["coded_tiles"] < info["tiles"])
+    assert info["kind"] == (2 if kind == "raw_default" else 3)
+    if kind != "raw_default":
+        assert (info["coded_tiles"] <= 1) if kind == "raw_tiles" else (0 < info["coded_tiles"] < info["tiles"])
     r = P.solve_problem(pr, "mpgp", "-qps_rtol 1e-8 -qps_mpgp_b200_driver fused")
     xr, ro = oracle_solve(pr, rtol=1e-8)
     check_parity(pr, r, xr, ro, band_kw=dict(rtol=1e-8))
