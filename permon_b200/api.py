@@ -728,7 +728,16 @@ def solve_problem(pr, qps_type=None, options: str = "", monitor=None, keep=False
     QPSetInitialVector(qp, x)
     QPSetBox(qp, is_, lb, ub)
     extra = []
-    if pr.B is not None:
+    if getattr(pr, "BE_local", None) is not None:
+        # row-partitioned AIJ equality matrix, the way a PETSc user assembles B_E: this rank's rows in CSR with GLOBAL column indices
+        # (pr.BE_local = (ia, ja, a)), pr.c = this rank's entries of c_E
+        BE = MatCreateAIJ(pr.BE_local[0], pr.BE_local[1], pr.BE_local[2], ncols_local=pr.n)
+        cE = VecFromArray(np.ascontiguousarray(pr.c, dtype=np.float64)) if pr.c is not None else None
+        QPSetEq(qp, BE, cE)
+        mats.append(BE)
+        if cE is not None:
+            extra.append(cE)
+    elif pr.B is not None:
         Bm = np.ascontiguousarray(pr.B, dtype=np.float64)
         if Bm.shape[0] == 1:
             brow = VecFromArray(Bm[0].copy())
@@ -761,7 +770,7 @@ def solve_problem(pr, qps_type=None, options: str = "", monitor=None, keep=False
     llb, lub = QPCBoxGetMultipliers(qpc)
     r.llb = VecGetArray(llb) if (llb is not None and not VecIsInvalidated(llb)) else None
     r.lub = VecGetArray(lub) if (lub is not None and not VecIsInvalidated(lub)) else None
-    if pr.B is None:
+    if pr.B is None and getattr(pr, "BE_local", None) is None:
         r.counts = QPSMPGPGetStepCounts(qps)
         r.alpha_user, _ = QPSMPGPGetAlpha(qps)
         r.maxeig = QPSMPGPGetOperatorMaxEigenvalue(qps)

@@ -140,6 +140,14 @@ struct _p_Mat : PObj {
   Vec twork = nullptr;
   // DENSEROWS: row-major m x n device array (orthonormalised equality rows)
   double *rows_d = nullptr;
+  // AIJ, row-partitioned with at most PB_MAXEQ_ALL GLOBAL rows (an equality matrix B_E created like any PETSc MPIAIJ: rank r owns a few
+  // rows with GLOBAL columns): the local rows are kept on the host and turned into dense M x n_local rows (column-partitioned like the
+  // vectors) on first use -- no halo plan, the rows are wide and their pattern is not symmetric
+  struct EqHost {
+    std::vector<int>    ia, ja;
+    std::vector<double> a;
+  };
+  EqHost *eq_host = nullptr;
   // PENALIZED: y = A x + rho G^T G x   (matpenalized.c:4-8); PROJ uses pf only
   Mat    A = nullptr;
   QPPF   pf = nullptr;
@@ -297,6 +305,7 @@ int  vec_norm2(Vec x, double *val);
 int  vec_mdot2(Vec x, Vec y0, Vec y1, double *v0, double *v1);
 int  mat_mult(Mat A, Vec x, Vec y);
 int  mat_mult_dev(Mat A, const double *x, double *y);        // raw device pointers (local lengths)
+int  mat_eqrows_dense(Mat A, double **Bd);                  // row-partitioned equality matrix -> dense M x n_local rows on the device (collective)
 int  qppf_apply_P_dev(QPPF cp, const double *x, double *y);   // y = x - G^T (G G^T)^{-1} G x on raw device pointers
 int  qppf_apply_mode_dev(QPPF cp, int mode, const double *x, double *y);   // 0: P, 1: Q, 2: G^T G
 int  mat_ensure_device(Mat A);                               // upload a lazily kept host split (multi-rank AIJ)

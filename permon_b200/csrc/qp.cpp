@@ -415,8 +415,12 @@ PetscErrorCode QPPFSetUp(QPPF cp)
   } else if (G->kind == MK_DENSEROWS) {
     cp->Bd       = G->rows_d;
     cp->Bd_owned = false;
+  } else if (G->kind == MK_AIJ && G->eq_host) {
+    // row-partitioned AIJ equality matrix (several GPUs): re-distributed by columns into dense rows (shim.cpp: mat_eqrows_dense)
+    PB_CHK(mat_eqrows_dense(G, &cp->Bd));
+    cp->Bd_owned = false;
   } else if (G->kind == MK_AIJ) {
-    if (G->comm->size > 1) return err(PETSC_ERR_SUP, "row-partitioned AIJ equality matrices are not supported; use MatCreateOneRow");
+    if (G->comm->size > 1) return err(PETSC_ERR_SUP, "a row-partitioned AIJ equality matrix may have at most %d rows", PB_MAXEQ_ALL);
     const int        m = G->m, n = G->n;
     std::vector<int> ia(m + 1), ja((size_t)G->Ad.nnz);
     std::vector<double> a((size_t)G->Ad.nnz), dense((size_t)m * n, 0.0);
@@ -532,12 +536,14 @@ static int mvec_get(Vec x, int m, double *t)
   return 0;
 }
 static int mvec_put(Vec y, int m, const double *t)
-{
+{   // every rank holds all m values; each stores the entries of its ownership range (rank 0 owns everything in the MatCreateOneRow layout,
+    // a row-partitioned B_E spreads them like its rows)
   if (y->n == 0) return 0;
-  if (y->n != m) return err(PETSC_ERR_ARG_SIZ, "expected a vector of length %d", m);
+  const bool whole = (y->comm->size == 1) || (y->N == m);
+  if ((y->comm->size == 1 && y->n != m) || !whole || y->rstart + y->n > m) return err(PETSC_ERR_ARG_SIZ, "expected a vector of (global) length %d", m);
   double *h;
   PB_CHK(vec_host_write(y, &h));
-  memcpy(h, t, sizeof(double) * m);
+  memcpy(h, t + (y->comm->size == 1 ? 0 : y->rstart), sizeof(double) * y->n);
   return 0;
 }
 

@@ -976,7 +976,8 @@ _p_Mat::~_p_Mat()
     pb::dfree(Ad.ell_lt);
     pb::dfree(Ad.ell_off);
   }
-  if (kind == MK_DENSEROWS) pb::dfree(rows_d);
+  if (kind == MK_DENSEROWS || eq_host) pb::dfree(rows_d);
+  delete eq_host;
   if (kind == MK_AIJ) {
     pb::dfree(Ao.ia);
     pb::dfree(Ao.ja);
@@ -1222,6 +1223,19 @@ PetscErrorCode MatCreateMPIAIJWithArrays(MPI_Comm comm, PetscInt m, PetscInt n, 
   A->N      = (PetscInt)cs[size];
   A->rstart = (PetscInt)rs[rank];
   A->cstart = (PetscInt)cs[rank];
+  if (A->M <= PB_MAXEQ_ALL && A->M != A->N) {
+    // a short and wide matrix: equality rows B_E (qp.c: QPSetEq).  No diagonal / off-diagonal split and no halo plan: the local rows are
+    // kept as they came and re-distributed by COLUMNS (the layout of the vectors) when the QPPF or a MatMult first needs them.
+    A->eq_host = new _p_Mat::EqHost;
+    A->eq_host->ia.assign(i, i + m + 1);
+    A->eq_host->ja.assign(j, j + i[m]);
+    A->eq_host->a.assign(a, a + i[m]);
+    A->Ad.n = m;
+    A->Ad.ncols = n;
+    A->Ad.nnz = i[m];
+    *mat = A;
+    return 0;
+  }
   const PetscInt c0 = A->cstart, c1 = A->cstart + n;
   const int64_t  nnz = i[m];
   const double   t_s0 = wall_now();
@@ -1811,8 +1825,60 @@ int mat_mult_dev(Mat A, const double *x, double *y)
   }
 }
 
+int mat_eqrows_dense(Mat A, double **Bd)
+{   // every rank publishes its rows as (global row, global column, value) triples; each rank keeps the entries of its own column range
+  if (A->rows_d) {
+    *Bd = A->rows_d;
+    return 0;
+  }
+  MPI_Comm  c = A->comm;
+  const int size = c->size;
+  if (!c->agi || !c->agv) return err(PETSC_ERR_ARG_WRONGSTATE, "communicator has no host exchange");
+  struct Trip {
+    int    r, c;
+    double v;
+  };
+  const _p_Mat::EqHost &E = *A->eq_host;
+  std::vector<Trip>     mine;
+  for (PetscInt r = 0; r < A->m; r++)
+    for (int k = E.ia[r]; k < E.ia[r + 1]; k++) mine.push_back(Trip{(int)(A->rstart + r), E.ja[k], E.a[k]});
+  std::vector<int64_t> bytes(size);
+  if (c->agi(c->agctx, (int64_t)(mine.size() * sizeof(Trip)), bytes.data())) return err(PETSC_ERR_LIB, "host all-gather failed");
+  int64_t tot = 0;
+  for (int r = 0; r < size; r++) tot += bytes[r];
+  std::vector<Trip> all((size_t)(tot / sizeof(Trip)) + 1);
+  if (c->agv(c->agctx, mine.data(), (int64_t)(mine.size() * sizeof(Trip)), all.data(), bytes.data())) return err(PETSC_ERR_LIB, "host all-gather failed");
+  const size_t        M = (size_t)A->M, nl = (size_t)A->n;
+  std::vector<double> dense(std::max<size_t>(M * nl, 1), 0.0);
+  const size_t        cnt = (size_t)(tot / sizeof(Trip));
+  for (size_t k = 0; k < cnt; k++) {
+    const Trip &t = all[k];
+    if (t.c >= A->cstart && t.c < A->cstart + A->n) dense[(size_t)t.r * nl + (size_t)(t.c - A->cstart)] += t.v;   // layout change only
+  }
+  PB_CHK(dev_init());
+  PB_CHK(dmalloc(&A->rows_d, dense.size()));
+  PB_CUDA(cudaMemcpy(A->rows_d, dense.data(), sizeof(double) * dense.size(), cudaMemcpyHostToDevice));
+  *Bd = A->rows_d;
+  return 0;
+}
+
 int mat_mult(Mat A, Vec x, Vec y)
 {
+  if (A->kind == MK_AIJ && A->eq_host) {   // y = B x for row-partitioned equality rows: every rank computes all M sums, keeps its own rows
+    if (x->n != A->n || y->n != A->m) return err(PETSC_ERR_ARG_SIZ, "MatMult: size mismatch (A %dx%d local, x %d, y %d)", (int)A->m, (int)A->n, (int)x->n, (int)y->n);
+    double       *Bd;
+    const double *dx;
+    double        t[PB_MAXEQ_ALL];
+    PB_CHK(mat_eqrows_dense(A, &Bd));
+    PB_CHK(vec_dev_read(x, &dx));
+    PB_CHK(dense_rows_mult_host(A->comm, A->n, A->M, Bd, dx, t));
+    if (y->n > 0) {
+      double *h;
+      PB_CHK(vec_host_write(y, &h));
+      for (PetscInt r = 0; r < A->m; r++) h[r] = t[A->rstart + r];
+    }
+    return 0;
+  }
   if (A->kind == MK_ONEROW) {   // MatMult_OneRow onerow.c:5-17: z = a . x
     double d;
     PB_CHK(vec_dot(A->row, x, &d));

@@ -47,6 +47,23 @@ def build_problem(kind, rank, size):
         loc.B = full.B[:, starts[rank]:starts[rank + 1]].copy()
         loc.c = full.c if rank == 0 else np.zeros(0)   # rank 0 owns the single equality row (MatCreateOneRow layout)
         return full, loc, starts, "-qps_rtol 1e-9", dict(rtol=1e-9)
+    if kind == "smalxe_aij2":
+        # two equality rows assembled as a ROW-partitioned AIJ matrix with global columns (rank 0 owns row 0, rank 1 row 1): the
+        # library re-distributes them by columns (shim.cpp: mat_eqrows_dense)
+        import scipy.sparse as sp
+        N = 64
+        n = N * N
+        starts = PR.row_partition(n, size, align=N)
+        full = PR.obstacle2d(N)
+        loc = PR.obstacle2d(N, rows=(starts[rank], starts[rank + 1]))
+        full.B = np.vstack([np.full(n, 1.0 / np.sqrt(n)), np.sin(np.arange(n) * 0.01) / np.sqrt(n)])
+        full.c = np.array([-0.05 * np.sqrt(n), 0.02])
+        mine = [rank] if rank < 2 else []
+        S = sp.csr_matrix(full.B[mine, :]) if mine else sp.csr_matrix((0, n))
+        loc.BE_local = (S.indptr.astype(np.int32), S.indices.astype(np.int32), S.data.astype(np.float64))
+        loc.B = None
+        loc.c = full.c[mine].copy()
+        return full, loc, starts, "-qps_rtol 1e-9", dict(rtol=1e-9)
     raise ValueError(kind)
 
 
@@ -70,7 +87,7 @@ def main():
     out = {}
     for kind in kinds:
         full, loc, starts, opts, okw = build_problem(kind, rank, size)
-        qtype = "smalxe" if kind == "smalxe" else "mpgp"
+        qtype = "smalxe" if kind.startswith("smalxe") else "mpgp"
         r = P.solve_problem(loc, qtype, opts)
         xs = [torch.zeros(starts[q + 1] - starts[q], dtype=torch.float64, device=dev) for q in range(size)]
         dist.all_gather(xs, torch.from_numpy(r.x).to(dev))
@@ -79,7 +96,7 @@ def main():
             from oracle import oracle_py as O
             op = O.Operator(full.ia, full.ja, full.a)
             bx = O.BoxC(full.n, full.lb, full.ub)
-            if kind == "smalxe":
+            if kind.startswith("smalxe"):
                 xr, ro = O.smalxe_solve(op, full.b, bx, full.B, full.c, full.x0, O.smalxe_opts(**okw))
                 op.c.m = 0
                 its_ref, its = ro["inner_its_accu"], r.stats["inner_iter_accu"]
@@ -95,7 +112,7 @@ def main():
             fo, fg = O.objective(op, full.b, xr), O.objective(op, full.b, x)
             out[kind] = dict(its=its, its_ref=its_ref, band=ro.get("band"), reason=r.reason, reason_ref=ro["reason"], relx=relx,
                              relf=float(abs(fg - fo) / abs(fo)), counts=r.counts,
-                             counts_ref={k: ro[k] for k in ("ncg", "nexp", "nprop", "nmv")} if kind != "smalxe" else None)
+                             counts_ref={k: ro[k] for k in ("ncg", "nexp", "nprop", "nmv")} if not kind.startswith("smalxe") else None)
         dist.barrier()
     if rank == 0:
         print("MGPU_RESULT " + json.dumps(out), flush=True)

@@ -22,7 +22,7 @@ def test_row_partitioned_solves_match_oracle(nproc, p2p):
     if _ngpu() < nproc:
         pytest.skip(f"needs {nproc} GPUs")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nproc}", "--master-addr", "127.0.0.1", "--master-port", "29613",
-           os.path.join(ROOT, "tests", "mgpu_worker.py"), "obstacle2d,obstacle3d,varcoef3d,varcoef3d64t,smalxe"]
+           os.path.join(ROOT, "tests", "mgpu_worker.py"), "obstacle2d,obstacle3d,varcoef3d,varcoef3d64t,smalxe,smalxe_aij2"]
     p = subprocess.run(cmd, capture_output=True, text=True, timeout=900, env={**os.environ, "PERMON_B200_P2P": p2p})
     assert p.returncode == 0, p.stdout[-3000:] + p.stderr[-3000:]
     line = [l for l in p.stdout.splitlines() if l.startswith("MGPU_RESULT ")][-1]

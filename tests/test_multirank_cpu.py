@@ -107,6 +107,18 @@ def _worker(rank, size, port, kind, ret):
         w = P.VecDuplicate(v)
         with pytest.raises(P.PermonError):
             P.MatMult(A, v, w)
+    # 7. a short and wide row-partitioned matrix (equality rows B_E assembled like any MPIAIJ: rank r owns row r, global columns) is accepted
+    #    without a halo plan (its pattern is not symmetric); its arithmetic needs a GPU as well
+    import scipy.sparse as sp2
+    Bfull = np.vstack([np.ones(n_glob), np.arange(n_glob, dtype=float)])
+    mine = [rank] if rank < 2 else []
+    S = sp2.csr_matrix(Bfull[mine, :]) if mine else sp2.csr_matrix((0, n_glob))
+    BE = P.MatCreateAIJ(S.indptr.astype(np.int32), S.indices.astype(np.int32), S.data.astype(np.float64), ncols_local=pr.n)
+    if P.device_count() == 0:
+        t = P.VecFromArray(np.zeros(len(mine)))
+        with pytest.raises(P.PermonError):
+            P.MatMult(BE, v, t)
+    P.MatDestroy(BE)
     dist.barrier()
     dist.destroy_process_group()
     ret[rank] = True
