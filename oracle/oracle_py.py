@@ -30,7 +30,7 @@ class Op(C.Structure):
     _fields_ = [("kind", C.c_int), ("n", C.c_int), ("ia", _ip), ("ja", _ip), ("a", _dp), ("d", C.c_int),
                 ("ia2", _ip), ("ja2", _ip), ("a2", _dp), ("twork", _dp), ("m", C.c_int), ("B", _dp),
                 ("rho", C.c_double), ("bwork", _dp),
-                ("pmode", C.c_int), ("pm", C.c_int), ("PG", _dp), ("porth", C.c_int), ("pw1", _dp), ("pw2", _dp)]
+                ("pmode", C.c_int), ("pm", C.c_int), ("PG", _dp), ("porth", C.c_int), ("pw1", _dp), ("pw2", _dp), ("bimplicit", C.c_int)]
 
 
 class Box(C.Structure):
@@ -65,7 +65,9 @@ class SmalxeOpts(C.Structure):
                 ("rtol_E", C.c_double), ("update_threshold", C.c_double), ("maxeig", C.c_double),
                 ("maxeig_tol", C.c_double), ("maxeig_iter", C.c_int), ("inject_maxeig", C.c_int),
                 ("inject_maxeig_set", C.c_int), ("inner_iter_min", C.c_int), ("inner_no_gtol_stop", C.c_int),
-                ("knoll", C.c_int), ("get_lambda", C.c_int), ("inner", MpgpOpts)]
+                ("knoll", C.c_int), ("get_lambda", C.c_int), ("inner", MpgpOpts),
+                ("implicit_orth", C.c_int), ("lag_enabled", C.c_int), ("lag_offset", C.c_int), ("Jstart", C.c_int), ("Jstep", C.c_int),
+                ("Jend", C.c_int), ("lag_lower", C.c_double), ("lag_upper", C.c_double)]
 
 
 class SmalxeResult(C.Structure):

@@ -183,6 +183,20 @@ static void gtg_apply(int n, int m, const double *B, const double *x, double *y,
 }
 
 static int  ggt_solve(int n, int m, const double *B, const double *r, double *y);
+/* y = B^T (B B^T)^{-1} (B x): QPPFApplyQ (qppf.c:454-502) for rows that are NOT explicitly orthonormal -- what QPPFApplyGtG computes when
+ * the rows are orthonormal implicitly (qppf.c:586-589)                                                                                  */
+static void q_apply(int n, int m, const double *B, const double *x, double *y, double *bwork)
+{
+  double s[64];
+  for (int j = 0; j < m; j++) bwork[j] = orc_dot(n, B + (size_t)j * n, x); /* G_left = G v */
+  ggt_solve(n, m, B, bwork, s);                                             /* Gt_right = (G G^T)^{-1} G_left */
+  PFOR for (int i = 0; i < n; i++)
+  {
+    double t = 0.0;
+    for (int j = 0; j < m; j++) t += B[(size_t)j * n + i] * s[j];
+    y[i] = t;
+  }
+}
 static void pf_apply_P(int n, int m, const double *G, int orth, const double *v, double *Pv, double *gl, double *y);
 
 /* the Hessian without the penalty term: A, or the MatProd P*A*P / P*A of QPTEnforceEqByProjector (applied right to left,
@@ -211,7 +225,8 @@ void orc_op_apply(const orc_op *op, const double *x, double *y)
     op_apply_hessian(op, x, y);
     return;
   }
-  gtg_apply(op->n, op->m, op->B, x, y, op->bwork);
+  if (op->bimplicit) q_apply(op->n, op->m, op->B, x, y, op->bwork);
+  else gtg_apply(op->n, op->m, op->B, x, y, op->bwork);
   v_scale(op->n, y, op->rho);
   if (op->pmode) {
     double *w = (double *)malloc(sizeof(double) * (size_t)op->n);
@@ -482,6 +497,8 @@ void orc_default_smalxe_opts(orc_smalxe_opts *o)
   o->inject_maxeig = 0; o->inject_maxeig_set = 0;                      /* :1181-1182 */
   o->inner_iter_min = 1; o->inner_no_gtol_stop = 0;                    /* :1205-1206 */
   o->knoll = 0; o->get_lambda = 0;
+  o->implicit_orth = 0;
+  o->lag_enabled = 0; o->lag_offset = 2; o->Jstart = 10; o->Jstep = 5; o->Jend = 20; o->lag_lower = 0.1; o->lag_upper = 1.1; /* :1190-1200 */
   orc_default_mpgp_opts(&o->inner);
 }
 
@@ -843,6 +860,12 @@ typedef struct {
   double       *Bu;
   orc_op       *op_inner; /* penalised operator (shares A with the outer op) */
   mpgp_t       *inner;
+  /* implicit orthonormalisation: SMALXEON norm updates (smalxe.c:265-370) */
+  int     implicit, lag_enabled, lag_offset, Jstart, Jstep, Jend;
+  double  lag_lower, lag_upper;
+  double *BtBu;            /* work[0] */
+  double  lag_normBu0;     /* the function statics of :291-293 */
+  int     lag_II, lag_J, lag_neval, lag_niter;
 } smalxe_t;
 
 /* QPSConvergedDefault for the OUTER solver (same code as converged_default, other struct) */
@@ -863,9 +886,57 @@ static void outer_converged_default(smalxe_t *o)
   else if (rnorm >= o->divtol * o->norm_rhs_div) o->reason = ORC_DIVERGED_DTOL;
 }
 
-/* QPSSMALXEUpdateNormBu_SMALXE: smalxe.c:247-261 */
+/* QPSSMALXEUpdateNormBu_SMALXEON: smalxe.c:265-285 */
+static void update_normBu_on(smalxe_t *o, const double *u, double *normBu, double *enorm)
+{
+  q_apply(o->n, o->m, o->B, u, o->BtBu, o->op_inner->bwork); /* BtBu = B'*B*u with BtB = the penalised term (Q) */
+  const double dot = orc_dot(o->n, u, o->BtBu);
+  *normBu = sqrt(dot);
+  *enorm  = *normBu / o->rtol_E;
+}
+
+/* QPSSMALXEUpdateNormBu_Lag_SMALXEON: smalxe.c:289-370 */
+static void update_normBu_lag_on(smalxe_t *o, const double *u, double *normBu, double *enorm)
+{
+  double normBu_approx, normBu_exact, enorm_exact, rdiff;
+  if (o->inner->iteration <= o->lag_offset) { /* :312-319 */
+    update_normBu_on(o, u, &normBu_exact, &enorm_exact);
+    o->lag_neval++;
+    o->lag_normBu0 = normBu_exact;
+    normBu_approx  = o->lag_normBu0;
+    o->lag_J       = o->Jstart;
+    o->lag_II      = 0;
+  } else {
+    if (o->lag_II == 0) { /* :321-339 */
+      update_normBu_on(o, u, &normBu_exact, &enorm_exact);
+      o->lag_neval++;
+      rdiff = fabs(normBu_exact / o->lag_normBu0);
+      if (rdiff >= o->lag_upper) { o->lag_II = 0; o->lag_J = o->Jstart; }
+      else if (rdiff < o->lag_lower) { o->lag_II = 0; o->lag_J = o->Jstart; }
+      else o->lag_II++;
+      o->lag_normBu0 = normBu_exact;
+    } else {
+      o->lag_II++;
+    }
+    normBu_approx = o->lag_normBu0;
+  }
+  o->lag_niter++;
+  if (o->lag_II == o->lag_J) { /* :345-348 */
+    o->lag_II = 0;
+    if (o->lag_J < o->Jend) o->lag_J += o->Jstep;
+  }
+  *normBu = normBu_approx;
+  *enorm  = *normBu / o->rtol_E;
+}
+
+/* QPSSMALXEUpdateNormBu_SMALXE: smalxe.c:247-261; the variant is chosen at set-up (:878-886) */
 static void update_normBu(smalxe_t *o, const double *u, double *normBu, double *enorm)
 {
+  if (o->implicit) {
+    if (o->lag_enabled) update_normBu_lag_on(o, u, normBu, enorm);
+    else update_normBu_on(o, u, normBu, enorm);
+    return;
+  }
   for (int j = 0; j < o->m; j++) o->Bu[j] = orc_dot(o->n, o->B + (size_t)j * o->n, u); /* Bu = B u */
   if (o->c) for (int j = 0; j < o->m; j++) o->Bu[j] += -1.0 * o->c[j];
   *normBu = orc_norm2(o->m, o->Bu);
@@ -1041,10 +1112,13 @@ int orc_smalxe_solve(orc_op *op, const double *b_user, const orc_box *bx_user, i
     rho = opts->rho_user;
   }
   orth = rows_orthonormal(n, m, B); /* QPPFSetUp :834 -> qppf.c:394 */
+  o.implicit = opts->implicit_orth; o.lag_enabled = opts->lag_enabled; o.lag_offset = opts->lag_offset;
+  o.Jstart = opts->Jstart; o.Jstep = opts->Jstep; o.Jend = opts->Jend; o.lag_lower = opts->lag_lower; o.lag_upper = opts->lag_upper;
+  o.BtBu = BtBu;
 
   /* QPTEnforceEqByPenalty(qp, rho, direct): qptransform.c:329-410; A_rho shell = matpenalized.c:212-243 */
   op_inner = *op;
-  op_inner.m = m; op_inner.B = B; op_inner.rho = rho;
+  op_inner.m = m; op_inner.B = B; op_inner.rho = rho; op_inner.bimplicit = opts->implicit_orth;
   op_inner.bwork = (double *)malloc(sizeof(double) * (size_t)(m > 0 ? m : 1));
   o.op_inner = &op_inner;
   v_copy(n, b, b_inner); /* :850-853 */
@@ -1054,7 +1128,7 @@ int orc_smalxe_solve(orc_op *op, const double *b_user, const orc_box *bx_user, i
   maxeig_inner = ORC_MAX(rho, maxeig); /* :865 */
   {
     int inject = opts->inject_maxeig;
-    if (!opts->inject_maxeig_set) inject = orth; /* :866 */
+    if (!opts->inject_maxeig_set) inject = orth || opts->implicit_orth; /* :866; QPPFGetGHasOrthonormalRows: explicitly or implicitly (qppf.c:732-740) */
     if (inject) in.maxeig = maxeig_inner;        /* :868 */
   }
   mpgp_setup(&in); /* QPSSetUp(inner) :871 */
@@ -1085,7 +1159,8 @@ int orc_smalxe_solve(orc_op *op, const double *b_user, const orc_box *bx_user, i
 
   for (i = 0; i < o.max_it; i++) { /* :957 */
     /* QPSSMALXEUpdateLambda_SMALXE :402-435: Btmu += rho * BtB u */
-    gtg_apply(n, m, B, x, BtBu, op_inner.bwork);
+    if (opts->implicit_orth) q_apply(n, m, B, x, BtBu, op_inner.bwork);
+    else gtg_apply(n, m, B, x, BtBu, op_inner.bwork);
     v_axpy(n, Btmu, rho, BtBu);
     if (o.reason) break; /* :962 */
     v_waxpy(n, b_inner, -1.0, Btmu, b); /* :965 */

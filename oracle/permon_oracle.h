@@ -96,6 +96,9 @@ typedef struct {
   const double *PG;     /* pm x n */
   int           porth;  /* G has orthonormal rows (QPPFApplyQ then skips the coarse solve, qppf.c:454-502) */
   double       *pw1, *pw2; /* two work vectors of length n */
+  /* the penalty rows are orthonormal IMPLICITLY (QPTOrthonormalizeEq with MAT_ORTH_IMPLICIT, qptransform.c:566-636): QPPFApplyGtG
+   * routes through QPPFApplyQ (qppf.c:586-589), the penalty term is rho * B^T (B B^T)^{-1} (B x)                                  */
+  int           bimplicit;
 } orc_op;
 
 /* Box constraint (QPC_Box, src/qpc/impls/box/qpcboximpl.h:5-10) optionally
@@ -154,6 +157,11 @@ typedef struct {
   int    inner_iter_min, inner_no_gtol_stop;
   int    knoll, get_lambda;
   orc_mpgp_opts inner; /* options of the inner MPGP ("smalxe_" prefix) */
+  /* QPTOrthonormalizeEq(MAT_ORTH_IMPLICIT) in front of SMALXE: B_E becomes a dummy without MatMult, so ||B u|| is updated by
+   * QPSSMALXEUpdateNormBu_SMALXEON (smalxe.c:265-285) or, with lag_enabled, by ..._Lag_SMALXEON (:289-370; defaults :1190-1200) */
+  int    implicit_orth;
+  int    lag_enabled, lag_offset, Jstart, Jstep, Jend;
+  double lag_lower, lag_upper;
 } orc_smalxe_opts;
 
 typedef struct {

@@ -124,7 +124,8 @@ struct HaloPlan {
   } *host = nullptr;
 };
 
-enum MatKind { MK_AIJ = 0, MK_ONEROW, MK_PROD, MK_PENALIZED, MK_PROJ /* P = I - G'(GG')^-1 G of a QPPF */, MK_DENSEROWS /* m x n dense rows on the device */ };
+enum MatKind { MK_AIJ = 0, MK_ONEROW, MK_PROD, MK_PENALIZED, MK_PROJ /* P = I - G'(GG')^-1 G of a QPPF */, MK_DENSEROWS /* m x n dense rows on the device */,
+               MK_DUMMY /* MatCreateDummy of the implicit orthonormalisation (permonmatorth.c:176-192): no MatMult; `A` = the matrix it stands for */ };
 
 struct _p_Mat : PObj {
   MatKind  kind = MK_AIJ;
@@ -174,6 +175,7 @@ struct _p_QPPF : PObj {   // qppfimpl.h:6-31
   bool                Bd_owned = false;
   std::vector<double> GGt, L;           // m x m and its Cholesky factor (host, replicated)
   bool                orth = false, setupcalled = false;
+  bool                implicit_orth = false;   // G_has_orthonormal_rows_implicitly (qppf.c:123-127): G stands for (G G^T)^{-1/2} G, applied as Q
   Vec                 G_left = nullptr, Gt_right = nullptr;
   // qppfimpl.h: explicitInv (apply inv(G G^T) as an explicit m x m matrix instead of two triangular solves), redundancy (number of
   // redundant coarse solves; the m x m factor is replicated on every rank here, so any value is honoured as "all ranks"), alpha_tilde
@@ -308,6 +310,7 @@ int  mat_mult_dev(Mat A, const double *x, double *y);        // raw device point
 int  mat_eqrows_dense(Mat A, double **Bd);                  // row-partitioned equality matrix -> dense M x n_local rows on the device (collective)
 int  qppf_apply_P_dev(QPPF cp, const double *x, double *y);   // y = x - G^T (G G^T)^{-1} G x on raw device pointers
 int  qppf_apply_mode_dev(QPPF cp, int mode, const double *x, double *y);   // 0: P, 1: Q, 2: G^T G
+int  qppf_coarse_solve(QPPF cp, const double *r, double *y);               // (G G^T) y = r, m host values
 int  mat_ensure_device(Mat A);                               // upload a lazily kept host split (multi-rank AIJ)
 int  mat_halo_begin(Mat A, const double *x);                 // pack + post send/recv on the comm stream
 int  mat_halo_end(Mat A);                                    // make the compute stream wait for the ghosts

@@ -359,8 +359,14 @@ PetscErrorCode QPPFSetFromOptions(QPPF cp)
   return 0;
 }
 PetscErrorCode QPPFSetG(QPPF cp, Mat G)
-{
-  if (G == cp->G) return 0;
+{   // qppf.c:116-138: a dummy left behind by the implicit orthonormalisation stands for its original matrix
+  bool implicit = false;
+  if (G && G->kind == MK_DUMMY && G->A) {
+    G        = G->A;
+    implicit = true;
+  }
+  if (G == cp->G && implicit == cp->implicit_orth) return 0;
+  cp->implicit_orth = implicit;
   pb::ref(G);
   pb::unref(cp->G);
   cp->G = G;
@@ -473,8 +479,9 @@ PetscErrorCode QPPFSetUp(QPPF cp)
   return 0;
 }
 PetscErrorCode QPPFGetGHasOrthonormalRows(QPPF cp, PetscBool *flg)
-{
-  *flg = cp->orth ? PETSC_TRUE : PETSC_FALSE;
+{   // qppf.c:732-740: explicitly or implicitly
+  PB_CHK(QPPFSetUp(cp));
+  *flg = (cp->orth || cp->implicit_orth) ? PETSC_TRUE : PETSC_FALSE;
   return 0;
 }
 
@@ -556,8 +563,10 @@ PetscErrorCode QPPFApplyCP(QPPF cp, Vec x, Vec y)
   return mvec_put(y, cp->m, s);
 }
 PetscErrorCode QPPFApplyGtG(QPPF cp, Vec v, Vec GtGv)
-{   // qppf.c:580-605 (with orthonormal rows the reference routes through ApplyQ = G^T (G v) as well)
+{   // qppf.c:580-605 (with explicitly orthonormal rows the reference routes through ApplyQ = G^T (G v) as well; with IMPLICITLY
+    // orthonormal rows ApplyQ = G^T (G G^T)^{-1} G v is the product with the orthonormalised matrix, :586-589)
   PB_CHK(QPPFSetUp(cp));
+  if (cp->implicit_orth) return QPPFApplyQ(cp, v, GtGv);
   double t[PB_MAXEQ_ALL];
   PB_CHK(qppf_G_mult(cp, v, t));
   return qppf_Gt_mult(cp, t, GtGv);
@@ -601,13 +610,18 @@ int qppf_apply_P_dev(QPPF cp, const double *x, double *y)
   PB_CHK(dense_rows_multT_host(cp->comm, cp->n, cp->m, cp->Bd, s, 1.0, y, 0));   // y = Q x
   return k_aypx(cp->n, y, -1.0, x);                                            // VecAYPX(Pv, -1, v)
 }
+int qppf_coarse_solve(QPPF cp, const double *r, double *y)
+{
+  PB_CHK(QPPFSetUp(cp));
+  return qppf_solve(cp, r, y);
+}
 int qppf_apply_mode_dev(QPPF cp, int mode, const double *x, double *y)
 {   // the shell operators of qppf.c:648-718: 0 P, 1 Q = G^T (G G^T)^{-1} G, 2 G^T G
   if (mode == 0) return qppf_apply_P_dev(cp, x, y);
   PB_CHK(QPPFSetUp(cp));
   double t[PB_MAXEQ_ALL], s[PB_MAXEQ_ALL];
   PB_CHK(dense_rows_mult_host(cp->comm, cp->n, cp->m, cp->Bd, x, t));
-  if (mode == 1 && !cp->orth) PB_CHK(qppf_solve(cp, t, s));
+  if ((mode == 1 || cp->implicit_orth) && !cp->orth) PB_CHK(qppf_solve(cp, t, s));
   else memcpy(s, t, sizeof(double) * cp->m);
   return dense_rows_multT_host(cp->comm, cp->n, cp->m, cp->Bd, s, 1.0, y, 0);
 }
@@ -1280,9 +1294,12 @@ PetscErrorCode QPTOrthonormalizeEq(QP qp, MatOrthType type, MatOrthForm form)
   PB_CHK(QPChainGetLast(qp, &qp));
   if (!qp->BE) return 0;
   if (type == MAT_ORTH_NONE) return 0;
-  if (type != MAT_ORTH_GS && type != MAT_ORTH_CHOLESKY) return err(PETSC_ERR_SUP, "QPTOrthonormalizeEq: the B200 path provides MAT_ORTH_GS and MAT_ORTH_CHOLESKY");
-  if (qp->comm->size > 1) return err(PETSC_ERR_SUP, "QPTOrthonormalizeEq is single-GPU in this round");
-  if (qp->BE && qp->BE->M > PB_MAXEQ) return err(PETSC_ERR_SUP, "QPTOrthonormalizeEq handles at most %d equality rows (got %d)", PB_MAXEQ, (int)qp->BE->M);
+  if (type != MAT_ORTH_GS && type != MAT_ORTH_CHOLESKY && type != MAT_ORTH_IMPLICIT)
+    return err(PETSC_ERR_SUP, "QPTOrthonormalizeEq: the B200 path provides MAT_ORTH_GS, MAT_ORTH_CHOLESKY and MAT_ORTH_IMPLICIT");
+  if (type != MAT_ORTH_IMPLICIT) {
+    if (qp->comm->size > 1) return err(PETSC_ERR_SUP, "explicit QPTOrthonormalizeEq is single-GPU (MAT_ORTH_IMPLICIT works on any number)");
+    if (qp->BE && qp->BE->M > PB_MAXEQ) return err(PETSC_ERR_SUP, "explicit QPTOrthonormalizeEq handles at most %d equality rows (got %d)", PB_MAXEQ, (int)qp->BE->M);
+  }
   QPPF pf;
   PB_CHK(QPGetQPPF(qp, &pf));
   PB_CHK(QPPFSetUp(pf));
@@ -1294,6 +1311,28 @@ PetscErrorCode QPTOrthonormalizeEq(QP qp, MatOrthType type, MatOrthForm form)
   PB_CHK(QPSetRhs(child, qp->b));
   if (qp->x) PB_CHK(QPSetInitialVector(child, qp->x));
   if (qp->qpc) PB_CHK(QPSetQPC(child, qp->qpc));
+  if (type == MAT_ORTH_IMPLICIT) {
+    // MatOrthRows_Implicit_Default (permonmatorth.c:176-192): nothing is computed -- T*BE is a dummy that remembers BE, the child's QPPF
+    // works on the ORIGINAL rows and applies G^T G as Q = G^T (G G^T)^{-1} G (qppf.c:123-127,586-589); c_E stays as it is (:609-611)
+    _p_Mat *D = new _p_Mat;
+    D->comm   = qp->comm;
+    D->kind   = MK_DUMMY;
+    D->m      = qp->BE->m;
+    D->M      = qp->BE->M;
+    D->n      = qp->BE->n;
+    D->N      = qp->BE->N;
+    D->rstart = qp->BE->rstart;
+    D->cstart = qp->BE->cstart;
+    D->A      = qp->BE;
+    pb::ref(qp->BE);
+    PB_CHK(qp_set_qppf(child, nullptr));
+    PB_CHK(QPSetEq(child, D, qp->cE));
+    Mat dm = D;
+    PB_CHK(MatDestroy(&dm));
+    child->postT.assign((size_t)m * m, 0.0);
+    for (int i = 0; i < m; i++) child->postT[(size_t)i * m + i] = 1.0;
+    return 0;
+  }
   // TBE
   _p_Mat *TB = new _p_Mat;
   TB->comm   = qp->comm;

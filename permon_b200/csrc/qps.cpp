@@ -547,6 +547,7 @@ struct MpgpImpl : QPSImpl {   // QPS_MPGP mpgpimpl.h:5-38
     Mat A = qps->solQP->A;
     if (A->kind == MK_PENALIZED) {
       if (A->pf && A->pf->G && A->pf->G->M > PB_MAXEQ) return false;   // the rank-m fusion keeps PB_MAXEQ accumulators; more rows: un-fused route
+      if (A->pf && A->pf->implicit_orth) return false;                 // penalised term Q = B'(BB')^-1 B: the coarse solve sits between the two rank-m halves
       A = A->A;
     }
     if (A->kind == MK_PROD) return A->M1->kind == MK_AIJ && A->M2->kind == MK_AIJ && A->comm->size == 1;
@@ -1235,6 +1236,8 @@ struct SmalxeImpl : QPSImpl {   // QPS_SMALXE smalxeimpl.h:13-67
   bool             lag_enabled = false, lag_monitor = false, lag_compare = false;
   PetscInt         lag_offset = 2, Jstart = 10, Jstep = 5, Jend = 20;
   double           lag_lower = 0.1, lag_upper = 1.1;
+  double           lag_normBu0 = 0.0;
+  PetscInt         lag_II = 0, lag_J = 0, lag_neval = 0, lag_niter = 0;
   double           normBu = NAN, normBu_old = NAN, normBu_prev = NAN, enorm = NAN;
   Vec              BtBu = nullptr;
 
@@ -1280,6 +1283,8 @@ struct SmalxeImpl : QPSImpl {   // QPS_SMALXE smalxeimpl.h:13-67
     return 0;
   }
   int update_normBu(QPS qps, Vec u, double *nBu, double *en);
+  int update_normBu_on(QPS qps, Vec u, double *nBu, double *en);
+  int update_normBu_lag_on(QPS qps, Vec u, double *nBu, double *en);
 };
 
 static SmalxeImpl *smalxe_of(QPS qps) { return (qps->impl && qps->type == QPSSMALXE) ? static_cast<SmalxeImpl *>(qps->impl) : nullptr; }
@@ -1323,9 +1328,9 @@ PetscErrorCode SmalxeImpl::setfromoptions(QPS qps)
   options_int(p, "-qps_smalxe_inner_no_gtol_stop", &inner_no_gtol_stop);
   options_real(p, "-qps_smalxe_update_threshold", &update_threshold);
   options_bool(p, "-qps_smalxe_knoll", &knoll);
-  // smalxe.c:754-762.  As in the reference the lag switches only take effect when B_E has no MatMult (the implicit orthonormalisation
-  // dummies, smalxe.c:878-886); every equality matrix of this library has one, so ||B u|| is evaluated exactly in every inner iteration
-  // (it costs no extra pass on the device: K_B reduces B u of the new iterate).
+  // smalxe.c:754-762.  As in the reference the lag switches only take effect when B_E has no MatMult (the dummy left behind by
+  // QPTOrthonormalizeEq(MAT_ORTH_IMPLICIT), smalxe.c:878-886); with an ordinary equality matrix ||B u|| is evaluated exactly in every
+  // inner iteration (on the fused path it costs no extra pass: K_B reduces B u of the new iterate).
   options_bool(p, "-qps_smalxe_norm_update_lag", &lag_enabled);
   options_bool(p, "-qps_smalxe_norm_update_lag_monitor", &lag_monitor);
   options_bool(p, "-qps_smalxe_norm_update_lag_compare", &lag_compare);
@@ -1344,6 +1349,8 @@ PetscErrorCode SmalxeImpl::setfromoptions(QPS qps)
 int SmalxeImpl::update_normBu(QPS qps, Vec u, double *nBu, double *en)
 {
   QPPF          pf = qps->solQP->pf;
+  if (qps->solQP->BE && qps->solQP->BE->kind == MK_DUMMY)   // smalxe.c:878-886: B_E has no MatMult (implicit orthonormalisation)
+    return lag_enabled ? update_normBu_lag_on(qps, u, nBu, en) : update_normBu_on(qps, u, nBu, en);
   const double *Bd, *du;
   int           m;
   PB_CHK(qppf_dense_rows(pf, &Bd, &m));
@@ -1352,6 +1359,70 @@ int SmalxeImpl::update_normBu(QPS qps, Vec u, double *nBu, double *en)
   PB_CHK(dense_rows_mult_host(qps->comm, u->n, m, Bd, du, t));
   for (int j = 0; j < m; j++) s += t[j] * t[j];
   *nBu = sqrt(s);
+  *en  = *nBu / rtol_E;
+  return 0;
+}
+
+// QPSSMALXEUpdateNormBu_SMALXEON smalxe.c:265-285: ||B u|| = sqrt(u' B'B u) with B'B the penalised term of the inner Hessian
+// (Q = B'(BB')^-1 B for implicitly orthonormal rows); B'B u is left in work[0] for the multiplier update
+int SmalxeImpl::update_normBu_on(QPS qps, Vec u, double *nBu, double *en)
+{
+  double dot;
+  PB_CHK(QPPFApplyGtG(qps->solQP->pf, u, BtBu));
+  PB_CHK(vec_dot(u, BtBu, &dot));
+  *nBu = sqrt(dot);
+  *en  = *nBu / rtol_E;
+  return 0;
+}
+// QPSSMALXEUpdateNormBu_Lag_SMALXEON smalxe.c:289-370: the norm is re-evaluated every J-th inner iteration only (J grows from Jstart to
+// Jend in steps of Jstep while consecutive exact values stay within [lower, upper) of each other); in between the last exact value is used.
+// The reference keeps the counters in function statics; here they live in the solver object.
+int SmalxeImpl::update_normBu_lag_on(QPS qps, Vec u, double *nBu, double *en)
+{
+  double normBu_approx, normBu_exact = 0.0, enorm_exact, rdiff;
+  bool   eval = false;
+  if (inner->iteration <= lag_offset) {
+    PB_CHK(update_normBu_on(qps, u, &normBu_exact, &enorm_exact));
+    eval = true;
+    lag_neval++;
+    lag_normBu0   = normBu_exact;
+    normBu_approx = lag_normBu0;
+    lag_J         = Jstart;
+    lag_II        = 0;
+  } else {
+    if (lag_II == 0) {
+      PB_CHK(update_normBu_on(qps, u, &normBu_exact, &enorm_exact));
+      eval = true;
+      lag_neval++;
+      rdiff = fabs(normBu_exact / lag_normBu0);
+      if (rdiff >= lag_upper || rdiff < lag_lower) {
+        lag_II = 0;
+        lag_J  = Jstart;
+      } else {
+        lag_II++;
+      }
+      lag_normBu0 = normBu_exact;
+    } else {
+      lag_II++;
+    }
+    normBu_approx = lag_normBu0;
+  }
+  lag_niter++;
+  if (lag_II == lag_J) {
+    lag_II = 0;
+    if (lag_J < Jend) lag_J += Jstep;
+  }
+  if (lag_compare) {
+    if (!eval) PB_CHK(update_normBu_on(qps, u, &normBu_exact, &enorm_exact));
+    rdiff           = fabs(normBu_approx - normBu_exact) / normBu_exact;
+    const char sign = (normBu_exact > normBu_approx) ? '>' : ((normBu_exact < normBu_approx) ? '<' : '=');
+    vprintf_viewer(nullptr, "QPSSMALXEUpdateNormBu_Lag_SMALXEON: out %3d in %4d   II=%2d J=%2d niter=%4d neval=%4d   ||Bu||=%.4e  %c  %.4e=~||Bu|| relative_difference=%.4e %c\n",
+                   (int)qps->iteration, (int)inner->iteration, (int)lag_II, (int)lag_J, (int)lag_niter, (int)lag_neval, normBu_exact, sign, normBu_approx, rdiff, rdiff > 10 ? sign : ' ');
+  } else if (lag_monitor) {
+    vprintf_viewer(nullptr, "QPSSMALXEUpdateNormBu_Lag_SMALXEON: out %3d in %4d   II=%2d J=%2d niter=%4d neval=%4d\n", (int)qps->iteration, (int)inner->iteration, (int)lag_II,
+                   (int)lag_J, (int)lag_niter, (int)lag_neval);
+  }
+  *nBu = normBu_approx;
   *en  = *nBu / rtol_E;
   return 0;
 }

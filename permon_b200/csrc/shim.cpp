@@ -1819,8 +1819,14 @@ int mat_mult_dev(Mat A, const double *x, double *y)
     PB_CHK(mat_mult_dev(A->A, x, y));
     double t[PB_MAXEQ_ALL];
     PB_CHK(dense_rows_mult_host(A->comm, A->n, m, Bd, x, t));                 // t = B x, rank-ordered sums
+    if (A->pf->implicit_orth) {   // implicitly orthonormal rows: the penalised term is Q = B^T (B B^T)^{-1} B (qppf.c:586-589)
+      double s[PB_MAXEQ_ALL];
+      PB_CHK(qppf_coarse_solve(A->pf, t, s));
+      memcpy(t, s, sizeof(double) * m);
+    }
     return dense_rows_multT_host(A->comm, A->n, m, Bd, t, A->rho, y, 1);      // y += rho B^T t
   }
+  case MK_DUMMY: return err(PETSC_ERR_SUP, "MatMult: a dummy matrix (implicit orthonormalisation) has no MatMult");
   default: return err(PETSC_ERR_SUP, "MatMult: unsupported matrix kind for device vectors");
   }
 }

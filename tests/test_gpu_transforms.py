@@ -124,3 +124,42 @@ def test_equality_only_project_then_cg(P):
     assert np.linalg.norm(r["x"] - xo) <= 1e-7 * np.linalg.norm(xo)
     assert np.max(np.abs(B @ r["x"])) <= 1e-8 * n
     P.QPDestroy(qp)
+
+
+@pytest.mark.parametrize("lag", [False, True])
+@pytest.mark.parametrize("with_c", [False, True])
+def test_implicit_orthonormalisation_smalxeon(P, lag, with_c):
+    """QPTOrthonormalizeEq(MAT_ORTH_IMPLICIT) (qptransform.c:566-636, permonmatorth.c:176-192): B_E becomes a dummy without MatMult, the
+    QPPF applies G'G as Q = G'(GG')^-1 G, and SMALXE switches to the u'B'Bu norm update (smalxe.c:265-285) -- with
+    -qps_smalxe_norm_update_lag to its lagged variant (:289-370).  Against the oracle's restatement of the same chain, and against the
+    explicitly (Cholesky) orthonormalised problem, which has the same solution."""
+    pr = PR.obstacle2d(32)
+    n = pr.n
+    B = eq_rows(n, 3)
+    pr.b = np.asarray(pr.b) * (1.0 + 40.0 * np.sin(np.arange(n) * 0.013) ** 2)
+    c = np.array([-0.6 * n, -0.3 * B[1].sum(), 0.05 * n]) if with_c else None
+    lag_opts = " -qps_smalxe_norm_update_lag -qps_smalxe_norm_update_lag_offset 3 -qps_smalxe_norm_update_lag_start 4 -qps_smalxe_norm_update_lag_step 2 -qps_smalxe_norm_update_lag_end 8" if lag else ""
+    qp, vx, keep = build_qp(P, pr, B, c)
+    P.QPTOrthonormalizeEq(qp, "implicit")
+    r = run(P, qp, vx, "-qps_type smalxe -qps_rtol 1e-8" + lag_opts)
+    assert r["type"] == "smalxe" and r["reason"] > 0
+    P.QPDestroy(qp)
+
+    op = O.Operator(pr.ia, pr.ja, pr.a)
+    bx = O.BoxC(n, pr.lb, None)
+    kw = dict(rtol=1e-8, implicit_orth=1)
+    if lag:
+        kw.update(lag_enabled=1, lag_offset=3, Jstart=4, Jstep=2, Jend=8)
+    xo, ro = O.smalxe_solve(op, pr.b, bx, B, c, np.zeros(n), O.smalxe_opts(**kw))
+    assert ro["reason"] == r["reason"]
+    assert abs(r["its"] - ro["outer_its"]) <= max(2, 0.15 * ro["outer_its"])
+    assert abs(r["stats"]["inner_iter_accu"] - ro["inner_its_accu"]) <= max(8, 0.15 * ro["inner_its_accu"])
+    assert np.linalg.norm(r["x"] - xo) <= 1e-6 * np.linalg.norm(xo)
+    assert np.max(np.abs(B @ r["x"] - (c if with_c else 0.0))) <= 1e-6 * n
+    assert np.min(r["x"] - pr.lb) >= -1e-12
+    # the explicitly orthonormalised chain (Cholesky) is the same problem
+    qp2, vx2, keep2 = build_qp(P, pr, B, c)
+    P.QPTOrthonormalizeEq(qp2, "cholesky")
+    r2 = run(P, qp2, vx2, "-qps_type smalxe -qps_rtol 1e-8")
+    assert np.linalg.norm(r["x"] - r2["x"]) <= 1e-5 * np.linalg.norm(r2["x"])
+    P.QPDestroy(qp2)

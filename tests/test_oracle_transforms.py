@@ -67,3 +67,27 @@ def test_projected_chain_reaches_the_solution_of_the_original_problem():
     assert r["reason"] == r2["reason"] == 2
     assert np.linalg.norm(x - x2) <= 1e-6 * np.linalg.norm(x2)
     assert np.sum(x - pr.lb < 1e-12) == np.sum(x2 - pr.lb < 1e-12) > 10
+
+
+def test_implicit_orthonormalisation_restatement_is_consistent():
+    """QPTOrthonormalizeEq(MAT_ORTH_IMPLICIT) + SMALXE with the u'B'Bu norm update (smalxe.c:265-285) and its lagged variant (:289-370):
+    penalising with Q = B'(BB')^-1 B instead of B'B changes the path, not the solution.  (Parity unpinned against the reference: its outputs
+    for this chain need FETI / MUMPS; the restatement is checked against the untransformed SMALXE solve.)"""
+    pr = PR.obstacle2d(24)
+    n = pr.n
+    rng = np.random.default_rng(3)
+    B = np.zeros((3, n))
+    B[0] = 1.0
+    B[1, n // 3:] = rng.random(n - n // 3)
+    B[2] = np.sin(np.arange(n) * 0.05)
+    b = np.asarray(pr.b) * (1.0 + 40.0 * np.sin(np.arange(n) * 0.013) ** 2)
+    for c in (None, np.array([-0.6 * n, -0.3 * B[1].sum(), 0.05 * n])):
+        bx = O.BoxC(n, pr.lb, None)
+        x0, r0 = O.smalxe_solve(O.Operator(pr.ia, pr.ja, pr.a), b, bx, B, c, np.zeros(n), O.smalxe_opts(rtol=1e-9))
+        x1, r1 = O.smalxe_solve(O.Operator(pr.ia, pr.ja, pr.a), b, bx, B, c, np.zeros(n), O.smalxe_opts(rtol=1e-9, implicit_orth=1))
+        x2, r2 = O.smalxe_solve(O.Operator(pr.ia, pr.ja, pr.a), b, bx, B, c, np.zeros(n),
+                                O.smalxe_opts(rtol=1e-9, implicit_orth=1, lag_enabled=1, lag_offset=3, Jstart=4, Jstep=2, Jend=8))
+        assert r0["reason"] == r1["reason"] == r2["reason"] == 2
+        assert np.linalg.norm(x1 - x0) <= 1e-6 * np.linalg.norm(x0)
+        assert np.linalg.norm(x2 - x0) <= 1e-6 * np.linalg.norm(x0)
+        assert np.max(np.abs(B @ x1 - (0.0 if c is None else c))) <= 1e-5 * n
