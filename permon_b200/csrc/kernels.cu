@@ -304,6 +304,9 @@ __device__ __forceinline__ void pdl_enter()
   asm volatile("griddepcontrol.wait;" ::: "memory");
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 }
+// The producer warp of the TMA rings stages partial tiles / unaligned vectors with plain (generic-proxy) shared stores into slots that
+// bulk copies (async proxy) write in other rounds: order the two proxies explicitly before the slot is handed over.
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 static bool pdl_enabled()
 {
   static int on = -1;
@@ -745,6 +748,7 @@ __global__ void __launch_bounds__(NT + 32) k_spmv_tma(CsrDev A, const double *__
           const double *src = epi.vsrc(v) + r0;
           for (int t = lane; t < r1 - r0; t += 32) vs[t] = src[t];
         }
+        fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) {
           meta_k0a[s] = k0a;
@@ -1082,6 +1086,7 @@ __global__ void __launch_bounds__(PK_CT + 32, MINB) k_spmv_pk(CsrDev A, const do
           const double *src = epi.vsrc(v) + r0;
           for (int t = lane; t < r1 - r0; t += 32) vs[t] = src[t];
         }
+        fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) {
           mbar_arrive_expect_tx(&full_bar[s], blob_bytes);
@@ -1294,6 +1299,7 @@ __global__ void __launch_bounds__(PK_CT + 32, 4) k_spmv_st(CsrDev A, const doubl
           const double *src = epi.vsrc(v) + r0;
           for (int t = lane; t < r1 - r0; t += 32) vs[t] = src[t];
         }
+        fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive(&full_bar[s]);
       }
