@@ -752,6 +752,13 @@ def solve_problem(pr, qps_type=None, options: str = "", monitor=None, keep=False
         mats.append(BE)
         if cE is not None:
             extra.append(cE)
+    for t in getattr(pr, "transforms", ()):     # QP transforms applied before the solver sees the chain (QPT*, qptransform.c)
+        if t.startswith("orth_"):
+            QPTOrthonormalizeEq(qp, t[len("orth_"):])
+        elif t == "projector":
+            QPTEnforceEqByProjector(qp)
+        else:
+            raise ValueError(t)
     qps = QPSCreate()
     if qps_type:
         QPSSetType(qps, qps_type)

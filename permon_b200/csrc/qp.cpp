@@ -1297,7 +1297,6 @@ PetscErrorCode QPTOrthonormalizeEq(QP qp, MatOrthType type, MatOrthForm form)
   if (type != MAT_ORTH_GS && type != MAT_ORTH_CHOLESKY && type != MAT_ORTH_IMPLICIT)
     return err(PETSC_ERR_SUP, "QPTOrthonormalizeEq: the B200 path provides MAT_ORTH_GS, MAT_ORTH_CHOLESKY and MAT_ORTH_IMPLICIT");
   if (type != MAT_ORTH_IMPLICIT) {
-    if (qp->comm->size > 1) return err(PETSC_ERR_SUP, "explicit QPTOrthonormalizeEq is single-GPU (MAT_ORTH_IMPLICIT works on any number)");
     if (qp->BE && qp->BE->M > PB_MAXEQ) return err(PETSC_ERR_SUP, "explicit QPTOrthonormalizeEq handles at most %d equality rows (got %d)", PB_MAXEQ, (int)qp->BE->M);
   }
   QPPF pf;

@@ -1710,7 +1710,8 @@ PetscErrorCode MatCreateProd(MPI_Comm comm, PetscInt nmat, const Mat *mats, Mat 
   Mat M2 = mats[0], M1 = mats[1];
   for (Mat F : {M1, M2})
     if (F->kind != MK_AIJ && F->kind != MK_PROJ && F->kind != MK_PROD && F->kind != MK_PENALIZED) return err(PETSC_ERR_SUP, "MatCreateProd: unsupported factor kind");
-  if (comm->size > 1) return err(PETSC_ERR_SUP, "product operators are single-GPU in this round");
+  // several GPUs: the factors are applied one after the other with their own halo exchanges / reductions (the un-fused route; the fused
+  // MPGP driver takes product Hessians on one GPU only, qps.cpp: fused_eligible)
   if (M1->n != M2->m) return err(PETSC_ERR_ARG_SIZ, "MatCreateProd: inner dimensions differ (%d vs %d)", (int)M1->n, (int)M2->m);
   _p_Mat *A = new _p_Mat;
   A->comm = comm;
@@ -1723,7 +1724,7 @@ PetscErrorCode MatCreateProd(MPI_Comm comm, PetscInt nmat, const Mat *mats, Mat 
   A->M = M1->M;
   A->n = M2->n;
   A->N = M2->N;
-  PB_CHK(vec_create(comm, M2->m, M2->m, &A->twork));
+  PB_CHK(vec_create(comm, M2->m, comm->size > 1 ? PETSC_DECIDE : M2->m, &A->twork));
   *mat = A;
   return 0;
 }

@@ -64,6 +64,31 @@ def build_problem(kind, rank, size):
         loc.B = None
         loc.c = full.c[mine].copy()
         return full, loc, starts, "-qps_rtol 1e-9", dict(rtol=1e-9)
+    if kind == "projector":
+        # SURVEY 8f rank 2 on several GPUs: QPTOrthonormalizeEq (Cholesky) + QPTEnforceEqByProjector, then SMALXE on (P A P, P b, box, T B):
+        # same solution as plain SMALXE on the untransformed problem (checked against the oracle's solve of that)
+        N = 48
+        n = N * N
+        starts = PR.row_partition(n, size, align=N)
+        full = PR.obstacle2d(N)
+        loc = PR.obstacle2d(N, rows=(starts[rank], starts[rank + 1]))
+        scale = 1.0 + 40.0 * np.sin(np.arange(n) * 0.013) ** 2
+        full.b = np.asarray(full.b) * scale
+        loc.b = np.asarray(loc.b) * scale[starts[rank]:starts[rank + 1]]
+        rng = np.random.default_rng(3)
+        B = np.zeros((2, n))
+        B[0] = 1.0
+        B[1, n // 3:] = rng.random(n - n // 3)
+        import scipy.sparse as sp
+        full.B = B
+        full.c = None
+        mine = [rank] if rank < 2 else []           # row-partitioned AIJ equality matrix with global columns
+        S = sp.csr_matrix(B[mine, :]) if mine else sp.csr_matrix((0, n))
+        loc.BE_local = (S.indptr.astype(np.int32), S.indices.astype(np.int32), S.data.astype(np.float64))
+        loc.B = None
+        loc.c = None
+        loc.transforms = ("orth_cholesky", "projector")
+        return full, loc, starts, "-qps_type smalxe -qps_rtol 1e-8", dict(rtol=1e-8)
     raise ValueError(kind)
 
 
@@ -87,7 +112,7 @@ def main():
     out = {}
     for kind in kinds:
         full, loc, starts, opts, okw = build_problem(kind, rank, size)
-        qtype = "smalxe" if kind.startswith("smalxe") else "mpgp"
+        qtype = "smalxe" if (kind.startswith("smalxe") or kind == "projector") else "mpgp"
         r = P.solve_problem(loc, qtype, opts)
         xs = [torch.zeros(starts[q + 1] - starts[q], dtype=torch.float64, device=dev) for q in range(size)]
         dist.all_gather(xs, torch.from_numpy(r.x).to(dev))
@@ -96,7 +121,7 @@ def main():
             from oracle import oracle_py as O
             op = O.Operator(full.ia, full.ja, full.a)
             bx = O.BoxC(full.n, full.lb, full.ub)
-            if kind.startswith("smalxe"):
+            if kind.startswith("smalxe") or kind == "projector":
                 xr, ro = O.smalxe_solve(op, full.b, bx, full.B, full.c, full.x0, O.smalxe_opts(**okw))
                 op.c.m = 0
                 its_ref, its = ro["inner_its_accu"], r.stats["inner_iter_accu"]
@@ -112,7 +137,7 @@ def main():
             fo, fg = O.objective(op, full.b, xr), O.objective(op, full.b, x)
             out[kind] = dict(its=its, its_ref=its_ref, band=ro.get("band"), reason=r.reason, reason_ref=ro["reason"], relx=relx,
                              relf=float(abs(fg - fo) / abs(fo)), counts=r.counts,
-                             counts_ref={k: ro[k] for k in ("ncg", "nexp", "nprop", "nmv")} if not kind.startswith("smalxe") else None)
+                             counts_ref={k: ro[k] for k in ("ncg", "nexp", "nprop", "nmv")} if not (kind.startswith("smalxe") or kind == "projector") else None)
         dist.barrier()
     if rank == 0:
         print("MGPU_RESULT " + json.dumps(out), flush=True)
