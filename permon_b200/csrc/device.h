@@ -270,6 +270,7 @@ int k_pmax(int n, double *w, const double *x, const double *y);
 int k_pmin(int n, double *w, const double *x, const double *y);
 int k_dot(int n, const double *x, const double *y, RedBuf rb);          // rb.out[0] = local x.y
 int k_mdot2(int n, const double *x, const double *y0, const double *y1, RedBuf rb);   // out[0]=x.y0, out[1]=x.y1
+int k_cg_update(int n, double a, const double *p, const double *w, double *x, double *r, RedBuf rb);   // x += a p; r -= a w; out[0] = r.r
 int k_dense_rows_mult(int n, int m, const double *B, const double *x, RedBuf rb);     // out[j] = B_j . x
 int k_dense_rows_multT_add(int n, int m, const double *B, const double *t /*device, m*/, double scale, double *y, int accumulate);
 int k_rows_forward_solve(int n, int m, const double *L /*host, m x m lower*/, const double *G, double *TB);   // L TB = G, column by column

@@ -3301,6 +3301,17 @@ int k_dot(int n, const double *x, const double *y, RedBuf rb)
 {
   return launch_red<0>(n, [=] __device__(int i, double(&a)[PB_NRED]) { a[0] += x[i] * y[i]; }, rb, KF_VEC, 16.0 * n);
 }
+// CG update in one pass (KSPSolve_CG: VecAXPY(X, a, P); VecAXPY(R, -a, W); dp = VecNorm(R); beta = VecDot(R, R)): x += a p, r -= a w,
+// out[0] = r.r of the new residual -- the norm and the dot product of the reference are the same sum
+int k_cg_update(int n, double a, const double *p, const double *w, double *x, double *r, RedBuf rb)
+{
+  return launch_red<0>(n, [=] __device__(int i, double(&acc)[PB_NRED]) {
+    x[i] += a * p[i];
+    const double ri = r[i] + (-a) * w[i];
+    r[i]            = ri;
+    acc[0] += ri * ri;
+  }, rb, KF_VEC, 48.0 * n);
+}
 int k_mdot2(int n, const double *x, const double *y0, const double *y1, RedBuf rb)
 {
   return launch_red<0>(n, [=] __device__(int i, double(&a)[PB_NRED]) {

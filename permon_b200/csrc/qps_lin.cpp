@@ -52,8 +52,80 @@ struct KspImpl : QPSImpl {
   }
   // QPSSolve_KSP (qpsksp.c:137-153) -> KSPSolve on KSPCG / PCNONE / KSP_NORM_UNPRECONDITIONED / non-zero initial guess
   // (QPSCreate_KSP qpsksp.c:232-253); the stopping test is the QPS one (QPSKSPConverged_KSP qpsksp.c:5-14).
+  // Fused form for a packed AIJ Hessian on one GPU (-qps_ksp_b200_driver generic switches it off): per iteration ONE SpMV kernel that
+  // also reduces p.Ap (the power-method skeleton, kernels.cu: EpiPower with s = 1), ONE update kernel (x += a p, r -= a w, r.r) and the
+  // direction update -- 3 kernels and 2 host round trips instead of 7 and 4, 11 vector passes instead of 15.  Same recurrence, same
+  // stopping test; the products p.w and r.r are summed by other kernels than in the un-fused form (deterministic, different order).
+  bool fused_ok(QPS qps) const
+  {
+    Mat A = qps->solQP->A;
+    std::string d = "auto";
+    options_string(qps->prefix, "-qps_ksp_b200_driver", &d);
+    if (d == "generic") return false;
+    if (A->kind != MK_AIJ || A->comm->size != 1 || A->m != A->n || A->eq_host) return false;
+    if (mat_ensure_device(A)) return false;
+    return A->Ad.kind == 3 || A->Ad.kind == 4;
+  }
+  PetscErrorCode solve_fused(QPS qps)
+  {
+    QP       qp = qps->solQP;
+    Mat      A = qp->A;
+    Vec      b = qp->b, x = qp->x, R = W.work[0], P = W.work[1], Wv = W.work[2];
+    double   beta, betaold = 1.0, dpi, dp;
+    PetscInt i = 0;
+    const PetscInt n = x->n;
+    Reducer &Rd = reducer(qps->comm);
+    PB_CHK(mat_mult(A, x, R));
+    PB_CHK(VecAYPX(R, -1.0, b));
+    PB_CHK(vec_dot(R, R, &beta));
+    dp             = sqrt(beta);
+    qps->iteration = 0;
+    qps->rnorm     = dp;
+    PB_CHK(qps->convergencetest(qps, &qps->reason));
+    if (qps->reason) return 0;
+    do {
+      if (beta == 0.0) {
+        qps->reason = KSP_CONVERGED_ATOL;
+        break;
+      }
+      if (!i) {
+        PB_CHK(VecCopy(R, P));
+      } else {
+        PB_CHK(VecAYPX(P, beta / betaold, R));
+      }
+      const double *dP, *dW;
+      double       *dWw, *dx, *dR;
+      PB_CHK(vec_dev_read(P, &dP));
+      PB_CHK(vec_dev_write(Wv, &dWw));
+      PB_CHK(k_power_step(A->Ad, dP, 1.0, dWw, Rd.rb));   // w = A p, out[0] = p.w
+      PB_CHK(Rd.fetch());
+      dpi     = Rd.sum(0);
+      betaold = beta;
+      if (!(dpi > 0.0)) {
+        qps->reason = KSP_DIVERGED_INDEFINITE_MAT;
+        break;
+      }
+      const double a = beta / dpi;
+      PB_CHK(vec_dev_read(Wv, &dW));
+      PB_CHK(vec_dev_rw(x, &dx));
+      PB_CHK(vec_dev_rw(R, &dR));
+      PB_CHK(k_cg_update(n, a, dP, dW, dx, dR, Rd.rb));
+      PB_CHK(Rd.fetch());
+      beta           = Rd.sum(0);
+      dp             = sqrt(beta);
+      qps->iteration = i + 1;
+      qps->rnorm     = dp;
+      PB_CHK(qps->convergencetest(qps, &qps->reason));
+      i++;
+      if (qps->reason) break;
+    } while (i < qps->max_it);
+    if (!qps->reason) qps->reason = KSP_DIVERGED_ITS;
+    qps->iteration = i;
+    return 0;
+  }
   PetscErrorCode solve(QPS qps) override
   {
+    if (fused_ok(qps)) return solve_fused(qps);
     QP     qp = qps->solQP;
     Mat    A = qp->A;
     Vec    b = qp->b, x = qp->x, R = W.work[0], P = W.work[1], Wv = W.work[2];

@@ -50,12 +50,14 @@ def solve(P, pr, b, x0, qps_type=None, G=None, c=None, options="-qps_rtol 1e-9")
     return out
 
 
+@pytest.mark.parametrize("driver", ["auto", "generic"])
 @pytest.mark.parametrize("N", [24, 96])
-def test_unconstrained_qp_defaults_to_cg(P, N):
+def test_unconstrained_qp_defaults_to_cg(P, N, driver):
+    """driver auto: the fused CG (SpMV + p.Ap in one kernel, x / r update + r.r in one kernel); generic: one kernel per KSPCG call"""
     pr = PR.obstacle2d(N)
     rng = np.random.default_rng(N)
     b, x0 = rng.standard_normal(pr.n), rng.standard_normal(pr.n)
-    r = solve(P, pr, b, x0)                                        # no type given, no constraints -> "ksp"
+    r = solve(P, pr, b, x0, options=f"-qps_rtol 1e-9 -qps_ksp_b200_driver {driver}")     # no type given, no constraints -> "ksp"
     assert r["type"] == "ksp" and r["solved"]
     xo, ro = O.cg_solve(O.Operator(pr.ia, pr.ja, pr.a), b, x0, O.lin_opts(rtol=1e-9))
     assert r["reason"] == ro["reason"] == 2
