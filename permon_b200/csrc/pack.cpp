@@ -97,6 +97,16 @@ struct TileDict {
 };
 }   // namespace
 
+// row `c` (columns jc, values ac, len entries) has the same (column - row, value) list as the row before it (jp, ap): every column is the
+// previous row's + 1 and the value bits agree.  A previous row that passed the stencil scan is sorted, so this one is sorted as well.
+static inline bool row_is_shift_of(const int *jc, const double *ac, const int *jp, const double *ap, int len)
+{
+  if (len <= 0) return false;
+  int ok = 1;
+  for (int k = 0; k < len; k++) ok &= (jc[k] == jp[k] + 1);
+  return ok && memcmp(ac, ap, sizeof(double) * (size_t)len) == 0;
+}
+
 // h_off: ntiles+1 offsets in units of 16 bytes.  Returns 0 on success; `packed` false when packing is not applicable
 // (a tile whose non-zero count or row lengths do not fit the 16-bit row offsets).
 //
@@ -151,7 +161,16 @@ int pk_build(int n, const int *ia, const int *ja, const double *a, RawBuf &blob,
         int      L = 0, pd[8];
         uint64_t pb[8];
         bool     st = (nnz > 0);
+        // a row whose columns are the previous row's + 1 with the same value bits has the previous row's (delta, value) list: nothing to
+        // merge and the same presence byte (almost every row of a grid operator: the scan then costs two compares per non-zero)
+        unsigned char same[TR];
+        int           prev_k = 0, prev_len = -1;
         for (int r = r0; r < r1 && st; r++) {
+          const int rk = ia[r], rlen = ia[r + 1] - rk;
+          same[r - r0] = (rlen == prev_len) && row_is_shift_of(ja + rk, a + rk, ja + prev_k, a + prev_k, rlen);
+          prev_k       = rk;
+          prev_len     = rlen > 0 ? rlen : -1;
+          if (same[r - r0]) continue;
           int j = 0, prev_d = 0;
           for (int k = ia[r]; k < ia[r + 1]; k++) {
             uint64_t b;
@@ -186,6 +205,10 @@ int pk_build(int n, const int *ia, const int *ja, const double *a, RawBuf &blob,
         }
         if (st) {
           for (int r = r0; r < r1; r++) {
+            if (same[r - r0]) {
+              masks_tmp[r] = masks_tmp[r - 1];
+              continue;
+            }
             int      j = 0;
             unsigned m = 0;
             for (int k = ia[r]; k < ia[r + 1]; k++) {
@@ -424,7 +447,19 @@ int pk_stencil_windowed(int n, const int *ia, const int *ja, const double *a, in
       uint64_t  pb[8];
       bool      st_ok = true;
       unsigned char *mk = st.masks.data() + (size_t)t * TR;
+      unsigned char  same[TR];   // same (delta, value) list as the previous row (see pk_build)
+      int            prev_k = 0, prev_len = -1;
       for (int r = r0; r < r1 && st_ok; r++) {
+        const int rk = ia[r], rlen = ia[r + 1] - rk;
+        // only rows without ghost columns qualify: the previous row had none (prev_len is reset otherwise) and this row's first / last
+        // column (sorted: checked for the previous row, whose shift this one is) lie inside the diagonal block
+        same[r - r0] = (rlen == prev_len) && ja[rk] - coff >= 0 && ja[rk + rlen - 1] - coff < ncols && row_is_shift_of(ja + rk, a + rk, ja + prev_k, a + prev_k, rlen);
+        prev_k       = rk;
+        prev_len     = rlen > 0 ? rlen : -1;
+        if (same[r - r0]) {
+          nd += rlen;
+          continue;
+        }
         int  j = 0, prev_d = 0;
         bool first = true;
         for (int k = ia[r]; k < ia[r + 1]; k++) {
@@ -433,6 +468,7 @@ int pk_stencil_windowed(int n, const int *ia, const int *ja, const double *a, in
             mine.row.push_back(r);
             mine.gcol.push_back(ja[k]);
             mine.val.push_back(a[k]);
+            prev_len = -1;             // the next row is scanned entry by entry
             continue;
           }
           uint64_t b;
@@ -472,6 +508,10 @@ int pk_stencil_windowed(int n, const int *ia, const int *ja, const double *a, in
         continue;
       }
       for (int r = r0; r < r1; r++) {   // presence bytes against the final pattern of the tile
+        if (same[r - r0]) {
+          mk[r - r0] = mk[r - r0 - 1];
+          continue;
+        }
         int      j = 0;
         unsigned m = 0;
         for (int k = ia[r]; k < ia[r + 1]; k++) {
