@@ -102,9 +102,14 @@ struct TileDict {
 static inline bool row_is_shift_of(const int *jc, const double *ac, const int *jp, const double *ap, int len)
 {
   if (len <= 0) return false;
-  int ok = 1;
-  for (int k = 0; k < len; k++) ok &= (jc[k] == jp[k] + 1);
-  return ok && memcmp(ac, ap, sizeof(double) * (size_t)len) == 0;
+  uint64_t acc = 0;   // branch-free: OR of the value-bit differences and of (column - previous column - 1)
+  for (int k = 0; k < len; k++) {
+    uint64_t x, y;
+    memcpy(&x, ac + k, 8);
+    memcpy(&y, ap + k, 8);
+    acc |= (x ^ y) | (uint64_t)(uint32_t)(jc[k] - jp[k] - 1);
+  }
+  return acc == 0;
 }
 
 // h_off: ntiles+1 offsets in units of 16 bytes.  Returns 0 on success; `packed` false when packing is not applicable
