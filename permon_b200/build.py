@@ -32,16 +32,24 @@ def build(force: bool = False, verbose: bool = False) -> str:
     hdr_paths = [os.path.join(CSRC, h) for h in HEADERS]
     objs = []
     relink = force or not os.path.exists(LIB)
+    todo = []
     for src in SOURCES:
         sp = os.path.join(CSRC, src)
         op = os.path.join(OBJ, src.rsplit(".", 1)[0] + ".o")
         objs.append(op)
         if force or _newer(sp, op) or any(_newer(h, op) for h in hdr_paths):
-            cmd = [NVCC, *ARCH, *COMMON, "-x", "cu", "-c", sp, "-o", op]
+            todo.append([NVCC, *ARCH, *COMMON, "-x", "cu", "-c", sp, "-o", op])
+    if todo:   # the translation units are independent: compile them side by side (kernels.cu dominates)
+        from concurrent.futures import ThreadPoolExecutor
+
+        def run(cmd):
             if verbose:
                 print(" ".join(cmd), flush=True)
             subprocess.check_call(cmd)
-            relink = True
+
+        with ThreadPoolExecutor(max_workers=min(len(todo), os.cpu_count() or 1)) as ex:
+            list(ex.map(run, todo))
+        relink = True
     if relink:
         cmd = [NVCC, *ARCH, "-shared", "-ccbin", "/usr/bin/g++", "-o", LIB, *objs, "-lnccl", "-lgomp", "-Xlinker", "--no-undefined"]
         if verbose:

@@ -1848,12 +1848,8 @@ static int launch_st(const CsrDev &A, const double *x, const Epi &epi, TileOrder
 template <class Epi, int LMAX>
 static int launch_sd_l(const CsrDev &A, const double *x, const Epi &epi, TileOrder ord)
 {
-  static int minb = 0;
-  if (!minb) {
-    const char *e = getenv("PERMON_B200_SD_OCC");
-    minb = e ? atoi(e) : 5;
-    if (minb != 4 && minb != 6) minb = 5;
-  }
+  // CTAs per SM: 5 for one row per thread (48 registers), 4 for two (64).  The other occupancies were measured and lost (4: 0.207 ms, 6:
+  // 0.133 ms against 0.127 ms on C2; profiles/r2_ab_kernel_variants.txt) -- only the winners are instantiated, which also halves the build time.
   static int pairs = -1;
   if (pairs < 0) {
     const char *e = getenv("PERMON_B200_SD_PAIRS");   // measured on C2 / C3: one row per thread is 2-10 % faster (more warps in flight); pairs stay selectable
@@ -1861,13 +1857,7 @@ static int launch_sd_l(const CsrDev &A, const double *x, const Epi &epi, TileOrd
   }
   if (pairs && (A.n % 2 == 0) && aligned16(x) && epi.pair_ok()) {
     // two adjacent rows per thread, 16-byte accesses
-    static int minb2 = 0;
-    if (!minb2) {
-      const char *e = getenv("PERMON_B200_SD2_OCC");
-      minb2 = e ? atoi(e) : 4;
-      if (minb2 != 3 && minb2 != 5) minb2 = 4;
-    }
-    auto       k2 = (minb2 == 3) ? k_spmv_sd2<Epi, LMAX, 3> : (minb2 == 5 ? k_spmv_sd2<Epi, LMAX, 5> : k_spmv_sd2<Epi, LMAX, 4>);
+    auto       k2 = k_spmv_sd2<Epi, LMAX, 4>;
     static int occ2 = 0;
     if (!occ2) {
       int nb = 0;
@@ -1888,7 +1878,7 @@ static int launch_sd_l(const CsrDev &A, const double *x, const Epi &epi, TileOrd
     launch_k(k2, grid, NT, 0, A, x, epi, o2);
     return 0;
   }
-  auto kern = (minb == 4) ? k_spmv_sd<Epi, LMAX, 4> : (minb == 5 ? k_spmv_sd<Epi, LMAX, 5> : k_spmv_sd<Epi, LMAX, 6>);
+  auto kern = k_spmv_sd<Epi, LMAX, 5>;
   static int pf = -1;
   if (pf < 0) {
     // L2 prefetch distance in grid sweeps.  OFF by default: measured on C2 / C3 (profiles/README.md, r2k) the bulk prefetches make K_A
