@@ -2892,7 +2892,18 @@ int k_fused_B(const MpgpVecs &v, const CtrlFold &cf, RedBuf rb, const PushRanges
 {
   const bool vec2 = (v.n % 2 == 0) && aligned16(v.x) && aligned16(v.p) && aligned16(v.g) && aligned16(v.Ap) && aligned16(v.gf) && aligned16(v.bx.lb) && aligned16(v.bx.ub) &&
                     !getenv("PERMON_B200_NOVEC");
-  int        grid = elementwise_grid();
+  // one resident wave: K_B holds 64 registers per thread (4 CTAs / SM, 3 with equality rows), so the generic 8-per-SM grid would run as two
+  // waves -- the prologue (step selection), the block reduction and the ticket would be paid twice per SM slot
+  static int occ_b[2] = {0, 0};
+  const int  eqi = v.m > 0 ? 1 : 0;
+  if (!occ_b[eqi]) {
+    int nb = 0;
+    cudaError_t e = (eqi ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_update_B<true, true, false>, NT, 0)
+                         : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_update_B<false, true, false>, NT, 0));
+    occ_b[eqi] = (e == cudaSuccess && nb >= 1) ? nb : 4;
+    if (getenv("PERMON_B200_KB_TWO_WAVES")) occ_b[eqi] = 8;   // A/B: the former grid
+  }
+  int        grid = g_ctx.sm_count * occ_b[eqi];
   int        need = ((vec2 ? v.n / 2 : v.n) + NT - 1) / NT;
   if (need < 1) need = 1;
   if (grid > need) grid = need;
