@@ -56,7 +56,8 @@ struct _p_Vec : PObj {
   double  *d = nullptr;
   bool     d_owned = false;
   bool     h_valid = false, d_valid = false;
-  bool     invalidated = false;
+  bool     invalidated = false;   // VecInvalidate (permonvecutils.c:266-284); read it through pb::vec_invalid(), set it through pb::vec_mark_invalid()
+  int64_t  inval_state = 0;       // object state at the time of the invalidation: a later write makes the vector valid again (:303-326)
   int64_t  state = 0;
   cudaEvent_t up_ev = nullptr;   // a prefetch (H2D on the copy stream) is in flight: settled by the next access
   bool        h2d_inflight = false;   // an asynchronous upload FROM the host buffer was enqueued on the compute stream: a host writer must wait for it
@@ -297,6 +298,17 @@ struct Reducer {
 };
 Reducer &reducer(MPI_Comm comm);           // shared scratch reducer of the communicator
 
+// VecIsInvalidated semantics of the reference: invalid until the vector is written again (its state counter moves past the recorded one)
+inline bool vec_invalid(Vec v)
+{
+  if (v->invalidated && v->state > v->inval_state) v->invalidated = false;
+  return v->invalidated;
+}
+inline void vec_mark_invalid(Vec v, bool invalid)
+{
+  v->invalidated = invalid;
+  v->inval_state = v->state;
+}
 int  vec_prefetch(Vec v);                                    // start the H2D copy of a host-valid vector on the copy stream (pinned buffers: truly asynchronous)
 // dense equality rows B (m x n, row-major on the device), any m <= PB_MAXEQ_ALL: t = B x (host values, summed over ranks) and
 // y (+)= scale * B^T t, in chunks of PB_NRED rows per launch

@@ -1015,10 +1015,10 @@ static int lagrangian_gradient(QP qp, Vec x, Vec r, bool with_box, bool with_eq,
     }
   }
   if (with_eq && qp->BE) {
-    if (qp->Bt_lambda && !qp->Bt_lambda->invalidated) {
+    if (qp->Bt_lambda && !pb::vec_invalid(qp->Bt_lambda)) {
       PB_CHK(VecAXPY(r, 1.0, qp->Bt_lambda));
       *name += " + (B'*lambda)";
-    } else if (qp->lambda_E && !qp->lambda_E->invalidated && qp->pf) {
+    } else if (qp->lambda_E && !pb::vec_invalid(qp->lambda_E) && qp->pf) {
       Vec t;
       PB_CHK(VecDuplicate(r, &t));
       double lam[PB_MAXEQ_ALL];
@@ -1055,7 +1055,7 @@ PetscErrorCode QPComputeMissingBoxMultipliers(QP qp)
   PB_CHK(QPSetUp(qp));
   QPC qpc = qp->qpc;
   if (!qpc || (!qpc->lb && !qpc->ub)) return 0;
-  bool flg = qpc->lb && qpc->llb->invalidated, flg2 = qpc->ub && qpc->lub->invalidated;
+  bool flg = qpc->lb && pb::vec_invalid(qpc->llb), flg2 = qpc->ub && pb::vec_invalid(qpc->lub);
   if (!flg && !flg2) return 0;
   bool        avail;
   std::string name;
@@ -1089,8 +1089,8 @@ PetscErrorCode QPComputeMissingEqMultiplier(QP qp)
 {
   PB_CHK(QPSetUp(qp));
   if (!qp->BE) return 0;
-  if (!qp->lambda_E->invalidated) return 0;
-  if (qp->Bt_lambda && !qp->Bt_lambda->invalidated) return 0;
+  if (!pb::vec_invalid(qp->lambda_E)) return 0;
+  if (qp->Bt_lambda && !pb::vec_invalid(qp->Bt_lambda)) return 0;
   bool        avail;
   std::string name;
   Vec         r = qp->xwork;
@@ -1216,8 +1216,8 @@ static PetscErrorCode post_projector(QP child, QP parent)
   PB_CHK(post_default(child, parent));
   bool skip_lambda_E = true, skip_Bt_lambda = true;
   if (child->BE) {   // -qpt_project_inherit_eq_multipliers defaults to true
-    skip_lambda_E  = !child->lambda_E || child->lambda_E->invalidated;
-    skip_Bt_lambda = !child->Bt_lambda || child->Bt_lambda->invalidated;
+    skip_lambda_E  = !child->lambda_E || pb::vec_invalid(child->lambda_E);
+    skip_Bt_lambda = !child->Bt_lambda || pb::vec_invalid(child->Bt_lambda);
   }
   if (skip_lambda_E && skip_Bt_lambda) return 0;
   Vec r = parent->xwork;

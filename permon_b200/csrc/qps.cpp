@@ -1649,7 +1649,7 @@ PetscErrorCode SmalxeImpl::solve(QPS qps)
     PB_CHK(QPPFApplyHalfQ(qp->pf, qp->Bt_lambda, qp->lambda_E));
     qp->lambda_E->invalidated = false;
   }
-  qp->Bt_lambda->invalidated = !get_Bt_lambda;   // :995
+  pb::vec_mark_invalid(qp->Bt_lambda, !get_Bt_lambda);   // :995
   return 0;
 }
 

@@ -881,7 +881,7 @@ PetscErrorCode VecCopy(Vec x, Vec y)
   double       *dy;
   PB_CHK(vec_dev_read(x, &dx));
   PB_CHK(vec_dev_write(y, &dy));
-  y->invalidated = x->invalidated;
+  pb::vec_mark_invalid(y, pb::vec_invalid(x));
   return k_copy(x->n, dx, dy);
 }
 PetscErrorCode VecScale(Vec x, PetscScalar alpha)
@@ -945,14 +945,16 @@ PetscErrorCode VecNorm(Vec x, NormType type, PetscReal *val)
   return vec_norm2(x, val);
 }
 // VecInvalidate / VecIsInvalidated: src/vec/interface/permonvecutils.c:266,303 ("this multiplier is not computed")
+// The reference also fills an invalidated vector with +inf (VecFlag, what src/tests/ex4.c prints); here only the flag is kept -- nothing on the
+// path reads an invalidated vector -- together with the rule that any later write (VecSet, VecCopy into it, VecGetArray ...) validates it again.
 PetscErrorCode VecInvalidate(Vec vec)
 {
-  vec->invalidated = true;
+  pb::vec_mark_invalid(vec, true);
   return 0;
 }
 PetscErrorCode VecIsInvalidated(Vec vec, PetscBool *flg)
 {
-  *flg = vec->invalidated ? PETSC_TRUE : PETSC_FALSE;
+  *flg = pb::vec_invalid(vec) ? PETSC_TRUE : PETSC_FALSE;
   return 0;
 }
 

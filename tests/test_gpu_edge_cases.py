@@ -245,3 +245,25 @@ def test_bound_chop_tol(P):
     assert abs(r.its - ro["its"]) <= max(2, 0.02 * ro["its"])
     assert np.linalg.norm(r.x - xr) <= 1e-7 * np.linalg.norm(xr)
     assert np.all(r.x >= lbf - 1e-12)
+
+
+def test_vec_invalidate_like_reference_tests_ex4(P):
+    """src/tests/ex4.c: a vector is valid, VecInvalidate makes it invalid, any later write (VecSet here, VecCopy / VecGetArray as well)
+    makes it valid again (permonvecutils.c:266-326: the invalid mark remembers the object state)"""
+    import ctypes as C
+    v = P.VecCreate(4)
+    P.call("VecSet", v, C.c_double(1.0))
+    assert not P.VecIsInvalidated(v)
+    P.call("VecInvalidate", v)
+    assert P.VecIsInvalidated(v)
+    P.call("VecSet", v, C.c_double(1.0))
+    assert not P.VecIsInvalidated(v)
+    P.call("VecInvalidate", v)
+    w = P.VecFromArray(np.arange(4.0))
+    P.call("VecCopy", w, v)                      # a copy INTO the vector validates it
+    assert not P.VecIsInvalidated(v)
+    assert np.array_equal(P.VecGetArray(v), np.arange(4.0))
+    P.call("VecInvalidate", w)
+    P.call("VecCopy", w, v)                      # ... unless the source itself is invalid
+    assert P.VecIsInvalidated(v)
+    P.VecDestroy(v), P.VecDestroy(w)
