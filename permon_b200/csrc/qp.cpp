@@ -654,8 +654,10 @@ PetscErrorCode QPPFGetGGt(QPPF cp, Mat *GGt)
     T->comm = cp->comm;
     T->kind = MK_DENSEROWS;
     T->m = T->n = T->M = T->N = m;
-    PB_CUDA(cudaMalloc(&T->rows_d, sizeof(double) * std::max<size_t>((size_t)m * m, 1)));
-    PB_CUDA(cudaMemcpy(T->rows_d, cp->GGt.data(), sizeof(double) * (size_t)m * m, cudaMemcpyHostToDevice));
+    // rows_d of a dense-rows Mat comes from the pool (its destructor returns it there): stream-ordered allocation and copy
+    PB_CHK(pb::dmalloc(&T->rows_d, std::max<size_t>((size_t)m * m, 1)));
+    PB_CUDA(cudaMemcpyAsync(T->rows_d, cp->GGt.data(), sizeof(double) * (size_t)m * m, cudaMemcpyHostToDevice, pb::ctx().stream));
+    PB_CUDA(cudaStreamSynchronize(pb::ctx().stream));
     cp->GGt_mat = T;
   }
   *GGt = cp->GGt_mat;

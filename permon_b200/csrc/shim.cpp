@@ -1865,8 +1865,9 @@ int mat_eqrows_dense(Mat A, double **Bd)
     if (t.c >= A->cstart && t.c < A->cstart + A->n) dense[(size_t)t.r * nl + (size_t)(t.c - A->cstart)] += t.v;   // layout change only
   }
   PB_CHK(dev_init());
-  PB_CHK(dmalloc(&A->rows_d, dense.size()));
-  PB_CUDA(cudaMemcpy(A->rows_d, dense.data(), sizeof(double) * dense.size(), cudaMemcpyHostToDevice));
+  PB_CHK(dmalloc(&A->rows_d, dense.size()));   // stream-ordered allocation: the copy goes on the same stream, and `dense` is a local
+  PB_CUDA(cudaMemcpyAsync(A->rows_d, dense.data(), sizeof(double) * dense.size(), cudaMemcpyHostToDevice, ctx().stream));
+  PB_CUDA(cudaStreamSynchronize(ctx().stream));
   *Bd = A->rows_d;
   return 0;
 }
